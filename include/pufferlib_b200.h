@@ -1,0 +1,190 @@
+/* pufferlib_b200.h -- C ABI of libpuffer_b200.so: the B200 (sm_100a) env-step + PPO-rollout hot path.
+ *
+ * This is the drop-in boundary for PufferLib's vectorised env step / rollout / GAE / minibatch path.
+ * Every entry point below names the reference interface it replaces (paths under /root/reference).
+ * The reference has no C ABI of its own on this path: its native seams are the `PufferEnv` buffer-injection
+ * protocol (pufferlib/environment.py:1-21 + vector.py:97-110) and two Cython functions
+ * (c_gae.pyx:11 `compute_gae`, pufferlib/extensions.pyx:19,32 `emulate`/`nativize`); the rest is Python
+ * (vector.py Serial/Multiprocessing send/recv, clean_pufferl.py Experience.store/sort_training_data/flatten_batch).
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, POD structs.  No torch / C++ types cross this boundary.
+ *   - Unless a parameter is suffixed `_host`, every data pointer is a DEVICE pointer owned by the caller
+ *     (e.g. `tensor.data_ptr()`); the library owns only the opaque `pb_env` handle and its internal state.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  All work is enqueued
+ *     asynchronously on it; nothing here synchronises the device unless documented.
+ *   - Every function returns 0 on success or a negative `PB_ERR_*`; `pb_last_error()` gives the message of the
+ *     calling thread's last failure.  No exceptions, no CPU fallback: without a CUDA device calls fail with
+ *     PB_ERR_CUDA.
+ *   - One host thread per GPU drives a handle; the library creates no threads and is re-entrant per handle.
+ *
+ * Rollout layout ("arrival order", identical to the reference's Experience tensors when every mask is True and
+ * agent_ids == arange(N), clean_pufferl.py:390-397,436-450): row index = t*N + e for step t, env e.
+ * "Sorted order" (what Experience.sort_training_data produces, clean_pufferl.py:452-464) is f = e*H + t; on the
+ * device that permutation is arithmetic, no index tensor exists.
+ */
+#ifndef PUFFERLIB_B200_H
+#define PUFFERLIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_ABI_VERSION 1
+
+enum {
+    PB_OK = 0,
+    PB_ERR_INVALID = -1,   /* bad argument (maps to APIUsageError / ValueError on the Python side) */
+    PB_ERR_CUDA = -2,      /* CUDA runtime failure or no device (RuntimeError) */
+    PB_ERR_STATE = -3,     /* call order violated, e.g. step before reset (APIUsageError, emulation.py:198-201) */
+    PB_ERR_UNSUPPORTED = -4
+};
+
+enum { PB_ENV_SQUARED = 0, PB_ENV_BREAKOUT = 1, PB_ENV_SNAKE = 2, PB_ENV_PONG = 3 };
+enum { PB_DTYPE_F32 = 0, PB_DTYPE_U8 = 1 };
+
+typedef struct pb_env pb_env; /* opaque: N env instances resident on one GPU */
+
+typedef struct {
+    int32_t kind;             /* PB_ENV_* */
+    int32_t num_envs;         /* N: env instances (== agents) on this GPU */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t reserved;
+    int64_t env_index_offset; /* global index of local env 0 (multi-GPU shards seed by GLOBAL index) */
+    int32_t iparam[8];        /* kind-specific, 0 = default:
+                                 SQUARED : [0]=distance_to_target (default 3; ocean/environment.py:28)
+                                 BREAKOUT: [0]=max_ticks (default 4096)
+                                 SNAKE   : [0]=max_ticks (default 1024)
+                                 PONG    : [0]=max_score (default 5) [1]=max_ticks (default 4096) */
+} pb_env_config;
+
+typedef struct {
+    int32_t obs_dtype;    /* PB_DTYPE_* */
+    int32_t obs_ndim;
+    int32_t obs_shape[4];
+    int64_t obs_bytes;    /* bytes of one agent's observation (O) */
+    int32_t num_actions;  /* Discrete(n) */
+    int32_t num_envs;
+    float obs_low, obs_high; /* Box bounds */
+} pb_env_info;
+
+/* Where one reset/step call writes its results.  With a time-major rollout tensor the caller passes
+ * obs = rollout_obs + t*N*O, obs_stride = O, rewards = rollout_rewards + t*N, dones_f32 = rollout_dones + t*N:
+ * the env kernel then stores straight into rollout row t (replaces buf.observations[row][:] = ob,
+ * emulation.py:158-164, plus the obs/reward/done part of Experience.store, clean_pufferl.py:442-447). */
+typedef struct {
+    void* obs;            /* env e writes obs_bytes at (char*)obs + e*obs_stride */
+    int64_t obs_stride;   /* bytes between consecutive envs' rows (>= obs_bytes) */
+    float* rewards;       /* [N] fp32                          (buf.rewards,     emulation.py:219-221) */
+    uint8_t* terminals;   /* [N] bool as one byte               (buf.terminals)   */
+    uint8_t* truncations; /* [N] bool, always 0 for these envs  (buf.truncations) */
+    uint8_t* masks;       /* [N] bool, always 1                 (buf.masks)       */
+    float* dones_f32;     /* optional [N]: terminal as 0.f/1.f  (Experience.dones, clean_pufferl.py:395,447); may be NULL */
+} pb_env_out;
+
+const char* pb_last_error(void);
+int pb_abi_version(void);
+int pb_device_count(int* out_count);
+
+/* -- environments ---------------------------------------------------------------------------------------------
+ * Replaces: the backend constructor instantiating N envs (vector.py:79), Serial.async_reset (vector.py:112-135),
+ * Serial.send's per-env `if env.done: reset() else: step()` loop (vector.py:137-156), the GymnasiumPufferEnv
+ * buffer writes (emulation.py:169-228) and EpisodeStats (postprocess.py:8-54), for the device-native env kinds. */
+int pb_env_create(const pb_env_config* cfg, pb_env** out);
+int pb_env_destroy(pb_env* env);
+int pb_env_get_info(const pb_env* env, pb_env_info* out);
+
+/* vector.py:112-135: (re)seed env i with seed + env_index_offset + i (make_seeds, vector.py:639-641), reset it and
+ * write the reset rows (r=0, terminal=False, truncation=False, mask=True; emulation.py:187-192). */
+int pb_env_reset(pb_env* env, uint64_t seed, const pb_env_out* out, void* stream);
+
+/* vector.py:137-156: envs whose previous row was terminal reset (action ignored, reset row written), all others
+ * step with actions[e] (int64, Discrete).  PB_ERR_STATE before the first reset.  `actions` is validated on the
+ * device only by clamping into [0, num_actions) -- the host layer does the reference's first-send
+ * action_space.contains check (vector.py:36-39). */
+int pb_env_step(pb_env* env, const int64_t* actions, const pb_env_out* out, void* stream);
+
+/* Episode statistics (EpisodeStats, postprocess.py:22-54).
+ * pb_env_episode_rows: per-env values of the episode that ENDED on the most recent step -- valid where that
+ * step's terminals[e] != 0: episode_return (fp64 sum), episode_length, score.  Pointers are device arrays [N]
+ * owned by the handle (read-only for the caller, overwritten by the next step).
+ * pb_env_stats_read: {episodes finished, sum episode_return, sum episode_length, sum score} accumulated on the
+ * device since the last read with clear != 0; copies 4 doubles to host memory and synchronises `stream`. */
+int pb_env_episode_rows(pb_env* env, const double** episode_return, const int32_t** episode_length,
+                        const float** score);
+int pb_env_stats_read(pb_env* env, double* out4_host, int clear, void* stream);
+
+/* -- rollout ---------------------------------------------------------------------------------------------------
+ * Replaces the policy-output part of Experience.store (clean_pufferl.py:443-446): one fused copy of value /
+ * logprob / action [N] into row t of the time-major rollout tensors (pass row pointers base + t*N). */
+int pb_rollout_store(const float* value, const float* logprob, const int64_t* action, float* values_row,
+                     float* logprobs_row, int64_t* actions_row, int64_t n, void* stream);
+
+/* Copy N obs rows between strided row sets (carry-over of the boundary observation into row 0 of the next
+ * rollout; the masked gather `obs[ptr:end] = obs[indices]` of clean_pufferl.py:442 with an all-True mask). */
+int pb_copy_rows(const void* src, int64_t src_stride, void* dst, int64_t dst_stride, int64_t row_bytes,
+                 int64_t n_rows, void* stream);
+
+/* -- GAE -------------------------------------------------------------------------------------------------------
+ * Replaces sort_training_data + the three numpy gathers + c_gae.compute_gae (clean_pufferl.py:163-169,
+ * c_gae.pyx:11-32): ONE backward chain over the whole sorted batch f = e*H + t, crossing env boundaries exactly
+ * as the reference does, A[B-1] = 0.  Inputs are the arrival-order (time-major [H][N]) rollout tensors; the
+ * kernel reads them transposed.  Outputs are in sorted order: advantages[f] (== advantages_np) and, if non-NULL,
+ * returns_sorted[f] = advantages[f] + values[t*N+e].  num_envs = 1 gives the reference's flat signature.
+ * fp32; element arithmetic keeps c_gae.pyx's association, only the scan tree reorders it (<= 1e-5 relative).
+ * `workspace`: pb_gae_workspace_bytes(...) bytes, zero-filled once by the caller; left zeroed by every call. */
+size_t pb_gae_workspace_bytes(int64_t num_envs, int64_t horizon);
+int pb_gae(const float* rewards, const float* values, const float* dones, float* advantages,
+           float* returns_sorted, int64_t num_envs, int64_t horizon, float gamma, float gae_lambda,
+           void* workspace, size_t workspace_bytes, void* stream);
+
+/* -- minibatch construction --------------------------------------------------------------------------------------
+ * Replaces Experience.flatten_batch (clean_pufferl.py:466-482) for the scalar tensors.  Segment k (bptt
+ * consecutive sorted rows) goes to minibatch k % n_mb, row k / n_mb (clean_pufferl.py:455-460,473-475).
+ * Outputs are dense [n_mb][rows][bptt].  returns_np (optional) reproduces clean_pufferl.py:476 literally:
+ * returns_np[i] = advantages_sorted[i] + values_arrival[i].  Any output pointer may be NULL. */
+int pb_flatten_batch(const int64_t* actions, const float* logprobs, const float* dones, const float* values,
+                     const float* advantages_sorted, int64_t* b_actions, float* b_logprobs, float* b_dones,
+                     float* b_values, float* b_advantages, float* b_returns, float* returns_np,
+                     int64_t num_envs, int64_t horizon, int64_t n_mb, int64_t rows, int64_t bptt, void* stream);
+
+/* Replaces `b_obs = obs[b_idxs_obs]` (clean_pufferl.py:477) for minibatches [mb_begin, mb_begin+mb_count):
+ * dst is dense [mb_count][rows][bptt][row_bytes]; src is the arrival-order obs tensor [H][N][row_bytes].
+ * Rows >= 4 KiB and 16-byte aligned go through TMA bulk copies (global->shared->global). */
+int pb_minibatch_gather(const void* obs, void* dst, int64_t row_bytes, int64_t num_envs, int64_t horizon,
+                        int64_t n_mb, int64_t rows, int64_t bptt, int64_t mb_begin, int64_t mb_count,
+                        void* stream);
+
+/* Replaces the per-minibatch advantage normalisation of train (clean_pufferl.py:211-213), for n_mb minibatches
+ * at once: out[m] = (adv[m] - mean_m) / (std_m + 1e-8), std unbiased (N-1).  in/out are [n_mb][mb_size] and may
+ * alias.  `workspace`: pb_adv_norm_workspace_bytes(...) bytes (no initialisation required). */
+size_t pb_adv_norm_workspace_bytes(int64_t n_mb, int64_t mb_size);
+int pb_adv_norm(const float* adv, float* out, int64_t n_mb, int64_t mb_size, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* -- image observation pack --------------------------------------------------------------------------------------
+ * Replaces the frame-stack materialisation inside `self.obs[:] = ob` for (S, 84, 84) uint8 observations
+ * (emulation.py:161-162 on a LazyFrames of S frames; atari/environment.py:37-39): for each env,
+ * obs_out[e][0..S-2] = prev_obs[e][1..S-1], obs_out[e][S-1] = new_frames[e]; where reset_mask[e] != 0 all S slots
+ * are filled with new_frames[e] (gymnasium FrameStack.reset).  frame_bytes % 16 == 0; staged through shared
+ * memory with TMA bulk copies (cp.async.bulk).  Strides are bytes between consecutive envs. */
+int pb_image_pack(const void* new_frames, int64_t frame_stride, const void* prev_obs, int64_t prev_stride,
+                  void* obs_out, int64_t out_stride, const uint8_t* reset_mask, int64_t num_envs,
+                  int64_t frame_bytes, int32_t stack, void* stream);
+
+/* -- fused sampling epilogue ----------------------------------------------------------------------
+ * Replaces sample_logits (pufferlib/frameworks/cleanrl.py:25-47) for one Discrete head when sampling:
+ * normalised = logits - logsumexp; action ~ Categorical(softmax) drawn with a counter-based RNG
+ * (seed, offset, row); logprob = normalised[action]; entropy = -sum p*log p.  Optionally also writes
+ * action/logprob/value into rollout row pointers (the pb_rollout_store copy, fused).  logits [n][n_act] fp32. */
+int pb_sample_logits(const float* logits, int64_t n, int32_t n_act, uint64_t seed, uint64_t offset,
+                     int64_t* actions, float* logprobs, float* entropies, const float* value,
+                     float* values_row, float* logprobs_row, int64_t* actions_row, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PUFFERLIB_B200_H */

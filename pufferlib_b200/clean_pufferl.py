@@ -1,0 +1,461 @@
+"""``clean_pufferl`` create / evaluate / train / close with the reference signatures, device-resident.
+
+Mirrors /root/reference/clean_pufferl.py: ``create`` (:30-73), ``evaluate`` (:75-154), ``train`` (:156-292),
+``close`` (:294-304), ``Experience`` (:380-482), ``make_losses`` (:369-378), ``seed_everything``.  What changes:
+
+* ``Experience`` tensors all live in HBM in arrival order (row t*N + e) -- the same memory layout the reference
+  gives them -- and the env-step kernel writes obs / reward / done rows into them directly
+  (``vecenv.bind_rollout``).  ``store`` is one fused kernel for value / logprob / action (pb_rollout_store).
+* ``sort_training_data`` is arithmetic (sorted position e*H+t <-> arrival row t*N+e): no Python sort, no index
+  tensor.  GAE is one launch (pb_gae) reading the arrival-order tensors transposed; ``flatten_batch`` is one
+  launch for the scalars (pb_flatten_batch) + one gather for the observations (pb_minibatch_gather); the
+  per-minibatch advantage normalisation of train (:211-213) is done for all minibatches at once (pb_adv_norm).
+* No per-step device<->host traffic in evaluate; losses are accumulated on the device and read once per train.
+* Multi-GPU: if torch.distributed is initialised, gradients are summed with ONE all-reduce over a flat bucket
+  per optimizer step (NCCL over NVLink) -- the reference has no distributed path.
+
+The policy stays a torch ``nn.Module`` with the reference's call convention
+(``policy(obs) -> actions, logprob, entropy, value``; ``policy(obs, action=a)`` in train).
+"""
+import ctypes as C
+import os
+import random
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+import pufferlib_b200
+from pufferlib_b200 import _native
+from pufferlib_b200.exceptions import APIUsageError
+
+torch.set_float32_matmul_precision('high')   # clean_pufferl.py:22
+
+numpy_to_torch_dtype_dict = {
+    np.dtype('float64'): torch.float64, np.dtype('float32'): torch.float32, np.dtype('float16'): torch.float16,
+    np.dtype('uint8'): torch.uint8, np.dtype('int8'): torch.int8, np.dtype('int16'): torch.int16,
+    np.dtype('int32'): torch.int32, np.dtype('int64'): torch.int64, np.dtype('bool'): torch.bool,
+}
+
+
+def seed_everything(seed, torch_deterministic):
+    random.seed(seed)
+    np.random.seed(seed)
+    if seed is not None:
+        torch.manual_seed(seed)
+    torch.backends.cudnn.deterministic = torch_deterministic
+
+
+def make_losses():
+    return pufferlib_b200.namespace(policy_loss=0, value_loss=0, entropy=0, old_approx_kl=0, approx_kl=0,
+                                    clipfrac=0, explained_variance=0)
+
+
+class Profile:
+    """Wall-clock buckets with the reference's names (clean_pufferl.py:306-367); device work is asynchronous, so
+    a bucket is only exact where the caller synchronises (end of evaluate / end of train)."""
+    BUCKETS = ('env', 'eval_forward', 'eval_misc', 'train_forward', 'learn', 'train_misc')
+
+    class _Timer:
+        def __init__(self):
+            self.elapsed = 0.0
+            self._t0 = 0.0
+
+        def __enter__(self):
+            self._t0 = time.perf_counter()
+            return self
+
+        def __exit__(self, *a):
+            self.elapsed += time.perf_counter() - self._t0
+
+    def __init__(self):
+        for b in self.BUCKETS:
+            setattr(self, b, Profile._Timer())
+        self.start = time.time()
+        self.SPS = 0
+        self.uptime = 0
+        self._last_step = 0
+        self._last_time = time.time()
+
+    def __iter__(self):
+        yield 'SPS', self.SPS
+        yield 'uptime', self.uptime
+        for b in self.BUCKETS:
+            yield b + '_time', getattr(self, b).elapsed
+
+    def update(self, data, interval_s=1):
+        now = time.time()
+        if now - self._last_time < interval_s:
+            return False
+        self.SPS = (data.global_step - self._last_step) / (now - self._last_time)
+        self._last_step, self._last_time = data.global_step, now
+        self.uptime = now - self.start
+        return True
+
+
+class Experience:
+    """Flat tensor storage in arrival order, on the device (reference: clean_pufferl.py:380-482)."""
+
+    def __init__(self, batch_size, bptt_horizon, minibatch_size, obs_shape, obs_dtype, atn_shape,
+                 cpu_offload=False, device='cuda', lstm=None, lstm_total_agents=0):
+        if minibatch_size is None:
+            minibatch_size = batch_size
+        if cpu_offload:
+            raise NotImplementedError('cpu_offload: the B200 rollout is device-resident by design')
+        if lstm is not None:
+            raise NotImplementedError('LSTM policies are not on the device path yet (SURVEY §8f-4)')
+        if len(tuple(atn_shape)) != 0:
+            raise NotImplementedError('only Discrete action spaces are on the device path')
+        obs_dtype = numpy_to_torch_dtype_dict[np.dtype(obs_dtype)]
+        dev = torch.device(device)
+        if dev.type != 'cuda':
+            raise RuntimeError('pufferlib_b200.Experience needs a CUDA device (no CPU fallback)')
+        self.device = dev
+        z = dict(device=dev)
+        self.obs = torch.zeros(batch_size, *obs_shape, dtype=obs_dtype, **z)
+        self.actions = torch.zeros(batch_size, dtype=torch.int64, **z)
+        self.logprobs = torch.zeros(batch_size, **z)
+        self.rewards = torch.zeros(batch_size, **z)
+        self.dones = torch.zeros(batch_size, **z)
+        self.truncateds = torch.zeros(batch_size, **z)   # never written, as in the reference
+        self.values = torch.zeros(batch_size, **z)
+        self.lstm_h = self.lstm_c = None
+
+        num_minibatches = batch_size / minibatch_size
+        self.num_minibatches = int(num_minibatches)
+        if self.num_minibatches != num_minibatches:
+            raise ValueError('batch_size must be divisible by minibatch_size')
+        minibatch_rows = minibatch_size / bptt_horizon
+        self.minibatch_rows = int(minibatch_rows)
+        if self.minibatch_rows != minibatch_rows:
+            raise ValueError('minibatch_size must be divisible by bptt_horizon')
+
+        self.batch_size = batch_size
+        self.bptt_horizon = bptt_horizon
+        self.minibatch_size = minibatch_size
+        self.obs_shape = tuple(obs_shape)
+        self.obs_row_bytes = int(np.prod(obs_shape, dtype=np.int64)) * self.obs.element_size()
+        self.ptr = 0
+        self.step = 0
+        self.num_envs = None      # agents per step, fixed by the first store()
+        # train-side tensors, allocated once and reused every epoch
+        nm, mb = self.num_minibatches, self.minibatch_size
+        self.advantages = torch.zeros(batch_size, **z)        # sorted order (== advantages_np)
+        self.returns_sorted = torch.zeros(batch_size, **z)
+        self.returns = torch.zeros(batch_size, **z)           # returns_np of clean_pufferl.py:476
+        shape3 = (nm, self.minibatch_rows, bptt_horizon)
+        self.b_obs = torch.zeros(nm, self.minibatch_rows, bptt_horizon, *obs_shape, dtype=obs_dtype, **z)
+        self.b_actions = torch.zeros(shape3, dtype=torch.int64, **z)
+        self.b_logprobs = torch.zeros(shape3, **z)
+        self.b_dones = torch.zeros(shape3, **z)
+        self.b_values = torch.zeros(nm, mb, **z)
+        self.b_advantages = torch.zeros(nm, mb, **z)
+        self.b_returns = torch.zeros(nm, mb, **z)
+        self.b_advantages_normalized = torch.zeros(nm, mb, **z)
+        lib = _native.lib()
+        self._advnorm_ws = torch.zeros(max(16, lib.pb_adv_norm_workspace_bytes(nm, mb)), dtype=torch.uint8, **z)
+        self._gae_ws = None
+
+    @property
+    def full(self):
+        return self.ptr >= self.batch_size
+
+    # numpy views of the reference become explicit device->host copies here
+    @property
+    def values_np(self):
+        return self.values.cpu().numpy()
+
+    @property
+    def returns_np(self):
+        return self.returns.cpu().numpy()
+
+    @property
+    def rewards_np(self):
+        return self.rewards.cpu().numpy()
+
+    @property
+    def dones_np(self):
+        return self.dones.cpu().numpy()
+
+    @property
+    def actions_np(self):
+        return self.actions.cpu().numpy()
+
+    @property
+    def logprobs_np(self):
+        return self.logprobs.cpu().numpy()
+
+    def store(self, obs, value, action, logprob, reward, done, env_id, mask):
+        """clean_pufferl.py:436-450 for an all-True mask with env_id == arange(N) (what the B200 backend
+        produces): rows ptr:ptr+N.  Tensors already living in their rollout row (bound vecenv) are not copied."""
+        n = value.shape[0]
+        if self.num_envs is None:
+            if self.batch_size % n != 0:
+                raise APIUsageError('batch_size must be a multiple of the agents per step')
+            self.num_envs = n
+        if n != self.num_envs:
+            raise APIUsageError('store(): the number of agents per step changed')
+        ptr, end = self.ptr, self.ptr + n
+        if end > self.batch_size:
+            raise APIUsageError('store(): rollout buffer is full')
+        lib, s = _native.lib(), _native.stream_ptr()
+        obs_row = self.obs.data_ptr() + ptr * self.obs_row_bytes
+        if obs.data_ptr() != obs_row:
+            obs = obs.to(self.device)
+            _native.check(lib.pb_copy_rows(_native.ptr(obs.contiguous()), self.obs_row_bytes, C.c_void_p(obs_row),
+                                           self.obs_row_bytes, self.obs_row_bytes, n, s))
+        if reward.data_ptr() != self.rewards.data_ptr() + ptr * 4:
+            self.rewards[ptr:end] = torch.as_tensor(reward).to(self.device, torch.float32)
+            self.dones[ptr:end] = torch.as_tensor(done).to(self.device, torch.float32)
+        value = value.reshape(-1).to(self.device, torch.float32).contiguous()
+        logprob = logprob.reshape(-1).to(self.device, torch.float32).contiguous()
+        action = torch.as_tensor(action).reshape(-1).to(self.device, torch.int64).contiguous()
+        _native.check(lib.pb_rollout_store(
+            _native.ptr(value), _native.ptr(logprob), _native.ptr(action),
+            C.c_void_p(self.values.data_ptr() + ptr * 4), C.c_void_p(self.logprobs.data_ptr() + ptr * 4),
+            C.c_void_p(self.actions.data_ptr() + ptr * 8), n, s))
+        self.ptr = end
+        self.step += 1
+
+    def sort_training_data(self):
+        """clean_pufferl.py:452-464.  The permutation is arithmetic on the device; the index array is only
+        materialised (on the host) for callers that ask for the reference's return value."""
+        n = self.num_envs
+        h = self.batch_size // n
+        self.horizon = h
+        self.ptr = 0
+        self.step = 0
+        return _LazyIdxs(n, h)
+
+    def compute_gae(self, gamma, gae_lambda):
+        """c_gae.compute_gae on the sorted batch (clean_pufferl.py:164-169) -> self.advantages (sorted order)."""
+        n, h = self.num_envs, self.horizon
+        lib = _native.lib()
+        need = lib.pb_gae_workspace_bytes(n, h)
+        if self._gae_ws is None or self._gae_ws.numel() < need:
+            self._gae_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        _native.check(lib.pb_gae(_native.ptr(self.rewards), _native.ptr(self.values), _native.ptr(self.dones),
+                                 _native.ptr(self.advantages), _native.ptr(self.returns_sorted), n, h,
+                                 C.c_float(gamma), C.c_float(gae_lambda), _native.ptr(self._gae_ws),
+                                 self._gae_ws.numel(), _native.stream_ptr()))
+        return self.advantages
+
+    def flatten_batch(self, advantages=None):
+        """clean_pufferl.py:466-482 (advantages: sorted-order device tensor, default self.advantages)."""
+        adv = self.advantages if advantages is None else advantages
+        n, h = self.num_envs, self.horizon
+        lib, s = _native.lib(), _native.stream_ptr()
+        _native.check(lib.pb_flatten_batch(
+            _native.ptr(self.actions), _native.ptr(self.logprobs), _native.ptr(self.dones), _native.ptr(self.values),
+            _native.ptr(adv), _native.ptr(self.b_actions), _native.ptr(self.b_logprobs), _native.ptr(self.b_dones),
+            _native.ptr(self.b_values), _native.ptr(self.b_advantages), _native.ptr(self.b_returns),
+            _native.ptr(self.returns), n, h, self.num_minibatches, self.minibatch_rows, self.bptt_horizon, s))
+        _native.check(lib.pb_minibatch_gather(
+            _native.ptr(self.obs), _native.ptr(self.b_obs), self.obs_row_bytes, n, h, self.num_minibatches,
+            self.minibatch_rows, self.bptt_horizon, 0, self.num_minibatches, s))
+
+    def normalize_advantages(self):
+        """clean_pufferl.py:211-213 for every minibatch at once -> self.b_advantages_normalized."""
+        _native.check(_native.lib().pb_adv_norm(
+            _native.ptr(self.b_advantages), _native.ptr(self.b_advantages_normalized), self.num_minibatches,
+            self.minibatch_size, _native.ptr(self._advnorm_ws), self._advnorm_ws.numel(), _native.stream_ptr()))
+        return self.b_advantages_normalized
+
+
+class _LazyIdxs:
+    """Return value of sort_training_data: the (env_id, step) argsort, computed only if someone looks."""
+
+    def __init__(self, n, h):
+        self.n, self.h = n, h
+
+    def __array__(self, dtype=None, copy=None):
+        e, t = np.divmod(np.arange(self.n * self.h), self.h)
+        idxs = t * self.n + e
+        return idxs if dtype is None else idxs.astype(dtype)
+
+    def __len__(self):
+        return self.n * self.h
+
+
+def create(config, vecenv, policy, optimizer=None, wandb=None):
+    seed_everything(config.seed, config.torch_deterministic)
+    profile = Profile()
+    losses = make_losses()
+    n_params = sum(p.numel() for p in policy.parameters() if p.requires_grad)
+    msg = f'Model Size: {n_params} parameters'
+
+    vecenv.async_reset(config.seed)
+    obs_shape = vecenv.single_observation_space.shape
+    obs_dtype = vecenv.single_observation_space.dtype
+    atn_shape = vecenv.single_action_space.shape
+    total_agents = vecenv.num_agents
+
+    lstm = policy.lstm if hasattr(policy, 'lstm') else None
+    experience = Experience(config.batch_size, config.bptt_horizon, config.minibatch_size, obs_shape, obs_dtype,
+                            atn_shape, config.cpu_offload, config.device, lstm, total_agents)
+    if hasattr(vecenv, 'bind_rollout') and not getattr(vecenv, 'host_buffers', False):
+        vecenv.bind_rollout(experience)     # env-step kernels write rollout rows directly
+
+    uncompiled_policy = policy
+    if getattr(config, 'compile', False):
+        raise NotImplementedError('torch.compile is not used on the B200 path (no Triton); set compile=False')
+
+    if optimizer is None:
+        optimizer = torch.optim.Adam(policy.parameters(), lr=config.learning_rate, eps=1e-5)
+
+    grad_bucket = None
+    if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size() > 1:
+        from pufferlib_b200.distributed import GradBucket
+        grad_bucket = GradBucket(policy)
+
+    return pufferlib_b200.namespace(
+        config=config, vecenv=vecenv, policy=policy, uncompiled_policy=uncompiled_policy, optimizer=optimizer,
+        experience=experience, profile=profile, losses=losses, wandb=wandb, global_step=0, epoch=0, stats={},
+        msg=msg, last_log_time=0, utilization=None, grad_bucket=grad_bucket,
+    )
+
+
+def evaluate(data):
+    config, profile, experience = data.config, data.profile, data.experience
+    policy = data.policy
+    infos = defaultdict(list)
+    vecenv = data.vecenv
+    on_device = not getattr(vecenv, 'host_buffers', False)
+
+    while not experience.full:
+        with profile.env:
+            o, r, d, t, info, env_id, mask = vecenv.recv()
+
+        with profile.eval_misc:
+            data.global_step += len(env_id) if on_device else int(sum(mask))
+            o = torch.as_tensor(o)
+            o_device = o.to(config.device, non_blocking=True)
+            r = torch.as_tensor(r)
+            d = torch.as_tensor(d)
+
+        with profile.eval_forward, torch.no_grad():
+            actions, logprob, _, value = policy(o_device)
+
+        with profile.eval_misc:
+            value = value.flatten()
+            if not on_device:
+                r, d = r.to(config.device, non_blocking=True), d.to(config.device, non_blocking=True)
+            experience.store(o_device, value, actions, logprob, r, d, env_id, mask)
+            for i in info:
+                for k, v in i.items():
+                    infos[k].append(v)
+
+        with profile.env:
+            vecenv.send(actions if on_device else actions.cpu().numpy())
+
+    with profile.eval_misc:
+        data.stats = {}
+        if hasattr(vecenv, 'episode_stats') and not getattr(vecenv, 'exact_infos', False):
+            means, count = vecenv.episode_stats(clear=True)    # device-side EpisodeStats reduction, one D2H
+            for k, v in means.items():
+                infos[k].append(v)
+        for k, v in infos.items():
+            try:
+                data.stats[k] = np.mean(v)
+            except Exception:
+                continue
+
+    return data.stats, infos
+
+
+def train(data):
+    config, profile, experience = data.config, data.profile, data.experience
+    data.losses = make_losses()
+    losses = data.losses
+    device = experience.device
+
+    with profile.train_misc:
+        experience.sort_training_data()
+        experience.compute_gae(config.gamma, config.gae_lambda)
+        experience.flatten_batch()
+        if config.norm_adv:
+            experience.normalize_advantages()
+
+    n_mb = experience.num_minibatches
+    acc = torch.zeros(6, device=device)       # policy, value, entropy, old_kl, kl, clipfrac
+    obs_shape = data.vecenv.single_observation_space.shape
+    for epoch in range(config.update_epochs):
+        for mb in range(n_mb):
+            with profile.train_misc:
+                obs = experience.b_obs[mb]
+                atn = experience.b_actions[mb]
+                log_probs = experience.b_logprobs[mb]
+                val = experience.b_values[mb]
+                adv = experience.b_advantages_normalized[mb] if config.norm_adv else experience.b_advantages[mb]
+                ret = experience.b_returns[mb]
+
+            with profile.train_forward:
+                _, newlogprob, entropy, newvalue = data.policy(obs.reshape(-1, *obs_shape), action=atn)
+
+            with profile.train_misc:
+                logratio = newlogprob - log_probs.reshape(-1)
+                ratio = logratio.exp()
+                with torch.no_grad():
+                    old_approx_kl = (-logratio).mean()
+                    approx_kl = ((ratio - 1) - logratio).mean()
+                    clipfrac = ((ratio - 1.0).abs() > config.clip_coef).float().mean()
+
+                adv = adv.reshape(-1)
+                pg_loss1 = -adv * ratio
+                pg_loss2 = -adv * torch.clamp(ratio, 1 - config.clip_coef, 1 + config.clip_coef)
+                pg_loss = torch.max(pg_loss1, pg_loss2).mean()
+
+                newvalue = newvalue.view(-1)
+                if config.clip_vloss:
+                    v_loss_unclipped = (newvalue - ret) ** 2
+                    v_clipped = val + torch.clamp(newvalue - val, -config.vf_clip_coef, config.vf_clip_coef)
+                    v_loss_clipped = (v_clipped - ret) ** 2
+                    v_loss = 0.5 * torch.max(v_loss_unclipped, v_loss_clipped).mean()
+                else:
+                    v_loss = 0.5 * ((newvalue - ret) ** 2).mean()
+
+                entropy_loss = entropy.mean()
+                loss = pg_loss - config.ent_coef * entropy_loss + v_loss * config.vf_coef
+
+            with profile.learn:
+                if data.grad_bucket is not None:
+                    data.grad_bucket.zero()                     # grads are views into one flat buffer
+                else:
+                    data.optimizer.zero_grad()
+                loss.backward()
+                if data.grad_bucket is not None:
+                    data.grad_bucket.all_reduce_mean()          # ONE NCCL all-reduce per optimizer step
+                torch.nn.utils.clip_grad_norm_(data.policy.parameters(), config.max_grad_norm)
+                data.optimizer.step()
+
+            with profile.train_misc, torch.no_grad():
+                acc += torch.stack([pg_loss.detach(), v_loss.detach(), entropy_loss.detach(), old_approx_kl,
+                                    approx_kl, clipfrac]) / n_mb
+
+        if config.target_kl is not None:
+            if approx_kl.item() > config.target_kl:
+                break
+
+    with profile.train_misc:
+        if config.anneal_lr:
+            frac = 1.0 - data.global_step / config.total_timesteps
+            data.optimizer.param_groups[0]['lr'] = frac * config.learning_rate
+
+        # explained variance on the device, same quantities as clean_pufferl.py:266-270
+        y_pred, y_true = experience.values, experience.returns
+        var_y = y_true.var(unbiased=False)
+        ev = 1 - (y_true - y_pred).var(unbiased=False) / var_y
+        host = torch.cat([acc, torch.stack([ev, var_y])]).cpu().numpy()    # the one D2H of train()
+        # the reference resets the accumulators every epoch of update_epochs? no: it divides by num_minibatches
+        # and keeps adding over epochs (clean_pufferl.py:249-254); same here.
+        losses.policy_loss, losses.value_loss, losses.entropy = float(host[0]), float(host[1]), float(host[2])
+        losses.old_approx_kl, losses.approx_kl, losses.clipfrac = float(host[3]), float(host[4]), float(host[5])
+        losses.explained_variance = float('nan') if host[7] == 0 else float(host[6])
+        data.epoch += 1
+        profile.update(data)
+
+
+def close(data):
+    data.vecenv.close()

@@ -1,0 +1,72 @@
+"""``pufferlib.frameworks.cleanrl`` equivalent: logits -> action / logprob / entropy, and the Policy wrapper.
+
+Reference: /root/reference/pufferlib/frameworks/cleanrl.py:25-47 (sample_logits), :50-66 (Policy).
+``sample_logits`` is the plain torch formulation (used in train, where actions are given);
+``Policy(fused_sample=True)`` routes the sampling case through the fused CUDA epilogue pb_sample_logits.
+"""
+import ctypes as C
+
+import torch
+
+from pufferlib_b200 import _native
+
+
+def log_prob(logits, value):
+    value = value.long().unsqueeze(-1)
+    value, log_pmf = torch.broadcast_tensors(value, logits)
+    value = value[..., :1]
+    return log_pmf.gather(-1, value).squeeze(-1)
+
+
+def entropy(logits):
+    min_real = torch.finfo(logits.dtype).min
+    logits = torch.clamp(logits, min=min_real)
+    p_log_p = logits * torch.softmax(logits, dim=-1)
+    return -p_log_p.sum(-1)
+
+
+def sample_logits(logits, action=None):
+    """Discrete head only (the configs of this path).  Returns (action, logprob, entropy)."""
+    normalized = logits - logits.logsumexp(dim=-1, keepdim=True)
+    if action is None:
+        action = torch.multinomial(torch.softmax(normalized, dim=-1), 1).squeeze(-1)
+    else:
+        action = action.reshape(-1)
+    return action, log_prob(normalized, action), entropy(normalized)
+
+
+class Policy(torch.nn.Module):
+    """Wrap a non-recurrent model: forward(x, action=None) -> (action, logprob, entropy, value)."""
+
+    def __init__(self, policy, fused_sample=False, seed=0):
+        super().__init__()
+        self.policy = policy
+        self.fused_sample = fused_sample
+        self._seed = int(seed)
+        self._offset = 0
+
+    def get_value(self, x, state=None):
+        _, value = self.policy(x)
+        return value
+
+    def get_action_and_value(self, x, action=None):
+        logits, value = self.policy(x)
+        if action is None and self.fused_sample and not torch.is_grad_enabled():
+            return (*self._sample_fused(logits), value)
+        action, logprob, ent = sample_logits(logits, action)
+        return action, logprob, ent, value
+
+    def _sample_fused(self, logits):
+        logits = logits.float().contiguous()
+        n, a = logits.shape
+        actions = torch.empty(n, dtype=torch.int64, device=logits.device)
+        logprob = torch.empty(n, dtype=torch.float32, device=logits.device)
+        ent = torch.empty(n, dtype=torch.float32, device=logits.device)
+        _native.check(_native.lib().pb_sample_logits(
+            _native.ptr(logits), n, a, C.c_uint64(self._seed), C.c_uint64(self._offset), _native.ptr(actions),
+            _native.ptr(logprob), _native.ptr(ent), None, None, None, None, _native.stream_ptr()))
+        self._offset += 1
+        return actions, logprob, ent
+
+    def forward(self, x, action=None):
+        return self.get_action_and_value(x, action)

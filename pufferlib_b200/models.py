@@ -1,0 +1,67 @@
+"""Policies for the configs in BASELINE.json: PyTorch modules, dense GEMMs on cuBLAS/cuDNN (tensor cores).
+
+Same architecture and call convention as the reference (adjacent to the hot path, not rewritten):
+  Default        /root/reference/pufferlib/models.py:12-62   Linear(prod(obs)->hidden)+ReLU; heads hidden->n_act, ->1
+  Convolutional  /root/reference/pufferlib/models.py:113-157 NatureCNN for (4,84,84) uint8 (atari/torch.py:8-18)
+  layer_init     /root/reference/pufferlib/pytorch.py:193-199
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
+    torch.nn.init.orthogonal_(layer.weight, std)
+    torch.nn.init.constant_(layer.bias, bias_const)
+    return layer
+
+
+class Default(nn.Module):
+    def __init__(self, env, hidden_size=128):
+        super().__init__()
+        self.encoder = nn.Linear(int(np.prod(env.single_observation_space.shape)), hidden_size)
+        self.decoder = layer_init(nn.Linear(hidden_size, env.single_action_space.n), std=0.01)
+        self.value_head = nn.Linear(hidden_size, 1)
+
+    def forward(self, observations):
+        hidden, lookup = self.encode_observations(observations)
+        return self.decode_actions(hidden, lookup)
+
+    def encode_observations(self, observations):
+        batch_size = observations.shape[0]
+        observations = observations.view(batch_size, -1)
+        return torch.relu(self.encoder(observations.float())), None
+
+    def decode_actions(self, hidden, lookup, concat=True):
+        return self.decoder(hidden), self.value_head(hidden)
+
+
+class Convolutional(nn.Module):
+    def __init__(self, env, *args, framestack=4, flat_size=64 * 7 * 7, input_size=512, hidden_size=512,
+                 output_size=512, channels_last=False, downsample=1, **kwargs):
+        super().__init__()
+        self.channels_last = channels_last
+        self.downsample = downsample
+        self.network = nn.Sequential(
+            layer_init(nn.Conv2d(framestack, 32, 8, stride=4)), nn.ReLU(),
+            layer_init(nn.Conv2d(32, 64, 4, stride=2)), nn.ReLU(),
+            layer_init(nn.Conv2d(64, 64, 3, stride=1)), nn.ReLU(),
+            nn.Flatten(),
+            layer_init(nn.Linear(flat_size, hidden_size)), nn.ReLU(),
+        )
+        self.actor = layer_init(nn.Linear(output_size, env.single_action_space.n), std=0.01)
+        self.value_fn = layer_init(nn.Linear(output_size, 1), std=1)
+
+    def forward(self, observations):
+        hidden, lookup = self.encode_observations(observations)
+        return self.decode_actions(hidden, lookup)
+
+    def encode_observations(self, observations):
+        if self.channels_last:
+            observations = observations.permute(0, 3, 1, 2)
+        if self.downsample > 1:
+            observations = observations[:, :, ::self.downsample, ::self.downsample]
+        return self.network(observations.float() / 255.0), None
+
+    def decode_actions(self, flat_hidden, lookup, concat=None):
+        return self.actor(flat_hidden), self.value_fn(flat_hidden)

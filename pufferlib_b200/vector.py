@@ -1,0 +1,410 @@
+"""``pufferlib.vector`` surface for device-resident envs: make / reset / step / send / recv.
+
+Mirrors /root/reference/pufferlib/vector.py: ``make`` (:577-637) with the same validation and error
+messages, module-level ``reset``/``step`` (:44-53), the RESET/SEND/RECV flag protocol and prechecks (:17-42),
+``joint_space`` (:55-68), ``make_seeds`` (:639-650) and the ``Serial`` object surface (:70-166).  The backend
+class ``B200`` replaces Serial/Multiprocessing: instead of N Python env objects stepped in a loop it owns one
+``pb_env`` handle (N env instances on one GPU) and every send() is one kernel launch that writes obs / reward /
+done rows where they are needed -- its own buffers, or straight into a bound rollout (``bind_rollout``).
+
+recv() returns torch CUDA tensors (aliasing internal buffers across calls, as the reference aliases its numpy
+buffers, vector.py:158-162).  With ``host_buffers=True`` it returns pinned-host numpy arrays exactly like Serial
+(D2H copy per step), which is what an unmodified ``clean_pufferl.evaluate`` consumes.
+"""
+import ctypes as C
+import functools
+
+import numpy as np
+import torch
+
+from pufferlib_b200 import _native, spaces
+from pufferlib_b200.environments import resolve
+from pufferlib_b200.exceptions import APIUsageError
+from pufferlib_b200.namespace import Namespace, namespace
+
+RESET = 0
+STEP = 1
+SEND = 2
+RECV = 3
+CLOSE = 4
+MAIN = 5
+INFO = 6
+
+
+def recv_precheck(vecenv):
+    if vecenv.flag != RECV:
+        raise APIUsageError('Call reset before stepping')
+    vecenv.flag = SEND
+
+
+def send_precheck(vecenv, actions):
+    if vecenv.flag != SEND:
+        raise APIUsageError('Call (async) reset + recv before sending')
+    if not vecenv.initialized:
+        vecenv.initialized = True
+        if isinstance(actions, torch.Tensor):
+            n = vecenv.single_action_space.n
+            ok = (actions.shape == (vecenv.num_agents,) and not actions.dtype.is_floating_point
+                  and bool(((actions >= 0) & (actions < n)).all()))
+        else:
+            ok = vecenv.action_space.contains(np.asarray(actions))
+        if not ok:
+            raise APIUsageError('Actions do not match action space')
+    vecenv.flag = RECV
+    return actions
+
+
+def reset(vecenv, seed=42):
+    vecenv.async_reset(seed)
+    obs, rewards, terminals, truncations, infos, env_ids, masks = vecenv.recv()
+    return obs, infos
+
+
+def step(vecenv, actions):
+    vecenv.send(actions)
+    obs, rewards, terminals, truncations, infos, env_ids, masks = vecenv.recv()
+    return obs, rewards, terminals, truncations, infos
+
+
+def joint_space(space, n):
+    if isinstance(space, spaces.Discrete):
+        return spaces.MultiDiscrete([space.n] * n)
+    elif isinstance(space, spaces.MultiDiscrete):
+        return spaces.Box(low=0, high=np.repeat(space.nvec[None] - 1, n, axis=0),
+                          shape=(n, len(space)), dtype=space.dtype)
+    elif isinstance(space, spaces.Box):
+        return spaces.Box(low=np.repeat(space.low[None], n, axis=0), high=np.repeat(space.high[None], n, axis=0),
+                          shape=(n, *space.shape), dtype=space.dtype)
+    else:
+        raise ValueError(f'Unsupported space: {space}')
+
+
+def make_seeds(seed, num_envs):
+    if isinstance(seed, int):
+        return [seed + i for i in range(num_envs)]
+    err = f'seed {seed} must be an integer or a list of integers'
+    if isinstance(seed, (list, tuple)):
+        if len(seed) != num_envs:
+            raise APIUsageError(err)
+        return seed
+    raise APIUsageError(err)
+
+
+_NP_DTYPES = {_native.DTYPE_F32: np.float32, _native.DTYPE_U8: np.uint8}
+_TORCH_DTYPES = {_native.DTYPE_F32: torch.float32, _native.DTYPE_U8: torch.uint8}
+
+
+class _DriverEnv:
+    """What ``vecenv.driver_env`` must expose: spaces, emulated, render()."""
+
+    def __init__(self, vec):
+        self.single_observation_space = vec.single_observation_space
+        self.single_action_space = vec.single_action_space
+        self.observation_space = vec.single_observation_space
+        self.action_space = vec.single_action_space
+        self.emulated = vec.emulated
+        self.num_agents = 1
+        self.render_mode = 'ansi'
+        self._vec = vec
+
+    def render(self):
+        obs = self._vec.buf.observations[0].detach().cpu().numpy()
+        return np.array2string(obs, max_line_width=200)
+
+
+class B200:
+    """Device-resident vectorised env backend (pass as ``backend=`` to ``make``)."""
+    reset = reset
+    step = step
+
+    @classmethod
+    def options(cls, **opts):
+        """``backend=B200.options(host_buffers=True, exact_infos=True, device=0, env_index_offset=...)``:
+        ``make`` forwards only num_workers / batch_size / zero_copy (vector.py:631-633), so backend options are
+        bound here."""
+        return functools.partial(cls, **opts)
+
+    @property
+    def num_envs(self):
+        return self.agents_per_batch
+
+    def __init__(self, env_creators, env_args, env_kwargs, num_envs, host_buffers=False, exact_infos=None,
+                 device=None, env_index_offset=0, **kwargs):
+        for k in kwargs:
+            if k not in ('num_workers', 'batch_size', 'zero_copy', 'backend'):
+                raise APIUsageError(f'Invalid argument: {k}')
+        if kwargs.get('batch_size') not in (None, num_envs):
+            raise NotImplementedError('B200 backend: batch_size < num_envs (pool mode) is not implemented')
+        kind, iparam = resolve(env_creators[0], env_args[0], env_kwargs[0])
+        for c, a, k in zip(env_creators, env_args, env_kwargs):
+            if resolve(c, a, k) != (kind, iparam):
+                raise APIUsageError('B200 backend: all env creators / args must be identical')
+        if not torch.cuda.is_available():
+            raise RuntimeError('pufferlib_b200 needs a CUDA device (no CPU fallback)')
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device('cuda', self.device_index)
+        self.kind = kind
+        self.host_buffers = bool(host_buffers)
+        self.exact_infos = self.host_buffers if exact_infos is None else bool(exact_infos)
+        lib = _native.lib()
+        cfg = _native.EnvConfig(kind=_native.ENV_KINDS[kind], num_envs=num_envs, device=self.device_index,
+                                reserved=0, env_index_offset=int(env_index_offset),
+                                iparam=(C.c_int32 * 8)(*iparam))
+        handle = C.c_void_p()
+        _native.check(lib.pb_env_create(C.byref(cfg), C.byref(handle)))
+        self._handle = handle
+        info = _native.EnvInfo()
+        _native.check(lib.pb_env_get_info(self._handle, C.byref(info)))
+        self.obs_bytes = int(info.obs_bytes)
+        self._obs_torch_dtype = _TORCH_DTYPES[info.obs_dtype]
+        obs_shape = tuple(info.obs_shape[i] for i in range(info.obs_ndim))
+        self.single_observation_space = spaces.Box(low=info.obs_low, high=info.obs_high, shape=obs_shape,
+                                                   dtype=_NP_DTYPES[info.obs_dtype])
+        self.single_action_space = spaces.Discrete(info.num_actions)
+        self.emulated = namespace(observation_dtype=self.single_observation_space.dtype,
+                                  emulated_observation_dtype=self.single_observation_space.dtype)
+        self.agents_per_batch = num_envs
+        self.num_agents = num_envs
+        self.action_space = joint_space(self.single_action_space, num_envs)
+        self.observation_space = joint_space(self.single_observation_space, num_envs)
+        self.agent_ids = np.arange(num_envs)
+        self.initialized = False
+        self.flag = RESET
+        self.infos = []
+        with torch.cuda.device(self.device):
+            self.buf = namespace(
+                observations=torch.zeros((num_envs, *obs_shape), dtype=self._obs_torch_dtype, device=self.device),
+                rewards=torch.zeros(num_envs, dtype=torch.float32, device=self.device),
+                terminals=torch.zeros(num_envs, dtype=torch.bool, device=self.device),
+                truncations=torch.zeros(num_envs, dtype=torch.bool, device=self.device),
+                masks=torch.ones(num_envs, dtype=torch.bool, device=self.device),
+                dones_f32=torch.zeros(num_envs, dtype=torch.float32, device=self.device),
+            )
+            self._actions_dev = torch.zeros(num_envs, dtype=torch.int64, device=self.device)
+        self.driver_env = _DriverEnv(self)
+        # rollout binding (clean_pufferl.create): step outputs go straight into Experience rows
+        self._rollout = None
+        self._cursor = 0            # rollout row of the observation recv() returns next
+        self._pending_own = True    # latest step output lives in self.buf (not yet in a rollout row)
+        if self.host_buffers:
+            self._host = namespace(
+                observations=torch.zeros((num_envs, *obs_shape), dtype=self._obs_torch_dtype).pin_memory(),
+                rewards=torch.zeros(num_envs, dtype=torch.float32).pin_memory(),
+                terminals=torch.zeros(num_envs, dtype=torch.bool).pin_memory(),
+                truncations=torch.zeros(num_envs, dtype=torch.bool).pin_memory(),
+                masks=torch.ones(num_envs, dtype=torch.bool).pin_memory(),
+                actions=torch.zeros(num_envs, dtype=torch.int64).pin_memory(),
+            )
+            self._host_np = namespace(**{k: v.numpy() for k, v in self._host.items()})
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    # -- rollout binding --------------------------------------------------------------------------------------
+    def bind_rollout(self, experience):
+        """Let send() write obs / reward / done rows directly into ``experience`` (time-major [H][N] tensors).
+        Row 0 of each rollout is filled from the carry-over buffers at the first recv()."""
+        if experience.batch_size % self.num_agents != 0:
+            raise APIUsageError('batch_size must be a multiple of num_envs to bind a rollout')
+        self._rollout = experience
+        self._horizon = experience.batch_size // self.num_agents
+        self._cursor = 0
+        self._pending_own = True
+
+    def _env_out(self, row):
+        """pb_env_out for rollout row `row`, or for the vecenv's own buffers when row is None."""
+        b = self.buf
+        if row is None:
+            return _native.EnvOut(obs=b.observations.data_ptr(), obs_stride=self.obs_bytes,
+                                  rewards=b.rewards.data_ptr(), terminals=b.terminals.data_ptr(),
+                                  truncations=b.truncations.data_ptr(), masks=b.masks.data_ptr(),
+                                  dones_f32=b.dones_f32.data_ptr())
+        x, n = self._rollout, self.num_agents
+        return _native.EnvOut(obs=x.obs.data_ptr() + row * n * self.obs_bytes, obs_stride=self.obs_bytes,
+                              rewards=x.rewards.data_ptr() + row * n * 4, terminals=b.terminals.data_ptr(),
+                              truncations=b.truncations.data_ptr(), masks=b.masks.data_ptr(),
+                              dones_f32=x.dones.data_ptr() + row * n * 4)
+
+    # -- vector.Serial surface ---------------------------------------------------------------------------------
+    def async_reset(self, seed=42):
+        if not isinstance(seed, int):
+            raise APIUsageError(f'seed {seed} must be an integer (per-env seed lists are not supported on the device)')
+        self.flag = RECV
+        out = self._env_out(None)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().pb_env_reset(self._handle, C.c_uint64(seed % (1 << 64)), C.byref(out),
+                                                     _native.stream_ptr()))
+        self._pending_own = True
+        self._cursor = 0
+        self.infos = []
+
+    def send(self, actions):
+        actions = send_precheck(self, actions)
+        with torch.cuda.device(self.device):
+            if isinstance(actions, torch.Tensor) and actions.is_cuda:
+                a = actions if (actions.dtype == torch.int64 and actions.is_contiguous()) else \
+                    actions.to(torch.int64).contiguous()
+            else:
+                a_np = np.ascontiguousarray(np.asarray(actions), dtype=np.int64)
+                if self.host_buffers:
+                    self._host_np.actions[:] = a_np
+                    self._actions_dev.copy_(self._host.actions, non_blocking=True)
+                else:
+                    self._actions_dev.copy_(torch.from_numpy(a_np), non_blocking=False)
+                self.h2d_bytes += a_np.nbytes
+                a = self._actions_dev
+            row = None
+            if self._rollout is not None and not self._pending_own and self._cursor + 1 < self._horizon:
+                row = self._cursor + 1
+            out = self._env_out(row)
+            _native.check(_native.lib().pb_env_step(self._handle, C.c_void_p(a.data_ptr()), C.byref(out),
+                                                    _native.stream_ptr()))
+            if self._rollout is not None:
+                if row is None:
+                    self._pending_own = True
+                    self._cursor = 0
+                else:
+                    self._cursor = row
+        self._stepped = True
+
+    def recv(self):
+        recv_precheck(self)
+        b = self.buf
+        with torch.cuda.device(self.device):
+            if self._rollout is not None:
+                x, n, t = self._rollout, self.num_agents, self._cursor
+                lo, hi = t * n, (t + 1) * n
+                if self._pending_own:   # carry-over rows (reset, or the step that closed the previous rollout)
+                    lib = _native.lib()
+                    _native.check(lib.pb_copy_rows(_native.ptr(b.observations), self.obs_bytes,
+                                                   C.c_void_p(x.obs.data_ptr() + lo * self.obs_bytes),
+                                                   self.obs_bytes, self.obs_bytes, n, _native.stream_ptr()))
+                    x.rewards[lo:hi].copy_(b.rewards)
+                    x.dones[lo:hi].copy_(b.dones_f32)
+                    self._pending_own = False
+                obs, rewards = x.obs[lo:hi], x.rewards[lo:hi]
+            else:
+                obs, rewards = b.observations, b.rewards
+            infos = self._collect_infos() if self.exact_infos else []
+            self.infos = infos
+            if self.host_buffers:
+                h = self._host
+                h.observations.copy_(obs, non_blocking=True)
+                h.rewards.copy_(rewards, non_blocking=True)
+                h.terminals.copy_(b.terminals, non_blocking=True)
+                h.truncations.copy_(b.truncations, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                self.d2h_bytes += (h.observations.numel() * h.observations.element_size()
+                                   + 4 * self.num_agents + 2 * self.num_agents)
+                hn = self._host_np
+                return (hn.observations, hn.rewards, hn.terminals, hn.truncations, infos, self.agent_ids, hn.masks)
+        return (obs, rewards, b.terminals, b.truncations, infos, self.agent_ids, b.masks)
+
+    def _collect_infos(self):
+        """Per-env info dicts for rows that just ended an episode (EpisodeStats, postprocess.py:36-52), in env
+        order like Serial.send (vector.py:153-154).  Costs one D2H of the terminal flags per recv."""
+        term = self.buf.terminals.cpu().numpy()
+        self.d2h_bytes += term.nbytes
+        idx = np.nonzero(term)[0]
+        if len(idx) == 0:
+            return []
+        lib = _native.lib()
+        p_ret, p_len, p_score = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _native.check(lib.pb_env_episode_rows(self._handle, C.byref(p_ret), C.byref(p_len), C.byref(p_score)))
+        n = self.num_agents
+        ret = _from_device(p_ret.value, n, np.float64)
+        length = _from_device(p_len.value, n, np.int32)
+        score = _from_device(p_score.value, n, np.float32)
+        self.d2h_bytes += n * 16
+        return [{'episode_return': float(ret[i]), 'episode_length': int(length[i]), 'score': float(score[i])}
+                for i in idx]
+
+    def episode_stats(self, clear=True):
+        """Device-side EpisodeStats reduction: {episode_return, episode_length, score} means over the episodes
+        finished since the last call, plus their count (one 32-byte D2H)."""
+        out = (C.c_double * 4)()
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().pb_env_stats_read(self._handle, out, int(clear), _native.stream_ptr()))
+        self.d2h_bytes += 32
+        cnt = out[0]
+        if cnt <= 0:
+            return {}, 0
+        return {'episode_return': out[1] / cnt, 'episode_length': out[2] / cnt, 'score': out[3] / cnt}, int(cnt)
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            _native.lib().pb_env_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _from_device(addr, n, dtype):
+    """Copy n elements of a raw device array to a numpy array (cudaMemcpy through a torch byte tensor)."""
+    nbytes = n * np.dtype(dtype).itemsize
+    out = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
+    _native.check(_native.lib().pb_copy_rows(C.c_void_p(addr), nbytes, _native.ptr(out), nbytes, nbytes, 1,
+                                             _native.stream_ptr()))
+    return out.cpu().numpy().view(dtype)
+
+
+def make(env_creator_or_creators, env_args=None, env_kwargs=None, backend=B200, num_envs=1, **kwargs):
+    """Same contract and error behaviour as the reference ``pufferlib.vector.make`` (vector.py:577-637)."""
+    if num_envs < 1:
+        raise APIUsageError('num_envs must be at least 1')
+    if num_envs != int(num_envs):
+        raise APIUsageError('num_envs must be an integer')
+
+    if 'num_workers' in kwargs:
+        num_workers = kwargs['num_workers']
+        envs_per_worker = num_envs / num_workers
+        if envs_per_worker != int(envs_per_worker):
+            raise APIUsageError('num_envs must be divisible by num_workers')
+        if 'batch_size' in kwargs:
+            batch_size = kwargs['batch_size']
+            if batch_size is None:
+                batch_size = num_envs
+            if batch_size % envs_per_worker != 0:
+                raise APIUsageError('batch_size must be divisible by (num_envs / num_workers)')
+
+    if env_args is None:
+        env_args = []
+    if env_kwargs is None:
+        env_kwargs = {}
+
+    if not isinstance(env_creator_or_creators, (list, tuple)):
+        env_creators = [env_creator_or_creators] * num_envs
+        env_args = [env_args] * num_envs
+        env_kwargs = [env_kwargs] * num_envs
+    else:
+        env_creators = env_creator_or_creators
+
+    if len(env_creators) != num_envs:
+        raise APIUsageError('env_creators must be a list of length num_envs')
+    if len(env_args) != num_envs:
+        raise APIUsageError('env_args must be a list of length num_envs')
+    if len(env_kwargs) != num_envs:
+        raise APIUsageError('env_kwargs must be a list of length num_envs')
+
+    # per-entry validation: identical objects are checked once (N can be 131072)
+    seen = set()
+    for i in range(num_envs):
+        key = (id(env_creators[i]), id(env_args[i]), id(env_kwargs[i]))
+        if key in seen:
+            continue
+        seen.add(key)
+        if not callable(env_creators[i]):
+            raise APIUsageError('env_creators must be a list of callables')
+        if not isinstance(env_args[i], (list, tuple)):
+            raise APIUsageError('env_args must be a list of lists or tuples')
+        if not isinstance(env_kwargs[i], (dict, Namespace)):
+            raise APIUsageError('env_kwargs must be a list of dictionaries')
+
+    for k in kwargs:
+        if k not in ['num_workers', 'batch_size', 'zero_copy', 'backend']:
+            raise APIUsageError(f'Invalid argument: {k}')
+
+    return backend(env_creators, env_args, env_kwargs, num_envs, **kwargs)

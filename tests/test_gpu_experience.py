@@ -1,0 +1,146 @@
+"""Experience (store -> GAE -> flatten_batch -> adv-norm) on the device vs the reference's own outputs
+(tests/golden/experience_*.npz) and the numpy oracle; plus the standalone train-prep kernels at larger sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import pufferlib_b200.vector as pvec
+from pufferlib_b200 import _native, clean_pufferl
+from pufferlib_b200.environments import ocean
+from oracle import experience as oexp
+from oracle import gae as ogae
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu(x):
+    return x.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize('case', ['experience_c1', 'experience_small', 'experience_one_mb'])
+@pytest.mark.parametrize('bound', [True, False])
+def test_experience_pipeline_vs_reference(golden, case, bound):
+    g = golden(case)
+    n, h = int(g['num_envs']), int(g['horizon'])
+    vec = pvec.make(ocean.env_creator('squared'), num_envs=n, backend=pvec.B200)
+    vec.async_reset(int(g['seed']))
+    exp = clean_pufferl.Experience(n * h, int(g['bptt']), int(g['minibatch_size']), (7, 7), np.float32, ())
+    if bound:
+        vec.bind_rollout(exp)
+    dev = torch.device('cuda')
+    t = 0
+    while not exp.full:
+        o, r, d, tr, infos, env_id, mask = vec.recv()
+        a = torch.as_tensor(g['tape'][t], device=dev)
+        exp.store(o, torch.as_tensor(g['values_in'][t], device=dev), a, torch.as_tensor(g['logprobs_in'][t], device=dev),
+                  r, d, env_id, mask)
+        vec.send(a)
+        t += 1
+    assert t == h
+    # stored rollout == the reference's Experience arrays, bit for bit
+    assert np.array_equal(cpu(exp.obs), g['stored_obs_i8'].astype(np.float32))
+    for k in ('actions', 'logprobs', 'rewards', 'dones', 'values'):
+        assert np.array_equal(cpu(getattr(exp, k)), g['stored_' + k]), k
+    idxs = exp.sort_training_data()
+    assert np.array_equal(np.asarray(idxs), g['idxs'])
+    adv = cpu(exp.compute_gae(float(g['gamma']), float(g['gae_lambda'])))
+    ref = g['advantages']
+    assert np.max(np.abs(adv - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-5
+    exp.flatten_batch()
+    assert np.array_equal(cpu(exp.b_obs), g['b_obs_i8'].astype(np.float32))
+    for k in ('b_actions', 'b_logprobs', 'b_dones', 'b_values'):
+        assert np.array_equal(cpu(getattr(exp, k)), g[k]), k
+    for k in ('b_advantages', 'b_returns'):
+        assert np.allclose(cpu(getattr(exp, k)), g[k], rtol=1e-5, atol=1e-5), k
+    assert np.allclose(cpu(exp.returns), g['returns_np'], rtol=1e-5, atol=1e-5)      # the literal :476 quantity
+    norm = cpu(exp.normalize_advantages())
+    assert np.allclose(norm, g['b_advantages_normalized'], rtol=1e-5, atol=2e-5)
+    # a second rollout through the same buffers: carry-over row 0 must be the step that closed the first rollout
+    o2 = vec.recv()[0]
+    assert cpu(o2).shape == (n, 7, 7)
+    vec.close()
+
+
+@pytest.mark.parametrize('n,h,mb,bptt,obs_shape,dtype', [
+    (64, 128, 2048, 16, (7, 7), np.float32), (33, 12, 36, 4, (5,), np.float32), (16, 64, 256, 8, (128,), np.float32),
+    (8, 32, 64, 16, (4, 84, 84), np.uint8), (100, 10, 250, 5, (3,), np.uint8), (256, 128, 4096, 32, (116,), np.float32)])
+def test_flatten_and_gather_vs_numpy_oracle(n, h, mb, bptt, obs_shape, dtype):
+    rng = np.random.default_rng(n * h)
+    b = n * h
+    dev = torch.device('cuda')
+    exp = clean_pufferl.Experience(b, bptt, mb, obs_shape, dtype, ())
+    ora = oexp.Experience(b, bptt, mb, obs_shape, dtype)
+    if np.dtype(dtype) == np.uint8:
+        obs = rng.integers(0, 256, size=(b, *obs_shape), dtype=np.uint8)
+    else:
+        obs = rng.standard_normal((b, *obs_shape)).astype(np.float32)
+    fields = dict(actions=rng.integers(0, 6, size=b).astype(np.int64), logprobs=-rng.random(b).astype(np.float32),
+                  rewards=rng.standard_normal(b).astype(np.float32), dones=(rng.random(b) < 0.05).astype(np.float32),
+                  values=rng.standard_normal(b).astype(np.float32))
+    exp.obs.copy_(torch.as_tensor(obs, device=dev))
+    ora.obs[:] = obs
+    for k, v in fields.items():
+        getattr(exp, k).copy_(torch.as_tensor(v, device=dev))
+        getattr(ora, k)[:] = v
+    exp.num_envs = n
+    ora.sort_keys = [(e, t) for t in range(h) for e in range(n)]
+    idxs = ora.sort_training_data()
+    assert np.array_equal(np.asarray(exp.sort_training_data()), idxs)
+    adv_ref = ogae.compute_gae(ora.dones[idxs], ora.values[idxs], ora.rewards[idxs], 0.99, 0.95)
+    adv = cpu(exp.compute_gae(0.99, 0.95))
+    assert np.max(np.abs(adv - adv_ref) / np.maximum(1.0, np.abs(adv_ref))) <= 1e-5
+    # feed the oracle's advantages so the remaining comparisons are exact byte movement
+    exp.advantages.copy_(torch.as_tensor(adv_ref, device=dev))
+    exp.flatten_batch()
+    ora.flatten_batch(adv_ref)
+    assert np.array_equal(cpu(exp.b_obs), ora.b_obs)
+    for k in ('b_actions', 'b_logprobs', 'b_dones', 'b_values', 'b_advantages', 'b_returns'):
+        assert np.array_equal(cpu(getattr(exp, k)), getattr(ora, k)), k
+    assert np.array_equal(cpu(exp.returns), ora.returns_np)
+    norm = cpu(exp.normalize_advantages())
+    for m in range(exp.num_minibatches):
+        t_ref = torch.as_tensor(ora.b_advantages[m])
+        t_ref = ((t_ref - t_ref.mean()) / (t_ref.std() + 1e-8)).numpy()      # clean_pufferl.py:213 on CPU fp32
+        assert np.allclose(norm[m], t_ref, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('n_mb,mb_size', [(1, 2), (1, 2048), (4, 65536), (2, 1048576), (3, 1000), (128, 16384)])
+def test_adv_norm_vs_torch(n_mb, mb_size):
+    dev = torch.device('cuda')
+    g = torch.Generator(device='cpu').manual_seed(n_mb * 7 + mb_size)
+    a = (torch.randn(n_mb, mb_size, generator=g) * 3 + 0.5).to(dev)
+    out = torch.empty_like(a)
+    lib = _native.lib()
+    ws = torch.zeros(max(16, lib.pb_adv_norm_workspace_bytes(n_mb, mb_size)), dtype=torch.uint8, device=dev)
+    _native.check(lib.pb_adv_norm(_native.ptr(a), _native.ptr(out), n_mb, mb_size, _native.ptr(ws), ws.numel(),
+                                  _native.stream_ptr()))
+    ref = torch.stack([(x - x.mean()) / (x.std() + 1e-8) for x in a.double()]).float()
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    # idempotence-style property at any size: the output has mean 0 and unbiased std 1
+    assert torch.allclose(out.double().mean(1), torch.zeros(n_mb, device=dev, dtype=torch.float64), atol=1e-5)
+    if mb_size > 2:
+        assert torch.allclose(out.double().std(1), torch.ones(n_mb, device=dev, dtype=torch.float64), atol=1e-4)
+    # in-place
+    _native.check(lib.pb_adv_norm(_native.ptr(a), _native.ptr(a), n_mb, mb_size, _native.ptr(ws), ws.numel(),
+                                  _native.stream_ptr()))
+    assert torch.equal(a, out)
+
+
+def test_copy_rows_and_store():
+    dev = torch.device('cuda')
+    lib = _native.lib()
+    for row_bytes, n_rows in [(196, 64), (512, 1000), (7, 33), (28224, 16), (16, 1)]:
+        src = torch.randint(0, 256, (n_rows, row_bytes + 16), dtype=torch.uint8, device=dev)
+        dst = torch.zeros(n_rows, row_bytes + 32, dtype=torch.uint8, device=dev)
+        _native.check(lib.pb_copy_rows(_native.ptr(src), row_bytes + 16, _native.ptr(dst), row_bytes + 32, row_bytes,
+                                       n_rows, _native.stream_ptr()))
+        assert torch.equal(dst[:, :row_bytes], src[:, :row_bytes]) and int(dst[:, row_bytes:].sum()) == 0
+    n = 1000
+    v, lp = torch.randn(n, device=dev), torch.randn(n, device=dev)
+    a = torch.randint(0, 8, (n,), device=dev)
+    vr, lr, ar = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, dtype=torch.int64, device=dev)
+    _native.check(lib.pb_rollout_store(_native.ptr(v), _native.ptr(lp), _native.ptr(a), _native.ptr(vr), _native.ptr(lr),
+                                       _native.ptr(ar), n, _native.stream_ptr()))
+    assert torch.equal(v, vr) and torch.equal(lp, lr) and torch.equal(a, ar)
