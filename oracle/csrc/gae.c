@@ -25,3 +25,18 @@ void oracle_compute_gae(const float* dones, const float* values, const float* re
         advantages[t_cur] = lastgaelam;
     }
 }
+
+/* The same recurrence in double: ground truth that puts the reference's fp32 rounding and the CUDA scan's
+ * rounding on one scale in the tolerance tests (gamma / lambda are the fp32 values widened, like the C floats). */
+void oracle_compute_gae_f64(const float* dones, const float* values, const float* rewards, float gamma,
+                            float gae_lambda, double* advantages, long num_steps) {
+    double last = 0.0, g = (double)gamma, l = (double)gae_lambda;
+    if (num_steps <= 0) return;
+    advantages[num_steps - 1] = 0.0;
+    for (long t = num_steps - 2; t >= 0; t--) {
+        double nnt = 1.0 - (double)dones[t + 1];
+        double delta = (double)rewards[t + 1] + g * (double)values[t + 1] * nnt - (double)values[t];
+        last = delta + g * l * nnt * last;
+        advantages[t] = last;
+    }
+}

@@ -2,7 +2,7 @@
 
 ``compute_gae_np``  sequential numpy-fp32 loop following /root/reference/c_gae.pyx:24-30 (small cases).
 ``compute_gae``     ctypes call into ``oracle/csrc/gae.c`` (same recurrence in C, any size).
-``compute_gae_f64`` the recurrence in float64: ground truth used to put both the reference's and the
+``compute_gae_f64`` the recurrence in float64 (C): ground truth used to put both the reference's and the
                     CUDA scan's rounding error on one scale in the tolerance tests.
 """
 import ctypes
@@ -40,14 +40,12 @@ def compute_gae(dones, values, rewards, gamma, gae_lambda):
 
 
 def compute_gae_f64(dones, values, rewards, gamma, gae_lambda):
-    d, v, r = (np.asarray(a, dtype=np.float64) for a in (dones, values, rewards))
-    g, l = float(np.float32(gamma)), float(np.float32(gae_lambda))
-    n = len(r)
+    lib = _build.load()
+    dones, values, rewards = (np.ascontiguousarray(a, dtype=np.float32) for a in (dones, values, rewards))
+    n = len(rewards)
     adv = np.zeros(n, dtype=np.float64)
-    last = 0.0
-    for t in range(n - 2, -1, -1):
-        nnt = 1.0 - d[t + 1]
-        delta = r[t + 1] + g * v[t + 1] * nnt - v[t]
-        last = delta + g * l * nnt * last
-        adv[t] = last
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.oracle_compute_gae_f64(dones.ctypes.data_as(fp), values.ctypes.data_as(fp), rewards.ctypes.data_as(fp),
+                               ctypes.c_float(gamma), ctypes.c_float(gae_lambda),
+                               adv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.c_long(n))
     return adv

@@ -24,16 +24,6 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
 
 
-def defines():
-    have = {os.path.basename(s) for s in sources()}
-    d = []
-    for f, macro in (('env_breakout.cu', 'PB_HAVE_BREAKOUT'), ('env_snake.cu', 'PB_HAVE_SNAKE'),
-                     ('env_pong.cu', 'PB_HAVE_PONG'), ('image.cu', 'PB_HAVE_IMAGE'), ('sample.cu', 'PB_HAVE_SAMPLE')):
-        if f in have:
-            d.append('-D' + macro)
-    return d
-
-
 def up_to_date():
     if not os.path.exists(SO):
         return False
@@ -56,7 +46,7 @@ def build(force=False, verbose=False):
                 and all(os.path.getmtime(obj) >= os.path.getmtime(h) for h in
                         glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(REPO, 'include', '*.h')))):
             continue
-        cmd = [NVCC] + ARCH_FLAGS + COMMON + defines() + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        cmd = [NVCC] + ARCH_FLAGS + COMMON + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()

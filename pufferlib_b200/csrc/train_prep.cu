@@ -286,10 +286,8 @@ extern "C" int pb_minibatch_gather(const void* obs, void* dst, int64_t row_bytes
     PB_REQUIRE(obs && dst, PB_ERR_INVALID, "pb_minibatch_gather: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const int vb = vec_bytes_for(obs, dst, row_bytes, row_bytes, row_bytes);
-#ifdef PB_HAVE_IMAGE
     if (vb == 16 && row_bytes >= 4096)
         return pb_minibatch_gather_tma(obs, dst, row_bytes, num_envs, horizon, n_mb, rows, bptt, mb_begin, mb_count, s);
-#endif
     const int64_t n_out = mb_count * rows * bptt;
     GatherGeom g{num_envs, horizon, n_mb, rows, bptt, mb_begin};
     constexpr int RPI = 4;
