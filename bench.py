@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/sec of the env-step + PPO-rollout hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one full PPO iteration over one batch: H vectorised env steps with the policy in the loop (obs /
+reward / done / value / logprob / action rows written into the device rollout), then GAE, minibatch construction,
+advantage normalisation and update_epochs x num_minibatches optimizer steps.  Workload = BASELINE.json configs[1]:
+breakout, num_envs=16384 per GPU, horizon=128, MLP policy (hidden 128); multi-GPU = configs[4] (env shards per
+rank, one NCCL gradient all-reduce per optimizer step, weak scaling).  PPO hyper-parameters are the reference's
+defaults (config.yaml:12-42) with its batch:minibatch ratio of 4.
+
+`value`  : everything device-resident (CUDA-graphed rollout, no per-step host traffic).
+`e2e`    : the same step through the public vector/clean_pufferl API with HOST buffers (recv() returns pinned numpy
+           arrays, send() takes numpy actions; obs H2D for the policy and action D2H every env step, like the
+           reference's evaluate loop).
+`--impl reference` / `cpu_baseline`: the oracle's CPU restatement of the same path (oracle/: C vectoriser + env with
+           OpenMP over all host cores, Python sort_training_data, C GAE, numpy flatten, torch-CPU policy and PPO
+           update) on a bounded sample of the workload.  /root/reference itself cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np
+import torch
+
+METRIC = 'agent-steps/sec (env step + PPO rollout/update hot path)'
+UNIT = 'agent-steps/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--env', default='breakout')
+    ap.add_argument('--num-envs', type=int, default=16384, help='per GPU')
+    ap.add_argument('--horizon', type=int, default=128)
+    ap.add_argument('--hidden', type=int, default=128)
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-horizon', type=int, default=8, help='bounded sample: env steps per reference-arm step')
+    return ap.parse_args()
+
+
+def ppo_config(num_envs, horizon, device, seed=1, cuda_graph=True):
+    import pufferlib_b200
+    batch = num_envs * horizon
+    return pufferlib_b200.namespace(
+        seed=seed, torch_deterministic=True, env='breakout', batch_size=batch, bptt_horizon=16,
+        minibatch_size=batch // 4, cpu_offload=False, device=device, compile=False, learning_rate=2.5e-4,
+        gamma=0.99, gae_lambda=0.95, update_epochs=4, norm_adv=True, clip_coef=0.1, clip_vloss=True,
+        vf_clip_coef=0.1, vf_coef=0.5, ent_coef=0.01, max_grad_norm=0.5, target_kl=None, anneal_lr=False,
+        total_timesteps=10_000_000_000, cuda_graph=cuda_graph)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def make_b200(args, rank, world, host_buffers, cuda_graph):
+    import pufferlib_b200.vector as pvec
+    from pufferlib_b200 import clean_pufferl, models, distributed as pdist
+    from pufferlib_b200.environments import ocean
+    from pufferlib_b200.frameworks import cleanrl
+    n = args.num_envs
+    vec = pvec.make(ocean.env_creator(args.env), num_envs=n,
+                    backend=pvec.B200.options(host_buffers=host_buffers, exact_infos=False,
+                                              env_index_offset=rank * n))
+    torch.manual_seed(1)
+    policy = cleanrl.Policy(models.Default(vec.driver_env, hidden_size=args.hidden), fused_sample=True, seed=1 + rank)
+    policy = policy.cuda()
+    pdist.broadcast_parameters(policy)
+    cfg = ppo_config(n, args.horizon, 'cuda', seed=1, cuda_graph=cuda_graph)
+    data = clean_pufferl.create(cfg, vec, policy)
+    return data, clean_pufferl
+
+
+def timed_steps(data, cp, steps, world):
+    """K steps bracketed by barrier + synchronize, timed with CUDA events; returns max-over-ranks milliseconds."""
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        cp.evaluate(data)
+        cp.train(data)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    return float(ms.item())
+
+
+def kernel_rooflines(data, args, peak_gbs, peak_src):
+    """Per-kernel achieved HBM GB/s from ALGORITHMIC bytes / average launch duration (CUDA events on the launch
+    stream, back-to-back launches, working sets larger than L2: the 1 GiB rollout rotates under the env kernel)."""
+    import ctypes as C
+    from pufferlib_b200 import _native
+    exp, vec = data.experience, data.vecenv
+    n, h, o = args.num_envs, args.horizon, vec.obs_bytes
+    lib, s = _native.lib(), _native.stream_ptr()
+    out = {}
+
+    def time_launches(fn, reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3     # seconds per launch
+
+    # env step + obs/reward/done row write (one launch = one vectorised step of N envs)
+    actions = torch.randint(0, vec.single_action_space.n, (n,), device='cuda')
+    rows = [vec._env_out(t) for t in range(h)]
+
+    def env_step(i):
+        _native.check(lib.pb_env_step(vec._handle, _native.ptr(actions), C.byref(rows[i % h]), s))
+    for i in range(h):
+        env_step(i)
+    t_env = time_launches(env_step, 2 * h)
+    bytes_env = n * (o + 16)
+    out['env_step'] = dict(kernel='k_breakout<1>', bytes_per_launch=bytes_env, seconds=t_env,
+                           launches_per_step=h)
+
+    # GAE (+returns): 20 B per agent-step
+    exp.num_envs, exp.horizon = n, h
+    def gae(i):
+        exp.compute_gae(0.99, 0.95)
+    gae(0)
+    t_gae = time_launches(gae, 20)
+    out['gae'] = dict(kernel='k_gae<16>', bytes_per_launch=n * h * 20, seconds=t_gae, launches_per_step=1)
+
+    # minibatch gather of the observations: read + write of every row
+    def gather(i):
+        _native.check(lib.pb_minibatch_gather(_native.ptr(exp.obs), _native.ptr(exp.b_obs), exp.obs_row_bytes, n, h,
+                                              exp.num_minibatches, exp.minibatch_rows, exp.bptt_horizon, 0,
+                                              exp.num_minibatches, s))
+    gather(0)
+    t_g = time_launches(gather, 5)
+    out['obs_gather'] = dict(kernel='k_minibatch_gather<uint4,4>', bytes_per_launch=2 * n * h * o, seconds=t_g,
+                             launches_per_step=1)
+    for k, v in out.items():
+        v['achieved'] = v['bytes_per_launch'] / v['seconds'] / 1e9
+        v['frac'] = v['achieved'] / peak_gbs
+        v['share_s'] = v['seconds'] * v['launches_per_step']
+    dom = max(out, key=lambda k: out[k]['share_s'])
+    d = out[dom]
+    roof = {'bound': 'hbm', 'kernel': d['kernel'], 'achieved': round(d['achieved'], 1), 'peak': peak_gbs,
+            'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(d['frac'], 4), 'traffic': None,
+            'algorithmic_bytes_per_launch': d['bytes_per_launch'], 'avg_launch_us': round(d['seconds'] * 1e6, 2)}
+    others = {k: {'kernel': v['kernel'], 'achieved': round(v['achieved'], 1), 'frac': round(v['frac'], 4),
+                  'avg_launch_us': round(v['seconds'] * 1e6, 2), 'algorithmic_bytes_per_launch': v['bytes_per_launch']}
+              for k, v in out.items()}
+    return roof, others
+
+
+def load_peak():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    try:
+        return float(json.load(open(p))['hbm_gbs']), 'MEASURED_PEAKS.json (measured copy bandwidth)'
+    except Exception:
+        return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+
+def run_b200(args):
+    from pufferlib_b200 import distributed as pdist, _native
+    rank, local, world = pdist.init()
+    assert world == args.gpus, f'launched with WORLD_SIZE={world} but --gpus {args.gpus}'
+    torch.cuda.set_device(local)
+    n, h = args.num_envs, args.horizon
+    data, cp = make_b200(args, rank, world, host_buffers=False, cuda_graph=not args.no_graph)
+    for _ in range(max(args.warmup, 3)):
+        cp.evaluate(data)
+        cp.train(data)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0, replays0 = _native.lib().pb_launch_count(), data.graph_replays
+    ms = timed_steps(data, cp, args.steps, world)
+    launches = (_native.lib().pb_launch_count() - launches0) + (data.graph_replays - replays0) * data.graph_launches
+    clk = clocks.stop() if rank == 0 else None
+    value = world * n * h * args.steps / (ms * 1e-3)
+    prof = {k: round(v, 4) for k, v in dict(data.profile).items() if k.endswith('_time')}
+    stats = {k: float(v) for k, v in data.stats.items()}
+
+    peak, peak_src = load_peak()
+    roof, roof_all = kernel_rooflines(data, args, peak, peak_src)
+
+    # ---- e2e: same step through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        hdata, _ = make_b200(args, rank, world, host_buffers=True, cuda_graph=False)
+        cp.evaluate(hdata); cp.train(hdata)
+        hv = hdata.vecenv
+        io0 = (hdata.io.h2d + hv.h2d_bytes, hdata.io.d2h + hv.d2h_bytes)
+        k_e2e = max(2, min(args.steps, 5))
+        ms_e = timed_steps(hdata, cp, k_e2e, world)
+        io1 = (hdata.io.h2d + hv.h2d_bytes, hdata.io.d2h + hv.d2h_bytes)
+        e2e = {'value': world * n * h * k_e2e / (ms_e * 1e-3), 'unit': UNIT, 'steps': k_e2e,
+               'h2d_bytes_per_step': int((io1[0] - io0[0]) / k_e2e), 'd2h_bytes_per_step': int((io1[1] - io0[1]) / k_e2e),
+               'api': 'pufferlib_b200.vector.make(backend=B200.options(host_buffers=True)) + clean_pufferl.evaluate/train'}
+        cp.close(hdata)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = reference_arm(args, steps=2, warmup=1)
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (env state int32; policy GEMMs tf32 like the reference)',
+            'data': 'synthetic (fixed-seed envs, random-init policy)',
+            'config': {'workload': f'{args.env} num_envs={n}/GPU horizon={h} MLP hidden={args.hidden} '
+                                   f'(BASELINE.json configs[1]; x{world} ranks = configs[4])',
+                       'global_batch': world * n * h, 'minibatch_size': n * h // 4, 'update_epochs': 4,
+                       'bptt_horizon': 16, 'parallelism': f'dp{world} (env shards + 1 NCCL grad all-reduce/step)',
+                       'l2': 'inputs larger than L2 (1 GiB rollout rotates; no flush needed)',
+                       'cuda_graph_rollout': not args.no_graph},
+            'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'roofline_kernels': roof_all,
+            'cpu_baseline': cpu, 'clocks': clk, 'profile_s': prof, 'env_stats': stats,
+        }
+        print(json.dumps(line))
+    cp.close(data)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_arm(args, steps, warmup):
+    """The reference path's CPU implementation, restated by the oracle, on all host cores, on a bounded sample."""
+    import psutil
+    from oracle.envs import OracleVec, NUM_ACTIONS, OBS
+    from oracle import experience as oexp
+    from oracle import gae as ogae
+    cores = psutil.cpu_count(logical=False) or os.cpu_count()
+    torch.set_num_threads(cores)
+    n, h = args.num_envs, args.ref_horizon
+    batch = n * h
+    shape, dtype = OBS[args.env]
+    vec = OracleVec(args.env, n, threads=cores)
+    vec.collect_infos = False
+    torch.manual_seed(1)
+    in_dim, n_act = int(np.prod(shape)), NUM_ACTIONS[args.env]
+    enc, dec, vh = torch.nn.Linear(in_dim, args.hidden), torch.nn.Linear(args.hidden, n_act), torch.nn.Linear(args.hidden, 1)
+    params = list(enc.parameters()) + list(dec.parameters()) + list(vh.parameters())
+    opt = torch.optim.Adam(params, lr=2.5e-4, eps=1e-5)
+
+    def policy(obs, action=None):
+        hid = torch.relu(enc(obs.reshape(obs.shape[0], -1).float()))
+        logits, value = dec(hid), vh(hid)
+        norm = logits - logits.logsumexp(-1, keepdim=True)
+        if action is None:
+            action = torch.multinomial(norm.exp(), 1).squeeze(-1)
+        logprob = norm.gather(-1, action.reshape(-1, 1)).squeeze(-1)
+        ent = -(norm * norm.exp()).sum(-1)
+        return action, logprob, ent, value
+
+    vec.async_reset(1)
+
+    def one_step():
+        exp = oexp.Experience(batch, 16, batch // 4, shape, dtype)
+        while not exp.full:                                           # clean_pufferl.evaluate (:84-124)
+            o, r, d, t, info, env_id, mask = vec.recv()
+            with torch.no_grad():
+                a, lp, _, v = policy(torch.as_tensor(o))
+            exp.store(o, v.flatten().numpy(), a.numpy(), lp.numpy(), r, d, env_id, mask)
+            vec.send(a.numpy())
+        idxs = exp.sort_training_data()                               # clean_pufferl.train (:163-170)
+        adv = ogae.compute_gae(exp.dones[idxs], exp.values[idxs], exp.rewards[idxs], 0.99, 0.95)
+        exp.flatten_batch(adv)
+        for epoch in range(4):
+            for mb in range(exp.num_minibatches):
+                obs = torch.as_tensor(exp.b_obs[mb]).reshape(-1, *shape)
+                atn = torch.as_tensor(exp.b_actions[mb]).reshape(-1)
+                _, nlp, ent, nv = policy(obs, atn)
+                logratio = nlp - torch.as_tensor(exp.b_logprobs[mb]).reshape(-1)
+                ratio = logratio.exp()
+                a_ = torch.as_tensor(exp.b_advantages[mb]).reshape(-1)
+                a_ = (a_ - a_.mean()) / (a_.std() + 1e-8)
+                pg = torch.max(-a_ * ratio, -a_ * torch.clamp(ratio, 0.9, 1.1)).mean()
+                nv = nv.view(-1)
+                ret, val = torch.as_tensor(exp.b_returns[mb]), torch.as_tensor(exp.b_values[mb])
+                v_clipped = val + torch.clamp(nv - val, -0.1, 0.1)
+                vl = 0.5 * torch.max((nv - ret) ** 2, (v_clipped - ret) ** 2).mean()
+                loss = pg - 0.01 * ent.mean() + 0.5 * vl
+                opt.zero_grad()
+                loss.backward()
+                torch.nn.utils.clip_grad_norm_(params, 0.5)
+                opt.step()
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = time.perf_counter() - t0
+    value = batch * steps / dt
+    return {'value': value, 'unit': UNIT, 'cores': int(cores), 'kind': 'port',
+            'sample': f'{args.env} num_envs={n} x {h} env steps of the {args.horizon}-step rollout per step '
+                      f'({batch} agent-steps), full PPO update on it (4 epochs x 4 minibatches), {steps} steps',
+            'seconds': dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    res = reference_arm(args, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    n, h = args.num_envs, args.ref_horizon
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': max(1, min(args.warmup, 2)), 'ms_per_step': res['seconds'] / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'{args.env} num_envs={n} horizon={args.horizon} MLP hidden={args.hidden} '
+                               f'(bounded sample: {h} env steps per step)', 'parallelism': 'host cores (OpenMP + torch CPU)'},
+        'cpu_baseline': {k: res[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+        'e2e': {'value': res['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

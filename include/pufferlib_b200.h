@@ -88,6 +88,9 @@ typedef struct {
 const char* pb_last_error(void);
 int pb_abi_version(void);
 int pb_device_count(int* out_count);
+/* number of CUDA kernels this library has launched in this process (host-side counter; used by bench.py's
+ * `gpu_launches`).  Kernels replayed by a CUDA graph are not counted again. */
+uint64_t pb_launch_count(void);
 
 /* -- environments ---------------------------------------------------------------------------------------------
  * Replaces: the backend constructor instantiating N envs (vector.py:79), Serial.async_reset (vector.py:112-135),
@@ -178,11 +181,12 @@ int pb_image_pack(const void* new_frames, int64_t frame_stride, const void* prev
 /* -- fused sampling epilogue ----------------------------------------------------------------------
  * Replaces sample_logits (pufferlib/frameworks/cleanrl.py:25-47) for one Discrete head when sampling:
  * normalised = logits - logsumexp; action ~ Categorical(softmax) drawn with a counter-based RNG
- * (seed, offset, row); logprob = normalised[action]; entropy = -sum p*log p.  Optionally also writes
+ * (seed, offset + *offset_dev, row) -- offset_dev (optional device counter) keeps replays of a captured CUDA
+ * graph on fresh random numbers; logprob = normalised[action]; entropy = -sum p*log p.  Optionally also writes
  * action/logprob/value into rollout row pointers (the pb_rollout_store copy, fused).  logits [n][n_act] fp32. */
 int pb_sample_logits(const float* logits, int64_t n, int32_t n_act, uint64_t seed, uint64_t offset,
-                     int64_t* actions, float* logprobs, float* entropies, const float* value,
-                     float* values_row, float* logprobs_row, int64_t* actions_row, void* stream);
+                     const uint64_t* offset_dev, int64_t* actions, float* logprobs, float* entropies,
+                     const float* value, float* values_row, float* logprobs_row, int64_t* actions_row, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     'pb_last_error': (C.c_char_p, []),
     'pb_abi_version': (C.c_int, []),
     'pb_device_count': (C.c_int, [C.POINTER(C.c_int)]),
+    'pb_launch_count': (C.c_uint64, []),
     'pb_env_create': (C.c_int, [C.POINTER(EnvConfig), C.POINTER(C.c_void_p)]),
     'pb_env_destroy': (C.c_int, [C.c_void_p]),
     'pb_env_get_info': (C.c_int, [C.c_void_p, C.POINTER(EnvInfo)]),
@@ -56,7 +57,7 @@ SIGNATURES = {
     'pb_adv_norm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     'pb_image_pack': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                 C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
-    'pb_sample_logits': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64] + [C.c_void_p] * 7
+    'pb_sample_logits': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64] + [C.c_void_p] * 8
                          + [C.c_void_p]),
 }
 

@@ -314,46 +314,90 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         config=config, vecenv=vecenv, policy=policy, uncompiled_policy=uncompiled_policy, optimizer=optimizer,
         experience=experience, profile=profile, losses=losses, wandb=wandb, global_step=0, epoch=0, stats={},
         msg=msg, last_log_time=0, utilization=None, grad_bucket=grad_bucket,
+        io=pufferlib_b200.namespace(h2d=0, d2h=0), graph_state=0, rollout_graph=None, graph_steps=0,
+        graph_launches=0, graph_replays=0,
     )
 
 
-def evaluate(data):
+def _rollout_loop(data, infos):
+    """The body of evaluate (clean_pufferl.py:84-124): recv -> policy -> store -> send until the buffer is full.
+    On the device path it contains no host synchronisation, so it can be captured in a CUDA graph."""
     config, profile, experience = data.config, data.profile, data.experience
-    policy = data.policy
-    infos = defaultdict(list)
-    vecenv = data.vecenv
+    policy, vecenv = data.policy, data.vecenv
     on_device = not getattr(vecenv, 'host_buffers', False)
-
+    io = data.io
     while not experience.full:
         with profile.env:
             o, r, d, t, info, env_id, mask = vecenv.recv()
 
         with profile.eval_misc:
             data.global_step += len(env_id) if on_device else int(sum(mask))
-            o = torch.as_tensor(o)
-            o_device = o.to(config.device, non_blocking=True)
-            r = torch.as_tensor(r)
-            d = torch.as_tensor(d)
+            if on_device:
+                o_device = o
+            else:   # host buffers: the reference's H2D of the observation batch (clean_pufferl.py:92-95)
+                o_device = vecenv.pinned(o).to(config.device, non_blocking=True)
+                r = vecenv.pinned(r).to(config.device, non_blocking=True)
+                d = vecenv.pinned(d).to(config.device, non_blocking=True)
+                io.h2d += o.nbytes + r.nbytes + d.nbytes
 
         with profile.eval_forward, torch.no_grad():
             actions, logprob, _, value = policy(o_device)
 
         with profile.eval_misc:
             value = value.flatten()
-            if not on_device:
-                r, d = r.to(config.device, non_blocking=True), d.to(config.device, non_blocking=True)
             experience.store(o_device, value, actions, logprob, r, d, env_id, mask)
             for i in info:
                 for k, v in i.items():
                     infos[k].append(v)
 
         with profile.env:
-            vecenv.send(actions if on_device else actions.cpu().numpy())
+            if on_device:
+                vecenv.send(actions)
+            else:   # the reference's D2H of the actions (clean_pufferl.py:114)
+                a_host = actions.cpu().numpy()
+                io.d2h += a_host.nbytes
+                vecenv.send(a_host)
+
+
+def evaluate(data):
+    """Collect one rollout.  With ``config.cuda_graph`` (device path only) the whole H-step loop -- env-step
+    kernels, policy forward, sampling, rollout stores -- is captured once and replayed as ONE graph launch; the
+    first call runs eagerly (warm-up and allocations), the second captures."""
+    config, profile, experience = data.config, data.profile, data.experience
+    infos = defaultdict(list)
+    vecenv = data.vecenv
+    on_device = not getattr(vecenv, 'host_buffers', False)
+    use_graph = bool(getattr(config, 'cuda_graph', False)) and on_device and \
+        not getattr(vecenv, 'exact_infos', False)
+
+    if not use_graph or data.graph_state == 0:
+        _rollout_loop(data, infos)
+        if use_graph:
+            data.graph_state = 1
+    else:
+        if data.graph_state == 1:
+            torch.cuda.synchronize()
+            step0, launches0 = data.global_step, _native.lib().pb_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                _rollout_loop(data, infos)       # python-side state advances exactly as in an eager rollout
+            data.rollout_graph = graph
+            data.graph_steps = data.global_step - step0
+            data.graph_launches = _native.lib().pb_launch_count() - launches0
+            data.graph_state = 2
+            data.global_step = step0
+        with profile.env:
+            data.rollout_graph.replay()
+        data.global_step += data.graph_steps
+        data.graph_replays += 1
+        experience.ptr = experience.batch_size    # what the captured loop leaves behind
+        experience.step = experience.batch_size // experience.num_envs
 
     with profile.eval_misc:
         data.stats = {}
         if hasattr(vecenv, 'episode_stats') and not getattr(vecenv, 'exact_infos', False):
             means, count = vecenv.episode_stats(clear=True)    # device-side EpisodeStats reduction, one D2H
+            data.io.d2h += 32
             for k, v in means.items():
                 infos[k].append(v)
         for k, v in infos.items():
@@ -448,6 +492,7 @@ def train(data):
         var_y = y_true.var(unbiased=False)
         ev = 1 - (y_true - y_pred).var(unbiased=False) / var_y
         host = torch.cat([acc, torch.stack([ev, var_y])]).cpu().numpy()    # the one D2H of train()
+        data.io.d2h += host.nbytes
         # the reference resets the accumulators every epoch of update_epochs? no: it divides by num_minibatches
         # and keeps adding over epochs (clean_pufferl.py:249-254); same here.
         losses.policy_loss, losses.value_loss, losses.entropy = float(host[0]), float(host[1]), float(host[2])

@@ -14,7 +14,10 @@ void pb_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+unsigned long long g_pb_launches = 0;
+
 extern "C" const char* pb_last_error(void) { return g_err; }
+extern "C" uint64_t pb_launch_count(void) { return g_pb_launches; }
 extern "C" int pb_abi_version(void) { return PB_ABI_VERSION; }
 
 extern "C" int pb_device_count(int* out_count) {

@@ -25,7 +25,12 @@ void pb_set_error(const char* fmt, ...);
         }                                \
     } while (0)
 
-#define PB_LAUNCH_CHECK() PB_CUDA(cudaGetLastError())
+extern unsigned long long g_pb_launches;  // kernels launched by this library (host-side count)
+#define PB_LAUNCH_CHECK()            \
+    do {                             \
+        ++g_pb_launches;             \
+        PB_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline int64_t pb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 #ifdef __CUDACC__

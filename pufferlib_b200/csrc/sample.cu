@@ -15,8 +15,8 @@ namespace {
 constexpr int MAX_ACT = 32;
 
 __global__ void __launch_bounds__(256) k_sample_logits(const float* __restrict__ logits, int64_t n, int n_act,
-                                                      uint64_t seed, uint64_t offset, int64_t* actions,
-                                                      float* logprobs, float* entropies, const float* value,
+                                                      uint64_t seed, uint64_t offset, const uint64_t* __restrict__ offset_dev,
+                                                      int64_t* actions, float* logprobs, float* entropies, const float* value,
                                                       float* values_row, float* logprobs_row, int64_t* actions_row) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) k_sample_logits(const float* __restrict__
         if (k < n_act) sum += expf(l[k] - m);
     const float lse = m + logf(sum);
     // uniform in [0,1) from the counter-based generator; inverse CDF over the probabilities
+    if (offset_dev) offset += *offset_dev;
     const uint32_t r = pb_mix32(seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull + (uint64_t)i * 0x2545F4914F6CDD1Dull);
     const float u = (float)(r >> 8) * (1.0f / 16777216.0f);
     float cdf = 0.f, ent = 0.f, lp_a = 0.f;
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(256) k_sample_logits(const float* __restrict__
 }  // namespace
 
 extern "C" int pb_sample_logits(const float* logits, int64_t n, int32_t n_act, uint64_t seed, uint64_t offset,
-                                int64_t* actions, float* logprobs, float* entropies, const float* value,
+                                const uint64_t* offset_dev, int64_t* actions, float* logprobs, float* entropies,
+                                const float* value,
                                 float* values_row, float* logprobs_row, int64_t* actions_row, void* stream) {
     PB_REQUIRE(n >= 0, PB_ERR_INVALID, "pb_sample_logits: negative n");
     if (n == 0) return PB_OK;
@@ -69,7 +71,7 @@ extern "C" int pb_sample_logits(const float* logits, int64_t n, int32_t n_act, u
     PB_REQUIRE(n_act >= 1 && n_act <= MAX_ACT, PB_ERR_UNSUPPORTED, "pb_sample_logits: n_act must be in [1, %d]", MAX_ACT);
     PB_REQUIRE(!values_row || value, PB_ERR_INVALID, "pb_sample_logits: values_row given without value");
     k_sample_logits<<<(unsigned)pb_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        logits, n, n_act, seed, offset, actions, logprobs, entropies, value, values_row, logprobs_row, actions_row);
+        logits, n, n_act, seed, offset, offset_dev, actions, logprobs, entropies, value, values_row, logprobs_row, actions_row);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

@@ -43,7 +43,7 @@ class Policy(torch.nn.Module):
         self.policy = policy
         self.fused_sample = fused_sample
         self._seed = int(seed)
-        self._offset = 0
+        self._counter = None     # device-side draw counter: CUDA-graph replays keep drawing fresh numbers
 
     def get_value(self, x, state=None):
         _, value = self.policy(x)
@@ -62,10 +62,13 @@ class Policy(torch.nn.Module):
         actions = torch.empty(n, dtype=torch.int64, device=logits.device)
         logprob = torch.empty(n, dtype=torch.float32, device=logits.device)
         ent = torch.empty(n, dtype=torch.float32, device=logits.device)
+        if self._counter is None:
+            self._counter = torch.zeros(1, dtype=torch.int64, device=logits.device)
         _native.check(_native.lib().pb_sample_logits(
-            _native.ptr(logits), n, a, C.c_uint64(self._seed), C.c_uint64(self._offset), _native.ptr(actions),
-            _native.ptr(logprob), _native.ptr(ent), None, None, None, None, _native.stream_ptr()))
-        self._offset += 1
+            _native.ptr(logits), n, a, C.c_uint64(self._seed), C.c_uint64(0), _native.ptr(self._counter),
+            _native.ptr(actions), _native.ptr(logprob), _native.ptr(ent), None, None, None, None,
+            _native.stream_ptr()))
+        self._counter.add_(1)
         return actions, logprob, ent
 
     def forward(self, x, action=None):

@@ -299,6 +299,14 @@ class B200:
                 return (hn.observations, hn.rewards, hn.terminals, hn.truncations, infos, self.agent_ids, hn.masks)
         return (obs, rewards, b.terminals, b.truncations, infos, self.agent_ids, b.masks)
 
+    def pinned(self, array):
+        """The pinned torch tensor behind one of the numpy arrays recv() returned in host_buffers mode (so the
+        caller's H2D copy is a true async pinned transfer)."""
+        for k, v in self._host_np.items():
+            if v is array:
+                return self._host[k]
+        return torch.as_tensor(array)
+
     def _collect_infos(self):
         """Per-env info dicts for rows that just ended an episode (EpisodeStats, postprocess.py:36-52), in env
         order like Serial.send (vector.py:153-154).  Costs one D2H of the terminal flags per recv."""

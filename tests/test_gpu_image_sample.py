@@ -52,7 +52,7 @@ def test_sample_logits_logprob_entropy_match_torch(n, n_act):
     value = torch.randn(n, device=dev)
     vr, lr, ar = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, dtype=torch.int64, device=dev)
     _native.check(_native.lib().pb_sample_logits(
-        _native.ptr(logits), n, n_act, C.c_uint64(7), C.c_uint64(3), _native.ptr(actions), _native.ptr(logprob),
+        _native.ptr(logits), n, n_act, C.c_uint64(7), C.c_uint64(3), None, _native.ptr(actions), _native.ptr(logprob),
         _native.ptr(ent), _native.ptr(value), _native.ptr(vr), _native.ptr(lr), _native.ptr(ar), _native.stream_ptr()))
     assert int(actions.min()) >= 0 and int(actions.max()) < n_act
     _, ref_lp, ref_ent = cleanrl.sample_logits(logits, action=actions)      # torch formulation, same actions
@@ -71,7 +71,7 @@ def test_sample_logits_distribution():
     acts = []
     for off in (0, 1):
         a = torch.empty(n, dtype=torch.int64, device=dev)
-        _native.check(_native.lib().pb_sample_logits(_native.ptr(logits), n, n_act, C.c_uint64(1), C.c_uint64(off),
+        _native.check(_native.lib().pb_sample_logits(_native.ptr(logits), n, n_act, C.c_uint64(1), C.c_uint64(off), None,
                                                      _native.ptr(a), None, None, None, None, None, None,
                                                      _native.stream_ptr()))
         acts.append(a)
