@@ -9,7 +9,7 @@ import os
 from pufferlib_b200.exceptions import APIUsageError
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, 'libpuffer_b200.so')
+SO_PATH = os.environ.get('PUFFERLIB_B200_SO', os.path.join(HERE, 'libpuffer_b200.so'))   # override: debug builds
 
 PB_OK, PB_ERR_INVALID, PB_ERR_CUDA, PB_ERR_STATE, PB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 ENV_KINDS = {'squared': 0, 'breakout': 1, 'snake': 2, 'pong': 3}

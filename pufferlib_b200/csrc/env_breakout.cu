@@ -6,9 +6,10 @@
 //
 // Layout: per-env state is 28 B of SoA in HBM (two packed words, a uint4 brick bitmap, the draw counter),
 // reloaded each step because the policy forward sits between steps.  One lane owns one env for the integer
-// physics; the 32 envs of a warp then emit their 512-byte observation rows cooperatively -- per row each lane
-// builds one float4 (lane 0-1: the 8 header scalars, lanes 2-31: 4 bricks each from the shuffled bitmap) so every
-// row is ONE fully coalesced 512 B warp store (4 x 128 B lines).  Reward / flag / done rows are [N]-contiguous.
+// physics (EPW = 8 envs per warp, so N = 16384 still fills the chip with 2048 warps); the envs of a warp then emit
+// their 512-byte observation rows cooperatively -- per row each lane builds one float4 (lane 0-1: the 8 header
+// scalars, lanes 2-31: 4 bricks each from the shuffled bitmap) so every row is ONE fully coalesced 512 B warp store
+// (4 x 128 B lines).  Reward / flag / done rows are [N]-contiguous.
 #include "env_common.cuh"
 
 namespace {
@@ -39,12 +40,16 @@ __device__ __forceinline__ uint32_t bk_draw(uint64_t seed_e, uint32_t& ctr) {
 }
 
 // MODE 0: async_reset rows for every env;  MODE 1: vectoriser send (reset-or-step)
+constexpr int EPW = 8;   // envs per warp: lanes 0..7 own one env each, all 32 lanes write the rows
+
 template <int MODE>
 __global__ void __launch_bounds__(128) k_breakout(BreakoutState st, int n, const int64_t* __restrict__ actions,
                                                  uint8_t* done, BkOut out, EpisodeAcc acc) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const bool active = e < n;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int e_base = warp * EPW;
+    const int e = e_base + lane;
+    const bool active = lane < EPW && e < n;
     int px = 68, lives = 5, in_play = 0, wait = 0, vx = 0, vy = 0, bx = 79, by = 188, tick = 0;
     uint4 bricks = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0x00ffffffu);
     uint32_t ctr = 0;
@@ -126,11 +131,10 @@ __global__ void __launch_bounds__(128) k_breakout(BreakoutState st, int n, const
 
     // ---- observation rows: 32 envs per warp, one coalesced 512 B store per env
     const int left_mine = __popc(bricks.x) + __popc(bricks.y) + __popc(bricks.z) + __popc(bricks.w);
-    const int e_base = e - lane;
     const int word_sel = (lane >= 2) ? ((4 * lane - 8) >> 5) : 0;   // which bitmap word this lane decodes
     const int bit0 = (4 * lane - 8) & 31;
-#pragma unroll 4
-    for (int j = 0; j < 32; ++j) {
+#pragma unroll
+    for (int j = 0; j < EPW; ++j) {
         if (e_base + j >= n) break;
         const int jpx = __shfl_sync(0xffffffffu, px, j), jbx = __shfl_sync(0xffffffffu, bx, j);
         const int jby = __shfl_sync(0xffffffffu, by, j), jvx = __shfl_sync(0xffffffffu, vx, j);
@@ -161,7 +165,7 @@ int breakout_launch(pb_env* env, int mode, const int64_t* actions, const pb_env_
                "breakout: obs pointer/stride must be 16-byte aligned");
     BkOut o{(float*)out->obs, out->obs_stride / 4, out->rewards, out->terminals, out->truncations, out->masks,
             out->dones_f32};
-    const int blocks = (int)pb_ceil_div(n, 128);
+    const int blocks = (int)pb_ceil_div(n, (128 / 32) * EPW);
     if (mode == 0) k_breakout<0><<<blocks, 128, 0, s>>>(*st, n, actions, env->d_done, o, pb_episode_acc(env));
     else k_breakout<1><<<blocks, 128, 0, s>>>(*st, n, actions, env->d_done, o, pb_episode_acc(env));
     PB_LAUNCH_CHECK();

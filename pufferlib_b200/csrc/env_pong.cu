@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(PG_THREADS) k_pong(PongState st, int n, const 
             p.ctr = st.ctr[e];
             int a = (int)actions[e];
             a = a < 0 ? 0 : (a > 5 ? 5 : a);
-            if (a == 2 || a == 4) p.ry = max(p.ry - 3, 0);
-            if (a == 3 || a == 5) p.ry = min(p.ry + 3, 72);
+            // dy+3 per action, 3 bits each: NOOP, FIRE -> 0; UP(2,4) -> -3; DOWN(3,5) -> +3   (oracle/SPEC.md §Pong)
+            p.ry = min(max(p.ry + (int)((0x30C1Bu >> (3 * a)) & 7u) - 3, 0), 72);
             const int tgt = min(max(p.by - 5, 0), 72);
             if (p.ly < tgt) p.ly = min(p.ly + 2, tgt);
             else if (p.ly > tgt) p.ly = max(p.ly - 2, tgt);

@@ -232,7 +232,11 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae(GaeParams p) {
                 uint32_t fl = 2u;
                 float jP = 0.f, jQ = 0.f;  // beyond the last tile: inclusive value 0
                 if (j < p.numTiles) {
-                    do { fl = pb_ld_acquire(&st[j].flag); } while (fl == 0u);
+                    uint32_t polls = 0;
+                    do {
+                        fl = pb_ld_acquire(&st[j].flag);
+                        if (++polls == (1u << 27)) __trap();   // seconds of polling: abort rather than hang the GPU
+                    } while (fl == 0u);
                     // status words share 128 B lines with their neighbours: read through L2 (.cg), never a stale L1 line
                     if (fl == 2u) { jP = __ldcg(&st[j].X); jQ = 0.f; }
                     else { jP = __ldcg(&st[j].P); jQ = __ldcg(&st[j].Q); }

@@ -68,7 +68,7 @@ def compare_run(kind, n, h, seed, env_kwargs, bound=False, offset=0, check_infos
 @pytest.mark.parametrize('n', [1, 37, 1024])
 def test_env_vs_oracle_fast_episodes(kind, n):
     """Short episodes (small max_ticks / max_score) so auto-resets, reset rows and infos are all exercised."""
-    eps = compare_run(kind, n, h=200 if n < 1024 else 80, seed=3 + n, env_kwargs=FAST_END[kind])
+    eps = compare_run(kind, n, h=200 if n < 1024 else 160, seed=3 + n, env_kwargs=FAST_END[kind])
     assert eps > 0
 
 
