@@ -52,17 +52,20 @@ def parse_args():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--minibatches', type=int, default=4, help='batch_size / minibatch_size (reference ratio: 4)')
+    ap.add_argument('--epochs', type=int, default=4)
+    ap.add_argument('--kernels-only', action='store_true', help='skip the PPO loop; report the per-kernel rooflines')
     ap.add_argument('--ref-horizon', type=int, default=8, help='bounded sample: env steps per reference-arm step')
     return ap.parse_args()
 
 
-def ppo_config(num_envs, horizon, device, seed=1, cuda_graph=True):
+def ppo_config(num_envs, horizon, device, seed=1, cuda_graph=True, minibatches=4, epochs=4, env='breakout'):
     import pufferlib_b200
     batch = num_envs * horizon
     return pufferlib_b200.namespace(
-        seed=seed, torch_deterministic=True, env='breakout', batch_size=batch, bptt_horizon=16,
-        minibatch_size=batch // 4, cpu_offload=False, device=device, compile=False, learning_rate=2.5e-4,
-        gamma=0.99, gae_lambda=0.95, update_epochs=4, norm_adv=True, clip_coef=0.1, clip_vloss=True,
+        seed=seed, torch_deterministic=True, env=env, batch_size=batch, bptt_horizon=16,
+        minibatch_size=batch // minibatches, cpu_offload=False, device=device, compile=False, learning_rate=2.5e-4,
+        gamma=0.99, gae_lambda=0.95, update_epochs=epochs, norm_adv=True, clip_coef=0.1, clip_vloss=True,
         vf_clip_coef=0.1, vf_coef=0.5, ent_coef=0.01, max_grad_norm=0.5, target_kl=None, anneal_lr=False,
         total_timesteps=10_000_000_000, cuda_graph=cuda_graph)
 
@@ -121,10 +124,12 @@ def make_b200(args, rank, world, host_buffers, cuda_graph):
                     backend=pvec.B200.options(host_buffers=host_buffers, exact_infos=False,
                                               env_index_offset=rank * n))
     torch.manual_seed(1)
-    policy = cleanrl.Policy(models.Default(vec.driver_env, hidden_size=args.hidden), fused_sample=True, seed=1 + rank)
+    net = models.Convolutional(vec.driver_env) if args.env == 'pong' else models.Default(vec.driver_env, hidden_size=args.hidden)
+    policy = cleanrl.Policy(net, fused_sample=True, seed=1 + rank)
     policy = policy.cuda()
     pdist.broadcast_parameters(policy)
-    cfg = ppo_config(n, args.horizon, 'cuda', seed=1, cuda_graph=cuda_graph)
+    cfg = ppo_config(n, args.horizon, 'cuda', seed=1, cuda_graph=cuda_graph, minibatches=args.minibatches,
+                     epochs=args.epochs, env=args.env)
     data = clean_pufferl.create(cfg, vec, policy)
     return data, clean_pufferl
 
@@ -188,8 +193,11 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     for i in range(h):
         env_step(i)
     t_env = time_launches(env_step, h)
-    bytes_env = n * (o + 16)
-    out['env_step'] = dict(kernel='k_breakout<1>', bytes_per_launch=bytes_env, seconds=t_env,
+    # algorithmic bytes per agent-step: obs row + reward + done + action; snake also reads the
+    # previous row (the obs is the state), pong reads the three surviving frames of it
+    extra = {'snake': o, 'pong': 3 * (o // 4)}.get(args.env, 0)
+    bytes_env = n * (o + 16 + extra)
+    out['env_step'] = dict(kernel=f'k_{args.env}<1>', bytes_per_launch=bytes_env, seconds=t_env,
                            launches_per_step=h)
 
     # GAE (+returns): 20 B per agent-step.  8 rotating input/output sets (8 x 42 MB > the 126 MB L2) so every launch
@@ -252,6 +260,14 @@ def run_b200(args):
     torch.cuda.set_device(local)
     n, h = args.num_envs, args.horizon
     data, cp = make_b200(args, rank, world, host_buffers=False, cuda_graph=not args.no_graph)
+    if args.kernels_only:   # per-kernel HBM rooflines of another config (C3 snake, C4 pong) without the PPO loop
+        peak, peak_src = load_peak()
+        roof, roof_all = kernel_rooflines(data, args, peak, peak_src)
+        if rank == 0:
+            print(json.dumps({'kernels_only': True, 'config': {'workload': f'{args.env} num_envs={n} horizon={h}'},
+                              'roofline': roof, 'roofline_kernels': roof_all}))
+        cp.close(data)
+        return
     for _ in range(max(args.warmup, 3)):
         cp.evaluate(data)
         cp.train(data)
@@ -296,7 +312,7 @@ def run_b200(args):
             'data': 'synthetic (fixed-seed envs, random-init policy)',
             'config': {'workload': f'{args.env} num_envs={n}/GPU horizon={h} MLP hidden={args.hidden} '
                                    f'(BASELINE.json configs[1]; x{world} ranks = configs[4])',
-                       'global_batch': world * n * h, 'minibatch_size': n * h // 4, 'update_epochs': 4,
+                       'global_batch': world * n * h, 'minibatch_size': n * h // args.minibatches, 'update_epochs': args.epochs,
                        'bptt_horizon': 16, 'parallelism': f'dp{world} (env shards + 1 NCCL grad all-reduce/step)',
                        'l2': 'inputs larger than L2 (1 GiB rollout rotates; no flush needed)',
                        'cuda_graph_rollout': not args.no_graph},

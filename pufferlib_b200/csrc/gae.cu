@@ -8,18 +8,20 @@
 //
 // Data layout: inputs are the arrival-order rollout tensors x[t*N + e] (time-major); the sorted order is never
 // materialised.  A tile is a contiguous f-range: E whole envs (E a power of two, all H steps) or, for N == 1 /
-// very long horizons, a flat chunk.  The loader walks the tile with e fastest, so every warp load is a run of E
-// consecutive floats of one time row (coalesced, full 32 B sectors for E >= 8), and transposes through shared
-// memory (row pitch H|1: conflict-free for both the e-fastest stores and the f-order reads).  Each warp scans
-// its 32-element rounds with shuffles, (P,Q) partials stay in registers, tiles chain through a 16-byte status
-// word each (aggregate / inclusive) with a warp-wide look-back window that stops as soon as the accumulated
-// slope is exactly 0 (any done flag, or (gamma*lambda)^k underflow).  Outputs are written in sorted order,
-// 128 B per warp store.  HBM traffic = 12 B read + 4 (or 8 with returns) B written per agent-step.
+// very long horizons, a flat chunk.  PERSISTENT blocks (one wave, no tail) claim tiles by atomic ticket in suffix
+// order and double-buffer them: the loader walks a tile with e fastest -- every warp request is runs of E
+// consecutive floats of one time row (full 32 B sectors for E >= 8) -- and lands the data transposed in shared
+// memory with cp.async (LDGSTS, no register staging; row pitch H|1 is conflict-free for the f-order reads), so the
+// loads of tile k+1 are in flight while tile k is scanned.  Each warp scans its 32-element rounds with shuffles,
+// (P,Q) partials stay in registers, tiles chain through a 16-byte status word each (aggregate / inclusive) with a
+// warp-wide look-back window that stops as soon as the accumulated slope is exactly 0 (any done flag, or
+// (gamma*lambda)^k underflow).  Outputs are written in sorted order, 128 B per warp store.
+// HBM traffic = 12 B read + 4 (or 8 with returns) B written per agent-step.
 #include "pb_common.cuh"
 
 namespace {
 
-constexpr int GAE_THREADS = 256;
+constexpr int GAE_THREADS = 128;
 constexpr int GAE_WARPS = GAE_THREADS / 32;
 
 struct __align__(16) GaeStatus {
@@ -28,7 +30,7 @@ struct __align__(16) GaeStatus {
 };
 
 struct GaeHeader {
-    uint32_t ticket, done, pad0, pad1;
+    uint32_t ticket, exited, pad0, pad1;
 };
 
 struct GaeParams {
@@ -54,251 +56,293 @@ __device__ __forceinline__ void compose(float& a, float& b, float a2, float b2) 
     b = b * b2;
 }
 
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct TileGeom {
+    int64_t f0, e0;
+    int Lt, Et;
+};
+
+__device__ __forceinline__ TileGeom tile_geom(const GaeParams& p, int tile) {
+    TileGeom g;
+    if (p.E > 0) {
+        g.e0 = (int64_t)tile * p.E;
+        g.Et = (int)min((int64_t)p.E, p.N - g.e0);
+        g.f0 = g.e0 * p.H;
+        g.Lt = g.Et * (int)p.H;
+    } else {
+        g.e0 = 0; g.Et = 0;
+        g.f0 = (int64_t)tile * p.L;
+        g.Lt = (int)min((int64_t)p.L, p.B - g.f0);
+    }
+    return g;
+}
+
+// Asynchronously load one tile (transposing) + its halo element into a shared-memory buffer.
+__device__ __forceinline__ void load_tile(const GaeParams& p, const TileGeom& g, float* sR, float* sV, float* sD,
+                                          float* halo) {
+    const int tid = threadIdx.x;
+    if (p.E > 0) {
+        const int total = p.E * (int)p.H, mask = p.E - 1;
+        for (int idx = tid; idx < total; idx += GAE_THREADS) {
+            const int el = idx & mask, t = idx >> p.logE;
+            if (el < g.Et) {
+                const int64_t a = (int64_t)t * p.N + g.e0 + el;
+                const int sp = el * p.pitch + t;
+                cp_async4(sR + sp, p.r + a);
+                cp_async4(sV + sp, p.v + a);
+                cp_async4(sD + sp, p.d + a);
+            }
+        }
+    } else if (p.N == 1) {
+        for (int idx = tid; idx < g.Lt; idx += GAE_THREADS) {
+            cp_async4(sR + idx, p.r + g.f0 + idx);
+            cp_async4(sV + idx, p.v + g.f0 + idx);
+            cp_async4(sD + idx, p.d + g.f0 + idx);
+        }
+    } else {  // long-horizon fallback: strided gathers
+        for (int idx = tid; idx < g.Lt; idx += GAE_THREADS) {
+            const int64_t f = g.f0 + idx, e = f / p.H, t = f - e * p.H;
+            const int64_t a = t * p.N + e;
+            cp_async4(sR + idx, p.r + a);
+            cp_async4(sV + idx, p.v + a);
+            cp_async4(sD + idx, p.d + a);
+        }
+    }
+    if (tid == 0) {  // halo: the element after the tile (the chain crosses env and tile boundaries)
+        const int64_t fn = g.f0 + g.Lt;
+        if (fn < p.B) {
+            const int64_t e = fn / p.H, t = fn - e * p.H;
+            const int64_t a = t * p.N + e;
+            cp_async4(halo + 0, p.r + a);
+            cp_async4(halo + 1, p.v + a);
+            cp_async4(halo + 2, p.d + a);
+        } else {
+            halo[0] = 0.f; halo[1] = 0.f; halo[2] = 1.f;
+        }
+    }
+    cp_async_commit();
+}
+
 template <int RW>
 __global__ void __launch_bounds__(GAE_THREADS) k_gae(GaeParams p) {
     extern __shared__ float smem[];
-    __shared__ int s_tile;
-    __shared__ float s_halo[3];
+    __shared__ int s_ticket[2];
+    __shared__ float s_halo[2][4];
     __shared__ float s_wP[GAE_WARPS], s_wQ[GAE_WARPS];
     __shared__ float s_carry;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = p.numTiles - 1 - (int)atomicAdd(&p.hdr->ticket, 1u);  // suffix order: last tile first
-    __syncthreads();
-    const int tile = s_tile;
-
-    // ---- tile geometry
-    int64_t f0;       // first sorted index of the tile
-    int Lt;           // elements in this tile
-    int64_t e0 = 0;   // first env (E-mode)
-    int Et = 0;       // envs in this tile (E-mode)
     const bool emode = p.E > 0;
-    if (emode) {
-        e0 = (int64_t)tile * p.E;
-        Et = (int)min((int64_t)p.E, p.N - e0);
-        f0 = e0 * p.H;
-        Lt = Et * (int)p.H;
-    } else {
-        f0 = (int64_t)tile * p.L;
-        Lt = (int)min((int64_t)p.L, p.B - f0);
-    }
     const int stride_arr = emode ? p.E * p.pitch : p.L;
-    float* sR = smem;
-    float* sV = smem + stride_arr;
-    float* sD = smem + 2 * stride_arr;
-
-    // ---- load (transposing) : arrival order x[t*N+e] -> shared [e_local][t]
-    if (emode) {
-        const int total = p.E * (int)p.H;
-        const int mask = p.E - 1;
-#pragma unroll 4
-        for (int idx = tid; idx < total; idx += GAE_THREADS) {
-            const int el = idx & mask, t = idx >> p.logE;
-            if (el < Et) {
-                const int64_t g = (int64_t)t * p.N + e0 + el;
-                const int sp = el * p.pitch + t;
-                sR[sp] = __ldcs(p.r + g);
-                sV[sp] = __ldcs(p.v + g);
-                sD[sp] = __ldcs(p.d + g);
-            }
-        }
-    } else if (p.N == 1) {
-#pragma unroll 4
-        for (int idx = tid; idx < Lt; idx += GAE_THREADS) {
-            sR[idx] = __ldcs(p.r + f0 + idx);
-            sV[idx] = __ldcs(p.v + f0 + idx);
-            sD[idx] = __ldcs(p.d + f0 + idx);
-        }
-    } else {  // long-horizon fallback: strided gathers
-        for (int idx = tid; idx < Lt; idx += GAE_THREADS) {
-            const int64_t f = f0 + idx, e = f / p.H, t = f - e * p.H;
-            const int64_t g = t * p.N + e;
-            sR[idx] = p.r[g];
-            sV[idx] = p.v[g];
-            sD[idx] = p.d[g];
-        }
-    }
-    if (tid == 0) {  // halo: the element after the tile (the chain crosses env and tile boundaries)
-        const int64_t fn = f0 + Lt;
-        if (fn < p.B) {
-            const int64_t e = fn / p.H, t = fn - e * p.H;
-            const int64_t g = t * p.N + e;
-            s_halo[0] = p.r[g];
-            s_halo[1] = p.v[g];
-            s_halo[2] = p.d[g];
-        } else {
-            s_halo[0] = s_halo[1] = 0.f;
-            s_halo[2] = 1.f;
-        }
-    }
-    __syncthreads();
-
-    // ---- per-element maps into registers
-    const int R = (Lt + 31) >> 5;                 // rounds of 32 in this tile
-    const int Rw = (R + GAE_WARPS - 1) / GAE_WARPS;  // rounds per warp (<= RW)
-    const int r_begin = warp * Rw;
-    float a[RW], b[RW];
+    const int buf_floats = 3 * stride_arr;
     const int dp = p.pitch - (int)p.H;            // shared index = i + (i / H) * dp   (E-mode)
-#pragma unroll
-    for (int k = 0; k < RW; ++k) {
-        const int i = ((r_begin + k) << 5) + lane;
-        a[k] = 0.f;
-        b[k] = 1.f;  // identity for padding lanes
-        if (k < Rw && i < Lt) {
-            int sp0 = i, sp1 = i + 1;
-            if (emode) {
-                sp0 = i + (int)__umulhi((uint32_t)i, p.magicH) * dp;
-                sp1 = i + 1 + (int)__umulhi((uint32_t)(i + 1), p.magicH) * dp;
-            }
-            float r1, v1, d1;
-            if (i + 1 < Lt) {
-                r1 = sR[sp1];
-                v1 = sV[sp1];
-                d1 = sD[sp1];
-            } else {
-                r1 = s_halo[0];
-                v1 = s_halo[1];
-                d1 = s_halo[2];
-            }
-            const float v0 = sV[sp0];
-            const float nnt = __fsub_rn(1.0f, d1);
-            // c_gae.pyx:28-29 association, no FMA contraction inside an element
-            a[k] = __fsub_rn(__fadd_rn(r1, __fmul_rn(__fmul_rn(p.gamma, v1), nnt)), v0);
-            b[k] = __fmul_rn(p.gl, nnt);
-            if (f0 + i == p.B - 1) {  // A[B-1] = 0
-                a[k] = 0.f;
-                b[k] = 0.f;
-            }
-        }
-    }
 
-    // ---- warp-level suffix scan, rounds from last to first; (a,b) become tile-local partials (P,Q) w.r.t. the
-    //      value entering this warp's range from the right
-    float cP = 0.f, cQ = 1.f;
-#pragma unroll
-    for (int k = RW - 1; k >= 0; --k) {
-        if (k < Rw) {
-            float x = a[k], y = b[k];
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const float x2 = __shfl_down_sync(0xffffffffu, x, off);
-                const float y2 = __shfl_down_sync(0xffffffffu, y, off);
-                if (lane + off < 32) compose(x, y, x2, y2);
-            }
-            compose(x, y, cP, cQ);
-            a[k] = x;
-            b[k] = y;
-            cP = __shfl_sync(0xffffffffu, x, 0);
-            cQ = __shfl_sync(0xffffffffu, y, 0);
-        }
-    }
-    if (lane == 0) {
-        s_wP[warp] = cP;
-        s_wQ[warp] = cQ;
-    }
+    // ---- prologue: claim the first tile and start its loads
+    if (tid == 0) s_ticket[0] = (int)atomicAdd(&p.hdr->ticket, 1u);
     __syncthreads();
+    int ticket = s_ticket[0];
+    int cur = 0;
+    if (ticket < p.numTiles) {
+        const TileGeom g0 = tile_geom(p, p.numTiles - 1 - ticket);   // suffix order: last tile first
+        float* b0 = smem;
+        load_tile(p, g0, b0, b0 + stride_arr, b0 + 2 * stride_arr, s_halo[0]);
+    }
 
-    // ---- tile aggregate + decoupled look-back (warp 0)
-    if (warp == 0) {
-        float tP = 0.f, tQ = 1.f;  // composition of all warps, in order 0..7
-#pragma unroll
-        for (int w = GAE_WARPS - 1; w >= 0; --w) {
-            float x = s_wP[w], y = s_wQ[w];
-            compose(x, y, tP, tQ);
-            tP = x;
-            tQ = y;
-        }
-        GaeStatus* st = p.status;
-        float carry = 0.f;
-        if (tile == p.numTiles - 1) {
-            if (lane == 0) {
-                st[tile].X = tP;  // A beyond the batch is 0
-                __threadfence();
-                pb_st_release(&st[tile].flag, 2u);
-            }
+    while (ticket < p.numTiles) {
+        const int tile = p.numTiles - 1 - ticket;
+        const TileGeom g = tile_geom(p, tile);
+        float* sR = smem + cur * buf_floats;
+        float* sV = sR + stride_arr;
+        float* sD = sR + 2 * stride_arr;
+        const float* halo = s_halo[cur];
+
+        // ---- claim the next tile and put its loads in flight behind this tile's
+        if (tid == 0) s_ticket[cur ^ 1] = (int)atomicAdd(&p.hdr->ticket, 1u);
+        __syncthreads();
+        const int next_ticket = s_ticket[cur ^ 1];
+        if (next_ticket < p.numTiles) {
+            const TileGeom gn = tile_geom(p, p.numTiles - 1 - next_ticket);
+            float* bn = smem + (cur ^ 1) * buf_floats;
+            load_tile(p, gn, bn, bn + stride_arr, bn + 2 * stride_arr, s_halo[cur ^ 1]);
+            cp_async_wait<1>();      // everything but the newest group (the next tile) has landed
         } else {
-            if (lane == 0) {
-                st[tile].P = tP;
-                st[tile].Q = tQ;
-                __threadfence();
-                pb_st_release(&st[tile].flag, 1u);
-            }
-            // window of 32 successor tiles per iteration
-            float accP = 0.f, accQ = 1.f;  // composition of the tiles already walked
-            int base = tile + 1;
-            bool finished = false;
-            while (!finished) {
-                const int j = base + lane;
-                uint32_t fl = 2u;
-                float jP = 0.f, jQ = 0.f;  // beyond the last tile: inclusive value 0
-                if (j < p.numTiles) {
-                    uint32_t polls = 0;
-                    do {
-                        fl = pb_ld_acquire(&st[j].flag);
-                        if (++polls == (1u << 27)) __trap();   // seconds of polling: abort rather than hang the GPU
-                    } while (fl == 0u);
-                    // status words share 128 B lines with their neighbours: read through L2 (.cg), never a stale L1 line
-                    if (fl == 2u) { jP = __ldcg(&st[j].X); jQ = 0.f; }
-                    else { jP = __ldcg(&st[j].P); jQ = __ldcg(&st[j].Q); }
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        const int64_t f0 = g.f0;
+        const int Lt = g.Lt;
+        // ---- per-element maps into registers
+        const int R = (Lt + 31) >> 5;                    // rounds of 32 in this tile
+        const int Rw = (R + GAE_WARPS - 1) / GAE_WARPS;  // rounds per warp (<= RW)
+        const int r_begin = warp * Rw;
+        float a[RW], b[RW];
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+            const int i = ((r_begin + k) << 5) + lane;
+            a[k] = 0.f;
+            b[k] = 1.f;  // identity for padding lanes
+            if (k < Rw && i < Lt) {
+                int sp0 = i, sp1 = i + 1;
+                if (emode) {
+                    sp0 = i + (int)__umulhi((uint32_t)i, p.magicH) * dp;
+                    sp1 = i + 1 + (int)__umulhi((uint32_t)(i + 1), p.magicH) * dp;
                 }
-                // an inclusive tile or an exactly-zero slope ends the chain: A = P regardless of what follows
-                const unsigned stop = __ballot_sync(0xffffffffu, fl == 2u || jQ == 0.f);
-                const int last = stop ? (__ffs(stop) - 1) : 31;
-                float x = (lane <= last) ? jP : 0.f, y = (lane <= last) ? jQ : 1.f;
+                float r1, v1, d1;
+                if (i + 1 < Lt) {
+                    r1 = sR[sp1]; v1 = sV[sp1]; d1 = sD[sp1];
+                } else {
+                    r1 = halo[0]; v1 = halo[1]; d1 = halo[2];
+                }
+                const float v0 = sV[sp0];
+                const float nnt = __fsub_rn(1.0f, d1);
+                // c_gae.pyx:28-29 association, no FMA contraction inside an element
+                a[k] = __fsub_rn(__fadd_rn(r1, __fmul_rn(__fmul_rn(p.gamma, v1), nnt)), v0);
+                b[k] = __fmul_rn(p.gl, nnt);
+                if (f0 + i == p.B - 1) {  // A[B-1] = 0
+                    a[k] = 0.f;
+                    b[k] = 0.f;
+                }
+            }
+        }
+
+        // ---- warp-level suffix scan, rounds from last to first; (a,b) become tile-local partials (P,Q) w.r.t.
+        //      the value entering this warp's range from the right
+        float cP = 0.f, cQ = 1.f;
+#pragma unroll
+        for (int k = RW - 1; k >= 0; --k) {
+            if (k < Rw) {
+                float x = a[k], y = b[k];
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
                     const float x2 = __shfl_down_sync(0xffffffffu, x, off);
                     const float y2 = __shfl_down_sync(0xffffffffu, y, off);
                     if (lane + off < 32) compose(x, y, x2, y2);
                 }
-                x = __shfl_sync(0xffffffffu, x, 0);
-                y = __shfl_sync(0xffffffffu, y, 0);
-                compose(accP, accQ, x, y);
-                finished = stop != 0u;
-                base += 32;
-            }
-            carry = accP;  // accQ == 0 here: value of A at the first element after this tile
-            if (lane == 0) {
-                st[tile].X = fmaf(tQ, carry, tP);
-                __threadfence();
-                pb_st_release(&st[tile].flag, 2u);
+                compose(x, y, cP, cQ);
+                a[k] = x;
+                b[k] = y;
+                cP = __shfl_sync(0xffffffffu, x, 0);
+                cQ = __shfl_sync(0xffffffffu, y, 0);
             }
         }
-        if (lane == 0) s_carry = carry;
-    }
-    __syncthreads();
+        if (lane == 0) {
+            s_wP[warp] = cP;
+            s_wQ[warp] = cQ;
+        }
+        __syncthreads();
 
-    // ---- carry entering this warp's range = later warps' aggregates applied to the tile carry
-    float cin = s_carry;
-    for (int w = GAE_WARPS - 1; w > warp; --w) cin = fmaf(s_wQ[w], cin, s_wP[w]);
-
-    // ---- outputs in sorted order (coalesced 128 B per warp store)
+        // ---- tile aggregate + decoupled look-back (warp 0)
+        if (warp == 0) {
+            float tP = 0.f, tQ = 1.f;  // composition of all warps, in order 0..W-1
 #pragma unroll
-    for (int k = 0; k < RW; ++k) {
-        const int i = ((r_begin + k) << 5) + lane;
-        if (k < Rw && i < Lt) {
-            const float A = fmaf(b[k], cin, a[k]);
-            __stcs(p.adv + f0 + i, A);
-            if (p.ret) {
-                const int sp0 = emode ? i + (int)__umulhi((uint32_t)i, p.magicH) * dp : i;
-                __stcs(p.ret + f0 + i, A + sV[sp0]);
+            for (int w = GAE_WARPS - 1; w >= 0; --w) {
+                float x = s_wP[w], y = s_wQ[w];
+                compose(x, y, tP, tQ);
+                tP = x;
+                tQ = y;
+            }
+            GaeStatus* st = p.status;
+            float carry = 0.f;
+            if (tile == p.numTiles - 1) {
+                if (lane == 0) {
+                    st[tile].X = tP;  // A beyond the batch is 0
+                    __threadfence();
+                    pb_st_release(&st[tile].flag, 2u);
+                }
+            } else {
+                if (lane == 0) {
+                    st[tile].P = tP;
+                    st[tile].Q = tQ;
+                    __threadfence();
+                    pb_st_release(&st[tile].flag, 1u);
+                }
+                // window of 32 successor tiles per iteration
+                float accP = 0.f, accQ = 1.f;  // composition of the tiles already walked
+                int base = tile + 1;
+                bool finished = false;
+                while (!finished) {
+                    const int j = base + lane;
+                    uint32_t fl = 2u;
+                    float jP = 0.f, jQ = 0.f;  // beyond the last tile: inclusive value 0
+                    if (j < p.numTiles) {
+                        uint32_t polls = 0;
+                        do {
+                            fl = pb_ld_acquire(&st[j].flag);
+                            if (++polls == (1u << 27)) __trap();   // seconds of polling: abort rather than hang
+                        } while (fl == 0u);
+                        // status words share 128 B lines with their neighbours: read through L2 (.cg)
+                        if (fl == 2u) { jP = __ldcg(&st[j].X); jQ = 0.f; }
+                        else { jP = __ldcg(&st[j].P); jQ = __ldcg(&st[j].Q); }
+                    }
+                    // an inclusive tile or an exactly-zero slope ends the chain: A = P regardless of what follows
+                    const unsigned stop = __ballot_sync(0xffffffffu, fl == 2u || jQ == 0.f);
+                    const int last = stop ? (__ffs(stop) - 1) : 31;
+                    float x = (lane <= last) ? jP : 0.f, y = (lane <= last) ? jQ : 1.f;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const float x2 = __shfl_down_sync(0xffffffffu, x, off);
+                        const float y2 = __shfl_down_sync(0xffffffffu, y, off);
+                        if (lane + off < 32) compose(x, y, x2, y2);
+                    }
+                    x = __shfl_sync(0xffffffffu, x, 0);
+                    y = __shfl_sync(0xffffffffu, y, 0);
+                    compose(accP, accQ, x, y);
+                    finished = stop != 0u;
+                    base += 32;
+                }
+                carry = accP;  // accQ == 0 here: value of A at the first element after this tile
+                if (lane == 0) {
+                    st[tile].X = fmaf(tQ, carry, tP);
+                    __threadfence();
+                    pb_st_release(&st[tile].flag, 2u);
+                }
+            }
+            if (lane == 0) s_carry = carry;
+        }
+        __syncthreads();
+
+        // ---- carry entering this warp's range = later warps' aggregates applied to the tile carry
+        float cin = s_carry;
+        for (int w = GAE_WARPS - 1; w > warp; --w) cin = fmaf(s_wQ[w], cin, s_wP[w]);
+
+        // ---- outputs in sorted order (coalesced 128 B per warp store)
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+            const int i = ((r_begin + k) << 5) + lane;
+            if (k < Rw && i < Lt) {
+                const float A = fmaf(b[k], cin, a[k]);
+                __stcs(p.adv + f0 + i, A);
+                if (p.ret) {
+                    const int sp0 = emode ? i + (int)__umulhi((uint32_t)i, p.magicH) * dp : i;
+                    __stcs(p.ret + f0 + i, A + sV[sp0]);
+                }
             }
         }
+        __syncthreads();   // this buffer (and s_wP/s_wQ/s_carry) may be refilled from here on
+        ticket = next_ticket;
+        cur ^= 1;
     }
 
-    // ---- self-cleaning workspace: the last block to finish zeroes the header and every status word
-    __syncthreads();
+    // ---- self-cleaning workspace: the last block to leave zeroes the header and every status word
     if (tid == 0) {
         __threadfence();
-        const uint32_t prev = atomicAdd(&p.hdr->done, 1u);
-        s_tile = (prev == (uint32_t)p.numTiles - 1u) ? 1 : 0;
+        const uint32_t prev = atomicAdd(&p.hdr->exited, 1u);
+        s_ticket[0] = (prev == gridDim.x - 1u) ? 1 : 0;
     }
     __syncthreads();
-    if (s_tile) {
+    if (s_ticket[0]) {
         for (int j = tid; j < p.numTiles; j += GAE_THREADS) {
             p.status[j].P = 0.f; p.status[j].Q = 0.f; p.status[j].X = 0.f; p.status[j].flag = 0u;
         }
-        if (tid == 0) { p.hdr->ticket = 0u; p.hdr->done = 0u; }
+        if (tid == 0) { p.hdr->ticket = 0u; p.hdr->exited = 0u; }
     }
 }
 
@@ -311,7 +355,7 @@ struct GaePlan {
 GaePlan gae_plan(int64_t N, int64_t H) {
     GaePlan g{};
     const int64_t B = N * H;
-    const int Ltarget = 4096, Lmax = 8192;
+    const int Ltarget = 2048, Lmax = 4096;
     if (N > 1 && H * 8 <= Lmax) {
         int E = 8;
         while ((int64_t)E * 2 * H <= Ltarget) E *= 2;   // largest power of two with E*H <= Ltarget, at least 8
@@ -323,14 +367,14 @@ GaePlan gae_plan(int64_t N, int64_t H) {
         g.pitch = (int)(H | 1);
         g.magicH = (uint32_t)(((1ull << 32) + (uint64_t)H - 1) / (uint64_t)H);
         g.numTiles = (int)pb_ceil_div(N, E);
-        g.smem = (size_t)3 * E * g.pitch * sizeof(float);
+        g.smem = (size_t)2 * 3 * E * g.pitch * sizeof(float);   // double-buffered
     } else {
         g.E = 0;
         g.L = (int)(B < Ltarget ? (B > 0 ? B : 1) : Ltarget);
         g.pitch = 0;
         g.magicH = 0;
         g.numTiles = (int)pb_ceil_div(B, g.L);
-        g.smem = (size_t)3 * g.L * sizeof(float);
+        g.smem = (size_t)2 * 3 * g.L * sizeof(float);
     }
     const int R = (g.L + 31) / 32;
     const int Rw = (R + GAE_WARPS - 1) / GAE_WARPS;
@@ -366,13 +410,20 @@ extern "C" int pb_gae(const float* rewards, const float* values, const float* do
     p.hdr = (GaeHeader*)workspace;
     p.status = (GaeStatus*)((char*)workspace + sizeof(GaeHeader));
     cudaStream_t s = (cudaStream_t)stream;
+    // persistent grid: every resident slot of the chip, never more blocks than tiles (one wave, no tail)
+    int per_sm = 0;
     if (g.RW == 16) {
         PB_CUDA(cudaFuncSetAttribute(k_gae<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        k_gae<16><<<g.numTiles, GAE_THREADS, g.smem, s>>>(p);
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae<16>, GAE_THREADS, g.smem));
     } else {
         PB_CUDA(cudaFuncSetAttribute(k_gae<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-        k_gae<32><<<g.numTiles, GAE_THREADS, g.smem, s>>>(p);
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae<32>, GAE_THREADS, g.smem));
     }
+    PB_REQUIRE(per_sm >= 1, PB_ERR_CUDA, "pb_gae: kernel does not fit on an SM (smem %zu)", g.smem);
+    int grid = per_sm * PB_NUM_SMS;
+    if (grid > g.numTiles) grid = g.numTiles;
+    if (g.RW == 16) k_gae<16><<<grid, GAE_THREADS, g.smem, s>>>(p);
+    else k_gae<32><<<grid, GAE_THREADS, g.smem, s>>>(p);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

@@ -48,7 +48,10 @@ struct GatherGeom {
     int64_t N, H, n_mb, rows, bptt, mb_begin;
 };
 
-template <typename V, int ROWS_PER_ITER>
+// One warp moves 32 output rows per iteration.  Lane k does the (division-heavy) index arithmetic for row o0+k
+// once; the row byte offsets are then shuffle-broadcast and every row is copied by all 32 lanes, UNROLL rows at a
+// time with all loads issued before the first store (memory-level parallelism).
+template <typename V, int UNROLL>
 __global__ void __launch_bounds__(256) k_minibatch_gather(const char* __restrict__ obs, char* __restrict__ dst,
                                                          int64_t row_bytes, int row_vecs, int64_t n_out_rows,
                                                          GatherGeom g) {
@@ -56,26 +59,27 @@ __global__ void __launch_bounds__(256) k_minibatch_gather(const char* __restrict
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int64_t mb_size = g.rows * g.bptt;
-    for (int64_t o0 = warp * ROWS_PER_ITER; o0 < n_out_rows; o0 += nwarps * ROWS_PER_ITER) {
-        const V* s[ROWS_PER_ITER];
-        V* d[ROWS_PER_ITER];
+    for (int64_t o0 = warp * 32; o0 < n_out_rows; o0 += nwarps * 32) {
+        const int64_t o = min(o0 + lane, n_out_rows - 1);
+        const int64_t mb = g.mb_begin + o / mb_size, rem = o % mb_size;
+        const int64_t r = rem / g.bptt, j = rem - r * g.bptt;
+        const int64_t f = (r * g.n_mb + mb) * g.bptt + j;
+        const int64_t e = f / g.H, t = f - e * g.H;
+        const int64_t my_src = (t * g.N + e) * row_bytes;
+        const int rows_here = (int)min((int64_t)32, n_out_rows - o0);
+        for (int k0 = 0; k0 < rows_here; k0 += UNROLL) {
+            const V* s[UNROLL];
 #pragma unroll
-        for (int k = 0; k < ROWS_PER_ITER; ++k) {
-            const int64_t o = min(o0 + k, n_out_rows - 1);
-            const int64_t mb = g.mb_begin + o / mb_size, rem = o % mb_size;
-            const int64_t r = rem / g.bptt, j = rem - r * g.bptt;
-            const int64_t f = (r * g.n_mb + mb) * g.bptt + j;
-            const int64_t e = f / g.H, t = f - e * g.H;
-            s[k] = reinterpret_cast<const V*>(obs + (t * g.N + e) * row_bytes);
-            d[k] = reinterpret_cast<V*>(dst + o * row_bytes);
-        }
-        for (int c = lane; c < row_vecs; c += 32) {
-            V tmp[ROWS_PER_ITER];
+            for (int u = 0; u < UNROLL; ++u)
+                s[u] = reinterpret_cast<const V*>(obs + __shfl_sync(0xffffffffu, my_src, min(k0 + u, rows_here - 1)));
+            for (int c = lane; c < row_vecs; c += 32) {
+                V tmp[UNROLL];
 #pragma unroll
-            for (int k = 0; k < ROWS_PER_ITER; ++k) tmp[k] = __ldcs(s[k] + c);  // all loads first (MLP)
+                for (int u = 0; u < UNROLL; ++u) tmp[u] = __ldcs(s[u] + c);
 #pragma unroll
-            for (int k = 0; k < ROWS_PER_ITER; ++k)
-                if (o0 + k < n_out_rows) d[k][c] = tmp[k];
+                for (int u = 0; u < UNROLL; ++u)
+                    if (k0 + u < rows_here) reinterpret_cast<V*>(dst + (o0 + k0 + u) * row_bytes)[c] = tmp[u];
+            }
         }
     }
 }
@@ -290,8 +294,8 @@ extern "C" int pb_minibatch_gather(const void* obs, void* dst, int64_t row_bytes
         return pb_minibatch_gather_tma(obs, dst, row_bytes, num_envs, horizon, n_mb, rows, bptt, mb_begin, mb_count, s);
     const int64_t n_out = mb_count * rows * bptt;
     GatherGeom g{num_envs, horizon, n_mb, rows, bptt, mb_begin};
-    constexpr int RPI = 4;
-    int64_t blocks = pb_ceil_div(pb_ceil_div(n_out, RPI), 8);
+    constexpr int RPI = 8;   // rows in flight per warp
+    int64_t blocks = pb_ceil_div(pb_ceil_div(n_out, 32), 8);
     const int64_t cap = (int64_t)PB_NUM_SMS * 8;
     if (blocks > cap) blocks = cap;
     if (vb == 16)
