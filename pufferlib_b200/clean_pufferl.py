@@ -397,7 +397,7 @@ def evaluate(data):
         data.stats = {}
         if hasattr(vecenv, 'episode_stats') and not getattr(vecenv, 'exact_infos', False):
             means, count = vecenv.episode_stats(clear=True)    # device-side EpisodeStats reduction, one D2H
-            data.io.d2h += 32
+            data.io.d2h += 256 * 32
             for k, v in means.items():
                 infos[k].append(v)
         for k, v in infos.items():

@@ -41,15 +41,15 @@ int pb_env_alloc_common(pb_env* env) {
     PB_CUDA(cudaMalloc(&env->d_row_return, n * sizeof(double)));
     PB_CUDA(cudaMalloc(&env->d_row_length, n * sizeof(int32_t)));
     PB_CUDA(cudaMalloc(&env->d_row_score, n * sizeof(float)));
-    PB_CUDA(cudaMalloc(&env->d_stats, 4 * sizeof(double)));
-    PB_CUDA(cudaMallocHost(&env->h_stats_pinned, 4 * sizeof(double)));
+    PB_CUDA(cudaMalloc(&env->d_stats, PB_STAT_SLOTS * 4 * sizeof(double)));
+    PB_CUDA(cudaMallocHost(&env->h_stats_pinned, PB_STAT_SLOTS * 4 * sizeof(double)));
     PB_CUDA(cudaMemset(env->d_done, 1, n));  // GymnasiumPufferEnv starts with done = True (emulation.py:129)
     PB_CUDA(cudaMemset(env->d_ep_return, 0, n * sizeof(double)));
     PB_CUDA(cudaMemset(env->d_ep_length, 0, n * sizeof(int32_t)));
     PB_CUDA(cudaMemset(env->d_row_return, 0, n * sizeof(double)));
     PB_CUDA(cudaMemset(env->d_row_length, 0, n * sizeof(int32_t)));
     PB_CUDA(cudaMemset(env->d_row_score, 0, n * sizeof(float)));
-    PB_CUDA(cudaMemset(env->d_stats, 0, 4 * sizeof(double)));
+    PB_CUDA(cudaMemset(env->d_stats, 0, PB_STAT_SLOTS * 4 * sizeof(double)));
     return PB_OK;
 }
 
@@ -163,9 +163,12 @@ extern "C" int pb_env_stats_read(pb_env* env, double* out4_host, int clear, void
     PB_REQUIRE(env && out4_host, PB_ERR_INVALID, "pb_env_stats_read: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     PB_CUDA(cudaSetDevice(env->cfg.device));
-    PB_CUDA(cudaMemcpyAsync(env->h_stats_pinned, env->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (clear) PB_CUDA(cudaMemsetAsync(env->d_stats, 0, 4 * sizeof(double), s));
+    const size_t bytes = PB_STAT_SLOTS * 4 * sizeof(double);
+    PB_CUDA(cudaMemcpyAsync(env->h_stats_pinned, env->d_stats, bytes, cudaMemcpyDeviceToHost, s));
+    if (clear) PB_CUDA(cudaMemsetAsync(env->d_stats, 0, bytes, s));
     PB_CUDA(cudaStreamSynchronize(s));
-    memcpy(out4_host, env->h_stats_pinned, 4 * sizeof(double));
+    for (int k = 0; k < 4; ++k) out4_host[k] = 0.0;
+    for (int slot = 0; slot < PB_STAT_SLOTS; ++slot)
+        for (int k = 0; k < 4; ++k) out4_host[k] += env->h_stats_pinned[slot * 4 + k];
     return PB_OK;
 }

@@ -6,6 +6,8 @@
 #pragma once
 #include "pb_common.cuh"
 
+constexpr int PB_STAT_SLOTS = 256;
+
 struct pb_env_vtable {
     int (*reset)(pb_env*, uint64_t seed, const pb_env_out*, cudaStream_t);
     int (*step)(pb_env*, const int64_t* actions, const pb_env_out*, cudaStream_t);
@@ -24,8 +26,9 @@ struct pb_env {
     double* d_row_return;    // values of the episode that ended on the most recent step (valid where terminal)
     int32_t* d_row_length;
     float* d_row_score;
-    double* d_stats;         // [4] episodes, sum return, sum length, sum score
-    double* h_stats_pinned;  // [4] pinned staging for pb_env_stats_read
+    double* d_stats;         // [PB_STAT_SLOTS][4] episodes, sum return, sum length, sum score (slot = warp hash:
+                             // same-address atomics serialise in L2, spreading them keeps the step kernel flat)
+    double* h_stats_pinned;  // [PB_STAT_SLOTS][4] pinned staging for pb_env_stats_read
     // where the previous call wrote the observations (snake / pong carry state in the obs rows)
     const void* cur_obs;
     int64_t cur_obs_stride;
@@ -86,10 +89,12 @@ __device__ __forceinline__ void episode_update(const EpisodeAcc& acc, int64_t e,
             s += __shfl_xor_sync(0xffffffffu, s, off);
         }
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd(acc.stats + 0, (double)__popc(m));
-            atomicAdd(acc.stats + 1, r);
-            atomicAdd(acc.stats + 2, l);
-            atomicAdd(acc.stats + 3, s);
+            const unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+            double* slot = acc.stats + 4 * ((gw * 2654435761u) >> 24);   // 256 slots, multiplicative hash of the warp id
+            atomicAdd(slot + 0, (double)__popc(m));
+            atomicAdd(slot + 1, r);
+            atomicAdd(slot + 2, l);
+            atomicAdd(slot + 3, s);
         }
     }
 }

@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(PG_THREADS) k_pong(PongState st, int n, const 
                 if (terminal) {
                     const float score = (float)(p.score_r - p.score_l);
                     acc.row_return[e] = ret; acc.row_length[e] = len; acc.row_score[e] = score;
-                    atomicAdd(acc.stats + 0, 1.0); atomicAdd(acc.stats + 1, ret);
-                    atomicAdd(acc.stats + 2, (double)len); atomicAdd(acc.stats + 3, (double)score);
+                    double* slot = acc.stats + 4 * (blockIdx.x & (PB_STAT_SLOTS - 1));
+                    atomicAdd(slot + 0, 1.0); atomicAdd(slot + 1, ret);
+                    atomicAdd(slot + 2, (double)len); atomicAdd(slot + 3, (double)score);
                 }
             }
             unsigned char* row = out.obs + e * out.stride;

@@ -346,7 +346,270 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae(GaeParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path (N > 1, H in {128, 256, 512}): tile = 16 whole envs, 128 threads, each thread owns KC = H/128 chunks of 16
+// consecutive steps of one env.  A chunk is composed SERIALLY in registers (2 FMAs per element instead of a 5-step
+// shuffle scan), so the kernel issues ~30 thread-instructions per element instead of ~100.  Shared-memory layout
+// [env][t] with row pitch H+1: the e-fastest cp.async loader and the per-thread chunk walks are both conflict-free
+// (lanes 0-15 / 16-31 of a warp hold envs 0-15 of two adjacent chunks -> banks el+j and el+16+j).
+constexpr int FE = 16;   // envs per tile
+constexpr int FC = 16;   // steps per chunk
+
+__device__ __forceinline__ float tile_lookback(GaeStatus* st, int tile, int numTiles, float tP, float tQ, int lane) {
+    float carry = 0.f;
+    if (tile == numTiles - 1) {
+        if (lane == 0) {
+            st[tile].X = tP;  // A beyond the batch is 0
+            __threadfence();
+            pb_st_release(&st[tile].flag, 2u);
+        }
+        return 0.f;
+    }
+    if (lane == 0) {
+        st[tile].P = tP;
+        st[tile].Q = tQ;
+        __threadfence();
+        pb_st_release(&st[tile].flag, 1u);
+    }
+    float accP = 0.f, accQ = 1.f;
+    int base = tile + 1;
+    bool finished = false;
+    while (!finished) {
+        const int j = base + lane;
+        uint32_t fl = 2u;
+        float jP = 0.f, jQ = 0.f;
+        if (j < numTiles) {
+            uint32_t polls = 0;
+            do {
+                fl = pb_ld_acquire(&st[j].flag);
+                if (++polls == (1u << 27)) __trap();
+            } while (fl == 0u);
+            if (fl == 2u) { jP = __ldcg(&st[j].X); jQ = 0.f; }
+            else { jP = __ldcg(&st[j].P); jQ = __ldcg(&st[j].Q); }
+        }
+        const unsigned stop = __ballot_sync(0xffffffffu, fl == 2u || jQ == 0.f);
+        const int last = stop ? (__ffs(stop) - 1) : 31;
+        float x = (lane <= last) ? jP : 0.f, y = (lane <= last) ? jQ : 1.f;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float x2 = __shfl_down_sync(0xffffffffu, x, off);
+            const float y2 = __shfl_down_sync(0xffffffffu, y, off);
+            if (lane + off < 32) compose(x, y, x2, y2);
+        }
+        x = __shfl_sync(0xffffffffu, x, 0);
+        y = __shfl_sync(0xffffffffu, y, 0);
+        compose(accP, accQ, x, y);
+        finished = stop != 0u;
+        base += 32;
+    }
+    carry = accP;
+    if (lane == 0) {
+        st[tile].X = fmaf(tQ, carry, tP);
+        __threadfence();
+        pb_st_release(&st[tile].flag, 2u);
+    }
+    return carry;
+}
+
+template <int KC>   // chunks per thread: H = 128 * KC
+__global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
+    constexpr int H = 128 * KC;
+    constexpr int PITCH = H + 1;
+    constexpr int CE = H / FC;                 // chunks per env
+    constexpr int ARR = FE * PITCH;            // floats per array per buffer
+    extern __shared__ float smem[];            // 2 buffers x {r, v, d} x ARR
+    __shared__ int s_ticket[2];
+    __shared__ float s_halo[2][4];
+    __shared__ float2 s_cagg[FE][CE + 1];      // chunk aggregates, then chunk carry maps (w.r.t. the env's right end)
+    __shared__ float2 s_eagg[FE];              // env carry maps w.r.t. the tile's right end
+    __shared__ float s_carry;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // loader role: this thread always copies env el_ld, time rows t_ld, t_ld + 8, ...
+    const int el_ld = tid & (FE - 1), t_ld = tid >> 4;
+
+    auto issue_tile = [&](int tile, int buf) {
+        const int64_t e0 = (int64_t)tile * FE;
+        const int Et = (int)min((int64_t)FE, p.N - e0);
+        float* sR = smem + buf * 3 * ARR;
+        float* sV = sR + ARR;
+        float* sD = sV + ARR;
+        if (el_ld < Et) {
+            const int64_t g0 = (int64_t)t_ld * p.N + e0 + el_ld;
+            const int64_t gstep = 8 * p.N;
+            const float* pr = p.r + g0;
+            const float* pv = p.v + g0;
+            const float* pd = p.d + g0;
+            int sp = el_ld * PITCH + t_ld;
+#pragma unroll 8
+            for (int k = 0; k < H / 8; ++k) {
+                cp_async4(sR + sp, pr);
+                cp_async4(sV + sp, pv);
+                cp_async4(sD + sp, pd);
+                pr += gstep; pv += gstep; pd += gstep;
+                sp += 8;
+            }
+        }
+        if (tid == 0) {
+            const int64_t en = e0 + Et;          // first env after the tile, its t = 0 row sits at index en
+            if (en < p.N) {
+                cp_async4(&s_halo[buf][0], p.r + en);
+                cp_async4(&s_halo[buf][1], p.v + en);
+                cp_async4(&s_halo[buf][2], p.d + en);
+            } else {
+                s_halo[buf][0] = 0.f; s_halo[buf][1] = 0.f; s_halo[buf][2] = 1.f;
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (tid == 0) s_ticket[0] = (int)atomicAdd(&p.hdr->ticket, 1u);
+    __syncthreads();
+    int ticket = s_ticket[0];
+    int cur = 0;
+    if (ticket < p.numTiles) issue_tile(p.numTiles - 1 - ticket, 0);
+
+    while (ticket < p.numTiles) {
+        const int tile = p.numTiles - 1 - ticket;
+        const int64_t e0 = (int64_t)tile * FE;
+        const int Et = (int)min((int64_t)FE, p.N - e0);
+        const float* sR = smem + cur * 3 * ARR;
+        const float* sV = sR + ARR;
+        const float* sD = sV + ARR;
+        const float* halo = s_halo[cur];
+
+        if (tid == 0) s_ticket[cur ^ 1] = (int)atomicAdd(&p.hdr->ticket, 1u);
+        __syncthreads();
+        const int next_ticket = s_ticket[cur ^ 1];
+        if (next_ticket < p.numTiles) {
+            issue_tile(p.numTiles - 1 - next_ticket, cur ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        // ---- pass 1: per-chunk serial composition (suffix order), element maps kept in registers
+        float a[KC][FC], b[KC][FC];
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+            const int q = tid + kc * GAE_THREADS;          // chunk id: el = q % 16, c = q / 16
+            const int el = q & (FE - 1), c = q >> 4;
+            float P = 0.f, Q = 1.f;
+            if (el < Et) {
+                const float* rr = sR + el * PITCH + c * FC;
+                const float* vv = sV + el * PITCH + c * FC;
+                const float* dd = sD + el * PITCH + c * FC;
+                // the element after the chunk: next step of the env, next env's first step, or the tile halo
+                float rn, vn, dn;
+                if (c < CE - 1) { rn = rr[FC]; vn = vv[FC]; dn = dd[FC]; }
+                else if (el + 1 < Et) { rn = sR[(el + 1) * PITCH]; vn = sV[(el + 1) * PITCH]; dn = sD[(el + 1) * PITCH]; }
+                else { rn = halo[0]; vn = halo[1]; dn = halo[2]; }
+                const bool last_of_batch = (e0 + el == p.N - 1) && (c == CE - 1);
+#pragma unroll
+                for (int j = FC - 1; j >= 0; --j) {
+                    const float r0 = rr[j], v0 = vv[j], d0 = dd[j];
+                    const float nnt = __fsub_rn(1.0f, dn);
+                    // c_gae.pyx:28-29 association, no FMA contraction inside an element
+                    float aj = __fsub_rn(__fadd_rn(rn, __fmul_rn(__fmul_rn(p.gamma, vn), nnt)), v0);
+                    float bj = __fmul_rn(p.gl, nnt);
+                    if (last_of_batch && j == FC - 1) { aj = 0.f; bj = 0.f; }   // A[B-1] = 0
+                    a[kc][j] = aj;
+                    b[kc][j] = bj;
+                    P = fmaf(bj, P, aj);     // (aj,bj) o (P,Q)
+                    Q = bj * Q;
+                    rn = r0; vn = v0; dn = d0;
+                }
+                s_cagg[el][c] = make_float2(P, Q);
+            } else {
+#pragma unroll
+                for (int j = 0; j < FC; ++j) { a[kc][j] = 0.f; b[kc][j] = 1.f; }
+            }
+        }
+        __syncthreads();
+
+        // ---- pass 2 (warp 0): chunk carries inside each env, env carries inside the tile, then the look-back
+        if (warp == 0) {
+            float eP = 0.f, eQ = 1.f;                    // env aggregate (identity for missing envs)
+            if (lane < Et) {
+                float cP = 0.f, cQ = 1.f;                // composition of the chunks to the right, w.r.t. the env end
+                for (int c = CE - 1; c >= 0; --c) {
+                    const float2 g = s_cagg[lane][c];
+                    s_cagg[lane][c] = make_float2(cP, cQ);   // carry map entering chunk c from the right
+                    const float nP = fmaf(g.y, cP, g.x), nQ = g.y * cQ;
+                    cP = nP; cQ = nQ;
+                }
+                eP = cP; eQ = cQ;
+            }
+            // exclusive suffix over the 16 envs: map from the tile's right end to env el's right end
+            float x = eP, y = eQ;                        // inclusive first
+#pragma unroll
+            for (int off = 1; off < FE; off <<= 1) {
+                const float x2 = __shfl_down_sync(0xffffffffu, x, off);
+                const float y2 = __shfl_down_sync(0xffffffffu, y, off);
+                if (lane + off < FE) compose(x, y, x2, y2);
+            }
+            const float tP = __shfl_sync(0xffffffffu, x, 0), tQ = __shfl_sync(0xffffffffu, y, 0);
+            float exP = __shfl_down_sync(0xffffffffu, x, 1), exQ = __shfl_down_sync(0xffffffffu, y, 1);
+            if (lane >= FE - 1) { exP = 0.f; exQ = 1.f; }
+            if (lane < FE) s_eagg[lane] = make_float2(exP, exQ);
+            const float carry = tile_lookback(p.status, tile, p.numTiles, tP, tQ, lane);
+            if (lane == 0) s_carry = carry;
+        }
+        __syncthreads();
+
+        // ---- pass 3: apply carries, write outputs in sorted order (64 B per thread-chunk, full sectors)
+        const float C = s_carry;
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+            const int q = tid + kc * GAE_THREADS;
+            const int el = q & (FE - 1), c = q >> 4;
+            if (el < Et) {
+                const float2 em = s_eagg[el], cm = s_cagg[el][c];
+                const float a_env_end = fmaf(em.y, C, em.x);           // A just after this env
+                float A = fmaf(cm.y, a_env_end, cm.x);                 // A just after this chunk
+                const int64_t f = (e0 + el) * (int64_t)H + c * FC;
+                float outA[FC];
+#pragma unroll
+                for (int j = FC - 1; j >= 0; --j) {
+                    A = fmaf(b[kc][j], A, a[kc][j]);
+                    outA[j] = A;
+                }
+                float4* pa = reinterpret_cast<float4*>(p.adv + f);
+#pragma unroll
+                for (int j4 = 0; j4 < FC / 4; ++j4)
+                    __stcs(pa + j4, make_float4(outA[4 * j4], outA[4 * j4 + 1], outA[4 * j4 + 2], outA[4 * j4 + 3]));
+                if (p.ret) {
+                    const float* vv = sV + el * PITCH + c * FC;
+                    float4* pr = reinterpret_cast<float4*>(p.ret + f);
+#pragma unroll
+                    for (int j4 = 0; j4 < FC / 4; ++j4)
+                        __stcs(pr + j4, make_float4(outA[4 * j4] + vv[4 * j4], outA[4 * j4 + 1] + vv[4 * j4 + 1],
+                                                    outA[4 * j4 + 2] + vv[4 * j4 + 2], outA[4 * j4 + 3] + vv[4 * j4 + 3]));
+                }
+            }
+        }
+        __syncthreads();
+        ticket = next_ticket;
+        cur ^= 1;
+    }
+
+    if (tid == 0) {
+        __threadfence();
+        const uint32_t prev = atomicAdd(&p.hdr->exited, 1u);
+        s_ticket[0] = (prev == gridDim.x - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_ticket[0]) {
+        for (int j = tid; j < p.numTiles; j += GAE_THREADS) {
+            p.status[j].P = 0.f; p.status[j].Q = 0.f; p.status[j].X = 0.f; p.status[j].flag = 0u;
+        }
+        if (tid == 0) { p.hdr->ticket = 0u; p.hdr->exited = 0u; }
+    }
+}
+
 struct GaePlan {
+    int fastKC;   // > 0: k_gae_fast<fastKC>
     int E, logE, L, pitch, numTiles, RW;
     uint32_t magicH;
     size_t smem;
@@ -356,6 +619,14 @@ GaePlan gae_plan(int64_t N, int64_t H) {
     GaePlan g{};
     const int64_t B = N * H;
     const int Ltarget = 2048, Lmax = 4096;
+    if (N > 1 && (H == 128 || H == 256 || H == 512) ) {
+        g.fastKC = (int)(H / 128);
+        g.E = FE; g.logE = 4; g.L = FE * (int)H; g.pitch = (int)H + 1; g.magicH = 0;
+        g.numTiles = (int)pb_ceil_div(N, FE);
+        g.smem = (size_t)2 * 3 * FE * (H + 1) * sizeof(float);
+        g.RW = 16;
+        return g;
+    }
     if (N > 1 && H * 8 <= Lmax) {
         int E = 8;
         while ((int64_t)E * 2 * H <= Ltarget) E *= 2;   // largest power of two with E*H <= Ltarget, at least 8
@@ -412,6 +683,23 @@ extern "C" int pb_gae(const float* rewards, const float* values, const float* do
     cudaStream_t s = (cudaStream_t)stream;
     // persistent grid: every resident slot of the chip, never more blocks than tiles (one wave, no tail)
     int per_sm = 0;
+    if (g.fastKC > 0) {
+        PB_REQUIRE(((uintptr_t)advantages & 15) == 0 && (!returns_sorted || ((uintptr_t)returns_sorted & 15) == 0),
+                   PB_ERR_INVALID, "pb_gae: advantages / returns must be 16-byte aligned");
+#define PB_GAE_FAST(KC)                                                                                               \
+    {                                                                                                                 \
+        PB_CUDA(cudaFuncSetAttribute(k_gae_fast<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));     \
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae_fast<KC>, GAE_THREADS, g.smem));        \
+        PB_REQUIRE(per_sm >= 1, PB_ERR_CUDA, "pb_gae: kernel does not fit on an SM (smem %zu)", g.smem);              \
+        int grid = per_sm * PB_NUM_SMS;                                                                               \
+        if (grid > g.numTiles) grid = g.numTiles;                                                                     \
+        k_gae_fast<KC><<<grid, GAE_THREADS, g.smem, s>>>(p);                                                          \
+    }
+        if (g.fastKC == 1) PB_GAE_FAST(1) else if (g.fastKC == 2) PB_GAE_FAST(2) else PB_GAE_FAST(4)
+#undef PB_GAE_FAST
+        PB_LAUNCH_CHECK();
+        return PB_OK;
+    }
     if (g.RW == 16) {
         PB_CUDA(cudaFuncSetAttribute(k_gae<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
         PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae<16>, GAE_THREADS, g.smem));

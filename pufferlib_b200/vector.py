@@ -332,7 +332,7 @@ class B200:
         out = (C.c_double * 4)()
         with torch.cuda.device(self.device):
             _native.check(_native.lib().pb_env_stats_read(self._handle, out, int(clear), _native.stream_ptr()))
-        self.d2h_bytes += 32
+        self.d2h_bytes += 256 * 32
         cnt = out[0]
         if cnt <= 0:
             return {}, 0

@@ -51,7 +51,8 @@ def test_gae_golden_flat(golden):
 
 
 @pytest.mark.parametrize('h,n', [(128, 64), (128, 16384), (1, 1), (1, 7), (5, 1), (3, 64), (41, 5), (17, 33),
-                                 (256, 96), (100, 200), (2048, 3), (1024, 16), (4, 70000), (5000, 1), (8, 513)])
+                                 (256, 96), (100, 200), (2048, 3), (1024, 16), (4, 70000), (5000, 1), (8, 513),
+                                 (128, 33), (256, 17), (512, 40), (128, 2), (512, 1000), (128, 15), (256, 16)])
 def test_gae_shapes(h, n):
     check_case(h, n, seed=h * 1000 + n, p_done=0.02, gamma=0.99, lam=0.95)
 
