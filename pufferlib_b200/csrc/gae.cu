@@ -17,6 +17,8 @@
 // warp-wide look-back window that stops as soon as the accumulated slope is exactly 0 (any done flag, or
 // (gamma*lambda)^k underflow).  Outputs are written in sorted order, 128 B per warp store.
 // HBM traffic = 12 B read + 4 (or 8 with returns) B written per agent-step.
+#include <stdlib.h>
+
 #include "pb_common.cuh"
 
 namespace {
@@ -50,10 +52,70 @@ struct GaeParams {
     GaeStatus* status;
 };
 
+// A tile's status is ONE aligned 16-byte word {P, Q, X, flag}: it is published with a single 128-bit store and read
+// with a single 128-bit load (both L2-coherent, one transaction), so value and flag can never be observed torn and no
+// __threadfence is needed around the hand-off (the scheme CUB's decoupled look-back uses for <= 16-byte payloads).
+__device__ __forceinline__ void status_store(GaeStatus* s, float P, float Q, float X, uint32_t flag) {
+    asm volatile("st.relaxed.gpu.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(s), "r"(__float_as_uint(P)),
+                 "r"(__float_as_uint(Q)), "r"(__float_as_uint(X)), "r"(flag)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t status_load(const GaeStatus* s, float& P, float& Q, float& X) {
+    uint32_t a, b, c, f;
+    asm volatile("ld.relaxed.gpu.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(f) : "l"(s)
+                 : "memory");
+    P = __uint_as_float(a); Q = __uint_as_float(b); X = __uint_as_float(c);
+    return f;
+}
+
 __device__ __forceinline__ void compose(float& a, float& b, float a2, float b2) {
     // (a,b) o (a2,b2): first apply the later map (a2,b2), then this one
     a = fmaf(b, a2, a);
     b = b * b2;
+}
+
+__device__ __forceinline__ float tile_lookback(GaeStatus* st, int tile, int numTiles, float tP, float tQ, int lane) {
+    if (tile == numTiles - 1) {
+        if (lane == 0) status_store(&st[tile], tP, tQ, tP, 2u);   // A beyond the batch is 0: inclusive = aggregate
+        return 0.f;
+    }
+    if (lane == 0) status_store(&st[tile], tP, tQ, 0.f, 1u);
+    float accP = 0.f, accQ = 1.f;    // composition of the successor tiles already walked
+    int base = tile + 1;
+    bool finished = false;
+    while (!finished) {
+        const int j = base + lane;
+        uint32_t fl = 2u;
+        float jP = 0.f, jQ = 0.f;    // beyond the last tile: inclusive value 0
+        if (j < numTiles) {
+            float P, Q, X;
+            uint32_t polls = 0;
+            do {
+                fl = status_load(&st[j], P, Q, X);
+                if (++polls == (1u << 27)) __trap();   // seconds of polling: abort rather than hang the GPU
+            } while (fl == 0u);
+            if (fl == 2u) { jP = X; jQ = 0.f; }
+            else { jP = P; jQ = Q; }
+        }
+        // an inclusive tile or an exactly-zero slope ends the chain: A = P regardless of what follows
+        const unsigned stop = __ballot_sync(0xffffffffu, fl == 2u || jQ == 0.f);
+        const int last = stop ? (__ffs(stop) - 1) : 31;
+        float x = (lane <= last) ? jP : 0.f, y = (lane <= last) ? jQ : 1.f;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float x2 = __shfl_down_sync(0xffffffffu, x, off);
+            const float y2 = __shfl_down_sync(0xffffffffu, y, off);
+            if (lane + off < 32) compose(x, y, x2, y2);
+        }
+        x = __shfl_sync(0xffffffffu, x, 0);
+        y = __shfl_sync(0xffffffffu, y, 0);
+        compose(accP, accQ, x, y);
+        finished = stop != 0u;
+        base += 32;
+    }
+    const float carry = accP;        // accQ == 0 here: value of A at the first element after this tile
+    if (lane == 0) status_store(&st[tile], tP, tQ, fmaf(tQ, carry, tP), 2u);
+    return carry;
 }
 
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
@@ -249,62 +311,7 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae(GaeParams p) {
                 tP = x;
                 tQ = y;
             }
-            GaeStatus* st = p.status;
-            float carry = 0.f;
-            if (tile == p.numTiles - 1) {
-                if (lane == 0) {
-                    st[tile].X = tP;  // A beyond the batch is 0
-                    __threadfence();
-                    pb_st_release(&st[tile].flag, 2u);
-                }
-            } else {
-                if (lane == 0) {
-                    st[tile].P = tP;
-                    st[tile].Q = tQ;
-                    __threadfence();
-                    pb_st_release(&st[tile].flag, 1u);
-                }
-                // window of 32 successor tiles per iteration
-                float accP = 0.f, accQ = 1.f;  // composition of the tiles already walked
-                int base = tile + 1;
-                bool finished = false;
-                while (!finished) {
-                    const int j = base + lane;
-                    uint32_t fl = 2u;
-                    float jP = 0.f, jQ = 0.f;  // beyond the last tile: inclusive value 0
-                    if (j < p.numTiles) {
-                        uint32_t polls = 0;
-                        do {
-                            fl = pb_ld_acquire(&st[j].flag);
-                            if (++polls == (1u << 27)) __trap();   // seconds of polling: abort rather than hang
-                        } while (fl == 0u);
-                        // status words share 128 B lines with their neighbours: read through L2 (.cg)
-                        if (fl == 2u) { jP = __ldcg(&st[j].X); jQ = 0.f; }
-                        else { jP = __ldcg(&st[j].P); jQ = __ldcg(&st[j].Q); }
-                    }
-                    // an inclusive tile or an exactly-zero slope ends the chain: A = P regardless of what follows
-                    const unsigned stop = __ballot_sync(0xffffffffu, fl == 2u || jQ == 0.f);
-                    const int last = stop ? (__ffs(stop) - 1) : 31;
-                    float x = (lane <= last) ? jP : 0.f, y = (lane <= last) ? jQ : 1.f;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const float x2 = __shfl_down_sync(0xffffffffu, x, off);
-                        const float y2 = __shfl_down_sync(0xffffffffu, y, off);
-                        if (lane + off < 32) compose(x, y, x2, y2);
-                    }
-                    x = __shfl_sync(0xffffffffu, x, 0);
-                    y = __shfl_sync(0xffffffffu, y, 0);
-                    compose(accP, accQ, x, y);
-                    finished = stop != 0u;
-                    base += 32;
-                }
-                carry = accP;  // accQ == 0 here: value of A at the first element after this tile
-                if (lane == 0) {
-                    st[tile].X = fmaf(tQ, carry, tP);
-                    __threadfence();
-                    pb_st_release(&st[tile].flag, 2u);
-                }
-            }
+            const float carry = tile_lookback(p.status, tile, p.numTiles, tP, tQ, lane);
             if (lane == 0) s_carry = carry;
         }
         __syncthreads();
@@ -355,63 +362,9 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae(GaeParams p) {
 constexpr int FE = 16;   // envs per tile
 constexpr int FC = 16;   // steps per chunk
 
-__device__ __forceinline__ float tile_lookback(GaeStatus* st, int tile, int numTiles, float tP, float tQ, int lane) {
-    float carry = 0.f;
-    if (tile == numTiles - 1) {
-        if (lane == 0) {
-            st[tile].X = tP;  // A beyond the batch is 0
-            __threadfence();
-            pb_st_release(&st[tile].flag, 2u);
-        }
-        return 0.f;
-    }
-    if (lane == 0) {
-        st[tile].P = tP;
-        st[tile].Q = tQ;
-        __threadfence();
-        pb_st_release(&st[tile].flag, 1u);
-    }
-    float accP = 0.f, accQ = 1.f;
-    int base = tile + 1;
-    bool finished = false;
-    while (!finished) {
-        const int j = base + lane;
-        uint32_t fl = 2u;
-        float jP = 0.f, jQ = 0.f;
-        if (j < numTiles) {
-            uint32_t polls = 0;
-            do {
-                fl = pb_ld_acquire(&st[j].flag);
-                if (++polls == (1u << 27)) __trap();
-            } while (fl == 0u);
-            if (fl == 2u) { jP = __ldcg(&st[j].X); jQ = 0.f; }
-            else { jP = __ldcg(&st[j].P); jQ = __ldcg(&st[j].Q); }
-        }
-        const unsigned stop = __ballot_sync(0xffffffffu, fl == 2u || jQ == 0.f);
-        const int last = stop ? (__ffs(stop) - 1) : 31;
-        float x = (lane <= last) ? jP : 0.f, y = (lane <= last) ? jQ : 1.f;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const float x2 = __shfl_down_sync(0xffffffffu, x, off);
-            const float y2 = __shfl_down_sync(0xffffffffu, y, off);
-            if (lane + off < 32) compose(x, y, x2, y2);
-        }
-        x = __shfl_sync(0xffffffffu, x, 0);
-        y = __shfl_sync(0xffffffffu, y, 0);
-        compose(accP, accQ, x, y);
-        finished = stop != 0u;
-        base += 32;
-    }
-    carry = accP;
-    if (lane == 0) {
-        st[tile].X = fmaf(tQ, carry, tP);
-        __threadfence();
-        pb_st_release(&st[tile].flag, 2u);
-    }
-    return carry;
-}
-
-template <int KC>   // chunks per thread: H = 128 * KC
+// NBUF = 2: double-buffered tiles inside a block; NBUF = 1: one buffer, twice the resident blocks (the overlap then
+// comes from occupancy: one block loads while its neighbours scan).
+template <int KC, int NBUF>   // chunks per thread: H = 128 * KC
 __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
     constexpr int H = 128 * KC;
     constexpr int PITCH = H + 1;
@@ -467,7 +420,7 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
     __syncthreads();
     int ticket = s_ticket[0];
     int cur = 0;
-    if (ticket < p.numTiles) issue_tile(p.numTiles - 1 - ticket, 0);
+    if (NBUF == 2 && ticket < p.numTiles) issue_tile(p.numTiles - 1 - ticket, 0);
 
     while (ticket < p.numTiles) {
         const int tile = p.numTiles - 1 - ticket;
@@ -478,13 +431,21 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
         const float* sD = sV + ARR;
         const float* halo = s_halo[cur];
 
-        if (tid == 0) s_ticket[cur ^ 1] = (int)atomicAdd(&p.hdr->ticket, 1u);
-        __syncthreads();
-        const int next_ticket = s_ticket[cur ^ 1];
-        if (next_ticket < p.numTiles) {
-            issue_tile(p.numTiles - 1 - next_ticket, cur ^ 1);
-            cp_async_wait<1>();
+        int next_ticket;
+        if (NBUF == 2) {
+            if (tid == 0) s_ticket[cur ^ 1] = (int)atomicAdd(&p.hdr->ticket, 1u);
+            __syncthreads();
+            next_ticket = s_ticket[cur ^ 1];
+            if (next_ticket < p.numTiles) {
+                issue_tile(p.numTiles - 1 - next_ticket, cur ^ 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
         } else {
+            issue_tile(tile, 0);
+            // claim the next tile now; the result is only read at the end of this iteration (latency hidden)
+            if (tid == 0) s_ticket[1] = (int)atomicAdd(&p.hdr->ticket, 1u);
             cp_async_wait<0>();
         }
         __syncthreads();
@@ -590,8 +551,13 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
             }
         }
         __syncthreads();
-        ticket = next_ticket;
-        cur ^= 1;
+        if (NBUF == 2) {
+            ticket = next_ticket;
+            cur ^= 1;
+        } else {
+            ticket = s_ticket[1];
+            __syncthreads();      // everyone has read s_ticket[1] before thread 0 overwrites it next iteration
+        }
     }
 
     if (tid == 0) {
@@ -609,11 +575,19 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
 }
 
 struct GaePlan {
-    int fastKC;   // > 0: k_gae_fast<fastKC>
+    int fastKC;   // > 0: k_gae_fast<fastKC, nbuf>
+    int nbuf;
     int E, logE, L, pitch, numTiles, RW;
     uint32_t magicH;
     size_t smem;
 };
+
+// PB_GAE_NBUF=1|2 overrides the buffering of the fast path (tuning / A-B measurements)
+int gae_nbuf_override(int dflt) {
+    const char* e = getenv("PB_GAE_NBUF");
+    if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+    return dflt;
+}
 
 GaePlan gae_plan(int64_t N, int64_t H) {
     GaePlan g{};
@@ -623,7 +597,8 @@ GaePlan gae_plan(int64_t N, int64_t H) {
         g.fastKC = (int)(H / 128);
         g.E = FE; g.logE = 4; g.L = FE * (int)H; g.pitch = (int)H + 1; g.magicH = 0;
         g.numTiles = (int)pb_ceil_div(N, FE);
-        g.smem = (size_t)2 * 3 * FE * (H + 1) * sizeof(float);
+        g.nbuf = (H == 512) ? 1 : gae_nbuf_override(H <= 256 ? 1 : 1);
+        g.smem = (size_t)g.nbuf * 3 * FE * (H + 1) * sizeof(float);
         g.RW = 16;
         return g;
     }
@@ -686,16 +661,18 @@ extern "C" int pb_gae(const float* rewards, const float* values, const float* do
     if (g.fastKC > 0) {
         PB_REQUIRE(((uintptr_t)advantages & 15) == 0 && (!returns_sorted || ((uintptr_t)returns_sorted & 15) == 0),
                    PB_ERR_INVALID, "pb_gae: advantages / returns must be 16-byte aligned");
-#define PB_GAE_FAST(KC)                                                                                               \
+#define PB_GAE_FAST_(KC, NB)                                                                                          \
     {                                                                                                                 \
-        PB_CUDA(cudaFuncSetAttribute(k_gae_fast<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));     \
-        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae_fast<KC>, GAE_THREADS, g.smem));        \
+        PB_CUDA(cudaFuncSetAttribute(k_gae_fast<KC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae_fast<KC, NB>, GAE_THREADS, g.smem));    \
         PB_REQUIRE(per_sm >= 1, PB_ERR_CUDA, "pb_gae: kernel does not fit on an SM (smem %zu)", g.smem);              \
         int grid = per_sm * PB_NUM_SMS;                                                                               \
         if (grid > g.numTiles) grid = g.numTiles;                                                                     \
-        k_gae_fast<KC><<<grid, GAE_THREADS, g.smem, s>>>(p);                                                          \
+        k_gae_fast<KC, NB><<<grid, GAE_THREADS, g.smem, s>>>(p);                                                      \
     }
+#define PB_GAE_FAST(KC) { if (g.nbuf == 2) PB_GAE_FAST_(KC, 2) else PB_GAE_FAST_(KC, 1) }
         if (g.fastKC == 1) PB_GAE_FAST(1) else if (g.fastKC == 2) PB_GAE_FAST(2) else PB_GAE_FAST(4)
+#undef PB_GAE_FAST_
 #undef PB_GAE_FAST
         PB_LAUNCH_CHECK();
         return PB_OK;
