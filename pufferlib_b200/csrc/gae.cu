@@ -354,98 +354,81 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae(GaeParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fast path (N > 1, H in {128, 256, 512}): tile = 16 whole envs, 128 threads, each thread owns KC = H/128 chunks of 16
-// consecutive steps of one env.  A chunk is composed SERIALLY in registers (2 FMAs per element instead of a 5-step
-// shuffle scan), so the kernel issues ~30 thread-instructions per element instead of ~100.  Shared-memory layout
-// [env][t] with row pitch H+1: the e-fastest cp.async loader and the per-thread chunk walks are both conflict-free
-// (lanes 0-15 / 16-31 of a warp hold envs 0-15 of two adjacent chunks -> banks el+j and el+16+j).
-constexpr int FE = 16;   // envs per tile
-constexpr int FC = 16;   // steps per chunk
+// Fast path (N > 1, N % 4 == 0, H in {128, 256, 512}): tile = 32 whole envs, 256 threads.
+//   * loads: every time row of the tile is one 128-byte run (32 envs), copied global->shared with 16-byte cp.async
+//     (LDGSTS.128): 12*KC async copies per thread, no register staging, no transposition -- shared layout is [t][32];
+//   * pass 1: thread (env = lane, chunk) composes its 16 consecutive steps SERIALLY in registers (2 FMAs per element
+//     instead of a 5-step shuffle scan); a warp's 32 lanes read 32 consecutive floats: conflict-free;
+//   * pass 2 (one warp): chunk carries inside each env, a 5-step shuffle suffix over the 32 env aggregates, then the
+//     decoupled look-back; pass 3: apply carries, 64 B of output per thread-chunk.
+// ~40 thread-instructions per element instead of ~180 for the generic kernel.
+constexpr int FE = 32;            // envs per tile
+constexpr int FC = 16;            // steps per chunk
+constexpr int FAST_THREADS = 256; // 32 envs x 8 chunk slots
 
-// NBUF = 2: double-buffered tiles inside a block; NBUF = 1: one buffer, twice the resident blocks (the overlap then
-// comes from occupancy: one block loads while its neighbours scan).
-template <int KC, int NBUF>   // chunks per thread: H = 128 * KC
-__global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+
+template <int KC>   // chunks per thread: H = 128 * KC
+__global__ void __launch_bounds__(FAST_THREADS) k_gae_fast(GaeParams p) {
     constexpr int H = 128 * KC;
-    constexpr int PITCH = H + 1;
     constexpr int CE = H / FC;                 // chunks per env
-    constexpr int ARR = FE * PITCH;            // floats per array per buffer
-    extern __shared__ float smem[];            // 2 buffers x {r, v, d} x ARR
+    constexpr int ARR = H * FE;                // floats per array
+    extern __shared__ __align__(16) float smem[];   // {r, v, d} x [H][32]
     __shared__ int s_ticket[2];
-    __shared__ float s_halo[2][4];
-    __shared__ float2 s_cagg[FE][CE + 1];      // chunk aggregates, then chunk carry maps (w.r.t. the env's right end)
+    __shared__ float s_halo[4];
+    __shared__ float2 s_cagg[CE][FE];          // chunk aggregates, then chunk carry maps (w.r.t. the env's right end)
     __shared__ float2 s_eagg[FE];              // env carry maps w.r.t. the tile's right end
     __shared__ float s_carry;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // loader role: this thread always copies env el_ld, time rows t_ld, t_ld + 8, ...
-    const int el_ld = tid & (FE - 1), t_ld = tid >> 4;
-
-    auto issue_tile = [&](int tile, int buf) {
-        const int64_t e0 = (int64_t)tile * FE;
-        const int Et = (int)min((int64_t)FE, p.N - e0);
-        float* sR = smem + buf * 3 * ARR;
-        float* sV = sR + ARR;
-        float* sD = sV + ARR;
-        if (el_ld < Et) {
-            const int64_t g0 = (int64_t)t_ld * p.N + e0 + el_ld;
-            const int64_t gstep = 8 * p.N;
-            const float* pr = p.r + g0;
-            const float* pv = p.v + g0;
-            const float* pd = p.d + g0;
-            int sp = el_ld * PITCH + t_ld;
-#pragma unroll 8
-            for (int k = 0; k < H / 8; ++k) {
-                cp_async4(sR + sp, pr);
-                cp_async4(sV + sp, pv);
-                cp_async4(sD + sp, pd);
-                pr += gstep; pv += gstep; pd += gstep;
-                sp += 8;
-            }
-        }
-        if (tid == 0) {
-            const int64_t en = e0 + Et;          // first env after the tile, its t = 0 row sits at index en
-            if (en < p.N) {
-                cp_async4(&s_halo[buf][0], p.r + en);
-                cp_async4(&s_halo[buf][1], p.v + en);
-                cp_async4(&s_halo[buf][2], p.d + en);
-            } else {
-                s_halo[buf][0] = 0.f; s_halo[buf][1] = 0.f; s_halo[buf][2] = 1.f;
-            }
-        }
-        cp_async_commit();
-    };
+    float* sR = smem;
+    float* sV = smem + ARR;
+    float* sD = smem + 2 * ARR;
 
     if (tid == 0) s_ticket[0] = (int)atomicAdd(&p.hdr->ticket, 1u);
     __syncthreads();
     int ticket = s_ticket[0];
-    int cur = 0;
-    if (NBUF == 2 && ticket < p.numTiles) issue_tile(p.numTiles - 1 - ticket, 0);
 
     while (ticket < p.numTiles) {
-        const int tile = p.numTiles - 1 - ticket;
+        const int tile = p.numTiles - 1 - ticket;          // suffix order: last tile first
         const int64_t e0 = (int64_t)tile * FE;
-        const int Et = (int)min((int64_t)FE, p.N - e0);
-        const float* sR = smem + cur * 3 * ARR;
-        const float* sV = sR + ARR;
-        const float* sD = sV + ARR;
-        const float* halo = s_halo[cur];
+        const int Et = (int)min((int64_t)FE, p.N - e0);     // multiple of 4 (N % 4 == 0)
 
-        int next_ticket;
-        if (NBUF == 2) {
-            if (tid == 0) s_ticket[cur ^ 1] = (int)atomicAdd(&p.hdr->ticket, 1u);
-            __syncthreads();
-            next_ticket = s_ticket[cur ^ 1];
-            if (next_ticket < p.numTiles) {
-                issue_tile(p.numTiles - 1 - next_ticket, cur ^ 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
+        // ---- async loads: row t of the tile = floats [t*N + e0, +Et)
+        {
+            const int quad = tid & 7, t0 = tid >> 3;         // 8 float4 per row, 32 rows per sweep
+            if (4 * quad < Et) {
+                const int64_t g0 = (int64_t)t0 * p.N + e0 + 4 * quad;
+                const int64_t gstep = 32 * p.N;
+                const float* pr = p.r + g0;
+                const float* pv = p.v + g0;
+                const float* pd = p.d + g0;
+                int sp = t0 * FE + 4 * quad;
+#pragma unroll
+                for (int k = 0; k < H / 32; ++k) {
+                    cp_async16(sR + sp, pr);
+                    cp_async16(sV + sp, pv);
+                    cp_async16(sD + sp, pd);
+                    pr += gstep; pv += gstep; pd += gstep;
+                    sp += 32 * FE;
+                }
             }
-        } else {
-            issue_tile(tile, 0);
-            // claim the next tile now; the result is only read at the end of this iteration (latency hidden)
-            if (tid == 0) s_ticket[1] = (int)atomicAdd(&p.hdr->ticket, 1u);
+            if (tid == 0) {
+                const int64_t en = e0 + Et;                  // first env after the tile; its t = 0 row entry
+                if (en < p.N) {
+                    cp_async4(&s_halo[0], p.r + en);
+                    cp_async4(&s_halo[1], p.v + en);
+                    cp_async4(&s_halo[2], p.d + en);
+                } else {
+                    s_halo[0] = 0.f; s_halo[1] = 0.f; s_halo[2] = 1.f;
+                }
+                // claim the next tile now; the value is only read at the end of this iteration (latency hidden)
+                s_ticket[1] = (int)atomicAdd(&p.hdr->ticket, 1u);
+            }
+            cp_async_commit();
             cp_async_wait<0>();
         }
         __syncthreads();
@@ -454,22 +437,19 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
         float a[KC][FC], b[KC][FC];
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) {
-            const int q = tid + kc * GAE_THREADS;          // chunk id: el = q % 16, c = q / 16
-            const int el = q & (FE - 1), c = q >> 4;
+            const int c = warp + kc * (FAST_THREADS / 32);      // chunk index; env = lane
             float P = 0.f, Q = 1.f;
-            if (el < Et) {
-                const float* rr = sR + el * PITCH + c * FC;
-                const float* vv = sV + el * PITCH + c * FC;
-                const float* dd = sD + el * PITCH + c * FC;
+            if (lane < Et) {
+                const int base = c * FC * FE + lane;
                 // the element after the chunk: next step of the env, next env's first step, or the tile halo
                 float rn, vn, dn;
-                if (c < CE - 1) { rn = rr[FC]; vn = vv[FC]; dn = dd[FC]; }
-                else if (el + 1 < Et) { rn = sR[(el + 1) * PITCH]; vn = sV[(el + 1) * PITCH]; dn = sD[(el + 1) * PITCH]; }
-                else { rn = halo[0]; vn = halo[1]; dn = halo[2]; }
-                const bool last_of_batch = (e0 + el == p.N - 1) && (c == CE - 1);
+                if (c < CE - 1) { rn = sR[base + FC * FE]; vn = sV[base + FC * FE]; dn = sD[base + FC * FE]; }
+                else if (lane + 1 < Et) { rn = sR[lane + 1]; vn = sV[lane + 1]; dn = sD[lane + 1]; }
+                else { rn = s_halo[0]; vn = s_halo[1]; dn = s_halo[2]; }
+                const bool last_of_batch = (e0 + lane == p.N - 1) && (c == CE - 1);
 #pragma unroll
                 for (int j = FC - 1; j >= 0; --j) {
-                    const float r0 = rr[j], v0 = vv[j], d0 = dd[j];
+                    const float r0 = sR[base + j * FE], v0 = sV[base + j * FE], d0 = sD[base + j * FE];
                     const float nnt = __fsub_rn(1.0f, dn);
                     // c_gae.pyx:28-29 association, no FMA contraction inside an element
                     float aj = __fsub_rn(__fadd_rn(rn, __fmul_rn(__fmul_rn(p.gamma, vn), nnt)), v0);
@@ -481,29 +461,26 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
                     Q = bj * Q;
                     rn = r0; vn = v0; dn = d0;
                 }
-                s_cagg[el][c] = make_float2(P, Q);
             } else {
 #pragma unroll
                 for (int j = 0; j < FC; ++j) { a[kc][j] = 0.f; b[kc][j] = 1.f; }
             }
+            s_cagg[c][lane] = make_float2(P, Q);
         }
         __syncthreads();
 
         // ---- pass 2 (warp 0): chunk carries inside each env, env carries inside the tile, then the look-back
         if (warp == 0) {
-            float eP = 0.f, eQ = 1.f;                    // env aggregate (identity for missing envs)
-            if (lane < Et) {
-                float cP = 0.f, cQ = 1.f;                // composition of the chunks to the right, w.r.t. the env end
-                for (int c = CE - 1; c >= 0; --c) {
-                    const float2 g = s_cagg[lane][c];
-                    s_cagg[lane][c] = make_float2(cP, cQ);   // carry map entering chunk c from the right
-                    const float nP = fmaf(g.y, cP, g.x), nQ = g.y * cQ;
-                    cP = nP; cQ = nQ;
-                }
-                eP = cP; eQ = cQ;
+            float cP = 0.f, cQ = 1.f;                    // composition of the chunks to the right, w.r.t. the env end
+#pragma unroll
+            for (int c = CE - 1; c >= 0; --c) {
+                const float2 g = s_cagg[c][lane];
+                s_cagg[c][lane] = make_float2(cP, cQ);   // carry map entering chunk c from the right
+                const float nP = fmaf(g.y, cP, g.x), nQ = g.y * cQ;
+                cP = nP; cQ = nQ;
             }
-            // exclusive suffix over the 16 envs: map from the tile's right end to env el's right end
-            float x = eP, y = eQ;                        // inclusive first
+            // inclusive suffix over the 32 env aggregates (missing envs are the identity)
+            float x = cP, y = cQ;
 #pragma unroll
             for (int off = 1; off < FE; off <<= 1) {
                 const float x2 = __shfl_down_sync(0xffffffffu, x, off);
@@ -511,9 +488,10 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
                 if (lane + off < FE) compose(x, y, x2, y2);
             }
             const float tP = __shfl_sync(0xffffffffu, x, 0), tQ = __shfl_sync(0xffffffffu, y, 0);
+            // exclusive: map from the tile's right end to env `lane`'s right end
             float exP = __shfl_down_sync(0xffffffffu, x, 1), exQ = __shfl_down_sync(0xffffffffu, y, 1);
-            if (lane >= FE - 1) { exP = 0.f; exQ = 1.f; }
-            if (lane < FE) s_eagg[lane] = make_float2(exP, exQ);
+            if (lane == FE - 1) { exP = 0.f; exQ = 1.f; }
+            s_eagg[lane] = make_float2(exP, exQ);
             const float carry = tile_lookback(p.status, tile, p.numTiles, tP, tQ, lane);
             if (lane == 0) s_carry = carry;
         }
@@ -521,15 +499,15 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
 
         // ---- pass 3: apply carries, write outputs in sorted order (64 B per thread-chunk, full sectors)
         const float C = s_carry;
+        if (lane < Et) {
+            const float2 em = s_eagg[lane];
+            const float a_env_end = fmaf(em.y, C, em.x);                // A just after this env
 #pragma unroll
-        for (int kc = 0; kc < KC; ++kc) {
-            const int q = tid + kc * GAE_THREADS;
-            const int el = q & (FE - 1), c = q >> 4;
-            if (el < Et) {
-                const float2 em = s_eagg[el], cm = s_cagg[el][c];
-                const float a_env_end = fmaf(em.y, C, em.x);           // A just after this env
-                float A = fmaf(cm.y, a_env_end, cm.x);                 // A just after this chunk
-                const int64_t f = (e0 + el) * (int64_t)H + c * FC;
+            for (int kc = 0; kc < KC; ++kc) {
+                const int c = warp + kc * (FAST_THREADS / 32);
+                const float2 cm = s_cagg[c][lane];
+                float A = fmaf(cm.y, a_env_end, cm.x);                  // A just after this chunk
+                const int64_t f = (e0 + lane) * (int64_t)H + c * FC;
                 float outA[FC];
 #pragma unroll
                 for (int j = FC - 1; j >= 0; --j) {
@@ -541,23 +519,20 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
                 for (int j4 = 0; j4 < FC / 4; ++j4)
                     __stcs(pa + j4, make_float4(outA[4 * j4], outA[4 * j4 + 1], outA[4 * j4 + 2], outA[4 * j4 + 3]));
                 if (p.ret) {
-                    const float* vv = sV + el * PITCH + c * FC;
+                    const int base = c * FC * FE + lane;
                     float4* pr = reinterpret_cast<float4*>(p.ret + f);
 #pragma unroll
                     for (int j4 = 0; j4 < FC / 4; ++j4)
-                        __stcs(pr + j4, make_float4(outA[4 * j4] + vv[4 * j4], outA[4 * j4 + 1] + vv[4 * j4 + 1],
-                                                    outA[4 * j4 + 2] + vv[4 * j4 + 2], outA[4 * j4 + 3] + vv[4 * j4 + 3]));
+                        __stcs(pr + j4, make_float4(outA[4 * j4] + sV[base + (4 * j4) * FE],
+                                                    outA[4 * j4 + 1] + sV[base + (4 * j4 + 1) * FE],
+                                                    outA[4 * j4 + 2] + sV[base + (4 * j4 + 2) * FE],
+                                                    outA[4 * j4 + 3] + sV[base + (4 * j4 + 3) * FE]));
                 }
             }
         }
-        __syncthreads();
-        if (NBUF == 2) {
-            ticket = next_ticket;
-            cur ^= 1;
-        } else {
-            ticket = s_ticket[1];
-            __syncthreads();      // everyone has read s_ticket[1] before thread 0 overwrites it next iteration
-        }
+        __syncthreads();          // the tile buffers, s_cagg / s_eagg / s_carry are free again
+        ticket = s_ticket[1];
+        __syncthreads();          // everyone has read s_ticket[1] before thread 0 overwrites it next iteration
     }
 
     if (tid == 0) {
@@ -567,7 +542,7 @@ __global__ void __launch_bounds__(GAE_THREADS) k_gae_fast(GaeParams p) {
     }
     __syncthreads();
     if (s_ticket[0]) {
-        for (int j = tid; j < p.numTiles; j += GAE_THREADS) {
+        for (int j = tid; j < p.numTiles; j += FAST_THREADS) {
             p.status[j].P = 0.f; p.status[j].Q = 0.f; p.status[j].X = 0.f; p.status[j].flag = 0u;
         }
         if (tid == 0) { p.hdr->ticket = 0u; p.hdr->exited = 0u; }
@@ -582,23 +557,16 @@ struct GaePlan {
     size_t smem;
 };
 
-// PB_GAE_NBUF=1|2 overrides the buffering of the fast path (tuning / A-B measurements)
-int gae_nbuf_override(int dflt) {
-    const char* e = getenv("PB_GAE_NBUF");
-    if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
-    return dflt;
-}
-
 GaePlan gae_plan(int64_t N, int64_t H) {
     GaePlan g{};
     const int64_t B = N * H;
     const int Ltarget = 2048, Lmax = 4096;
-    if (N > 1 && (H == 128 || H == 256 || H == 512) ) {
+    if (N > 1 && N % 4 == 0 && (H == 128 || H == 256 || H == 512)) {
         g.fastKC = (int)(H / 128);
-        g.E = FE; g.logE = 4; g.L = FE * (int)H; g.pitch = (int)H + 1; g.magicH = 0;
+        g.nbuf = 1;
+        g.E = FE; g.logE = 5; g.L = FE * (int)H; g.pitch = FE; g.magicH = 0;
         g.numTiles = (int)pb_ceil_div(N, FE);
-        g.nbuf = (H == 512) ? 1 : gae_nbuf_override(H <= 256 ? 1 : 1);
-        g.smem = (size_t)g.nbuf * 3 * FE * (H + 1) * sizeof(float);
+        g.smem = (size_t)3 * FE * H * sizeof(float);
         g.RW = 16;
         return g;
     }
@@ -661,18 +629,18 @@ extern "C" int pb_gae(const float* rewards, const float* values, const float* do
     if (g.fastKC > 0) {
         PB_REQUIRE(((uintptr_t)advantages & 15) == 0 && (!returns_sorted || ((uintptr_t)returns_sorted & 15) == 0),
                    PB_ERR_INVALID, "pb_gae: advantages / returns must be 16-byte aligned");
-#define PB_GAE_FAST_(KC, NB)                                                                                          \
+        PB_REQUIRE(((uintptr_t)rewards & 15) == 0 && ((uintptr_t)values & 15) == 0 && ((uintptr_t)dones & 15) == 0,
+                   PB_ERR_INVALID, "pb_gae: rewards / values / dones must be 16-byte aligned");
+#define PB_GAE_FAST(KC)                                                                                               \
     {                                                                                                                 \
-        PB_CUDA(cudaFuncSetAttribute(k_gae_fast<KC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
-        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae_fast<KC, NB>, GAE_THREADS, g.smem));    \
+        PB_CUDA(cudaFuncSetAttribute(k_gae_fast<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));     \
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae_fast<KC>, FAST_THREADS, g.smem));       \
         PB_REQUIRE(per_sm >= 1, PB_ERR_CUDA, "pb_gae: kernel does not fit on an SM (smem %zu)", g.smem);              \
         int grid = per_sm * PB_NUM_SMS;                                                                               \
         if (grid > g.numTiles) grid = g.numTiles;                                                                     \
-        k_gae_fast<KC, NB><<<grid, GAE_THREADS, g.smem, s>>>(p);                                                      \
+        k_gae_fast<KC><<<grid, FAST_THREADS, g.smem, s>>>(p);                                                         \
     }
-#define PB_GAE_FAST(KC) { if (g.nbuf == 2) PB_GAE_FAST_(KC, 2) else PB_GAE_FAST_(KC, 1) }
         if (g.fastKC == 1) PB_GAE_FAST(1) else if (g.fastKC == 2) PB_GAE_FAST(2) else PB_GAE_FAST(4)
-#undef PB_GAE_FAST_
 #undef PB_GAE_FAST
         PB_LAUNCH_CHECK();
         return PB_OK;
