@@ -183,10 +183,13 @@ int pb_image_pack(const void* new_frames, int64_t frame_stride, const void* prev
  * normalised = logits - logsumexp; action ~ Categorical(softmax) drawn with a counter-based RNG
  * (seed, offset + *offset_dev, row) -- offset_dev (optional device counter) keeps replays of a captured CUDA
  * graph on fresh random numbers; logprob = normalised[action]; entropy = -sum p*log p.  Optionally also writes
- * action/logprob/value into rollout row pointers (the pb_rollout_store copy, fused).  logits [n][n_act] fp32. */
-int pb_sample_logits(const float* logits, int64_t n, int32_t n_act, uint64_t seed, uint64_t offset,
-                     const uint64_t* offset_dev, int64_t* actions, float* logprobs, float* entropies,
-                     const float* value, float* values_row, float* logprobs_row, int64_t* actions_row, void* stream);
+ * action/logprob/value into rollout row pointers (the pb_rollout_store copy, fused).  logits: fp32 rows of n_act
+ * values, `logits_stride` floats apart (>= n_act; lets both heads come out of one GEMM); value: one float per row,
+ * `value_stride` floats apart. */
+int pb_sample_logits(const float* logits, int64_t logits_stride, int64_t n, int32_t n_act, uint64_t seed,
+                     uint64_t offset, const uint64_t* offset_dev, int64_t* actions, float* logprobs, float* entropies,
+                     const float* value, int64_t value_stride, float* values_row, float* logprobs_row,
+                     int64_t* actions_row, void* stream);
 
 #ifdef __cplusplus
 }

@@ -208,6 +208,12 @@ class Experience:
         if reward.data_ptr() != self.rewards.data_ptr() + ptr * 4:
             self.rewards[ptr:end] = torch.as_tensor(reward).to(self.device, torch.float32)
             self.dones[ptr:end] = torch.as_tensor(done).to(self.device, torch.float32)
+        if isinstance(value, torch.Tensor) and value.data_ptr() == self.values.data_ptr() + ptr * 4 and \
+                isinstance(action, torch.Tensor) and action.data_ptr() == self.actions.data_ptr() + ptr * 8 and \
+                logprob.data_ptr() == self.logprobs.data_ptr() + ptr * 4:
+            self.ptr = end          # the fused sampling epilogue already wrote value / logprob / action in place
+            self.step += 1
+            return
         value = value.reshape(-1).to(self.device, torch.float32).contiguous()
         logprob = logprob.reshape(-1).to(self.device, torch.float32).contiguous()
         action = torch.as_tensor(action).reshape(-1).to(self.device, torch.int64).contiguous()
@@ -217,6 +223,12 @@ class Experience:
             C.c_void_p(self.actions.data_ptr() + ptr * 8), n, s))
         self.ptr = end
         self.step += 1
+
+    def rows(self):
+        """(values, logprobs, actions) views of the rollout rows the next store() will fill."""
+        n = self.num_envs
+        lo, hi = self.ptr, self.ptr + n
+        return self.values[lo:hi], self.logprobs[lo:hi], self.actions[lo:hi]
 
     def sort_training_data(self):
         """clean_pufferl.py:452-464.  The permutation is arithmetic on the device; the index array is only
@@ -316,6 +328,8 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         msg=msg, last_log_time=0, utilization=None, grad_bucket=grad_bucket,
         io=pufferlib_b200.namespace(h2d=0, d2h=0), graph_state=0, rollout_graph=None, graph_steps=0,
         graph_launches=0, graph_replays=0,
+        fused_rows=bool(getattr(policy, 'fused_sample', False)) and hasattr(vecenv, 'bind_rollout')
+        and not getattr(vecenv, 'host_buffers', False),
     )
 
 
@@ -341,7 +355,10 @@ def _rollout_loop(data, infos):
                 io.h2d += o.nbytes + r.nbytes + d.nbytes
 
         with profile.eval_forward, torch.no_grad():
-            actions, logprob, _, value = policy(o_device)
+            if data.fused_rows and experience.num_envs is not None:
+                actions, logprob, _, value = policy(o_device, out=experience.rows())
+            else:
+                actions, logprob, _, value = policy(o_device)
 
         with profile.eval_misc:
             value = value.flatten()

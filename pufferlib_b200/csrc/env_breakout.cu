@@ -59,18 +59,22 @@ __global__ void __launch_bounds__(128) k_breakout(BreakoutState st, int n, const
     if (active) {
         const uint64_t seed_e = st.seed + (uint64_t)e;
         bool do_reset = true;
-        if (MODE == 1) {
+        uint32_t a0 = 0, a1 = 0;
+        uint4 bricks_in = bricks;
+        int a = 0;
+        if (MODE == 1) {   // all state loads are issued together (independent of `done`): one latency, not two
             ctr = st.ctr[e];
+            a0 = st.s0[e]; a1 = st.s1[e];
+            bricks_in = st.bricks[e];
+            a = (int)actions[e];
             do_reset = done[e] != 0;
         }
         if (!do_reset) {
             reset_row = false;
-            const uint32_t a0 = st.s0[e], a1 = st.s1[e];
             px = a0 & 0xff; lives = (a0 >> 8) & 7; in_play = (a0 >> 11) & 1; wait = (a0 >> 12) & 31;
             vx = (int)((a0 >> 17) & 7) - 3; vy = (int)((a0 >> 20) & 7) - 2;
             bx = a1 & 0xff; by = (a1 >> 8) & 0xff; tick = a1 >> 16;
-            bricks = st.bricks[e];
-            int a = (int)actions[e];
+            bricks = bricks_in;
             a = a < 0 ? 0 : (a > 3 ? 3 : a);
             if (a == 2) px = min(px + 4, 136);
             if (a == 3) px = max(px - 4, 0);

@@ -87,8 +87,14 @@ __global__ void __launch_bounds__(128) k_snake(SnakeState st, int n, const int64
     if (valid) {
         const uint64_t seed_e = st.seed + (uint64_t)e;
         bool do_reset = true;
-        if (MODE == 1) {
+        uint32_t a0 = 0, a1 = 0;
+        uint4 v_prev = v;
+        int a = 0;
+        if (MODE == 1) {   // every load is issued before the `done` branch: one DRAM latency, not two
+            v_prev = *reinterpret_cast<const uint4*>(prev + (int64_t)e * prev_stride + sub * 16);
             ctr = st.ctr[e];
+            a0 = st.s0[e]; a1 = st.s1[e];
+            a = (int)actions[e];
             do_reset = done[e] != 0;
         }
         if (do_reset) {
@@ -98,10 +104,8 @@ __global__ void __launch_bounds__(128) k_snake(SnakeState st, int n, const int64
             place_food(v, sub, gmask, r % 254u);
         } else {
             reset_row = false;
-            const uint32_t a0 = st.s0[e];
-            head = a0 & 0xff; dir = (a0 >> 8) & 3; len = (a0 >> 16) & 0xff; tick = st.s1[e] & 0xffff;
-            v = *reinterpret_cast<const uint4*>(prev + (int64_t)e * prev_stride + sub * 16);
-            int a = (int)actions[e];
+            head = a0 & 0xff; dir = (a0 >> 8) & 3; len = (a0 >> 16) & 0xff; tick = a1 & 0xffff;
+            v = v_prev;
             a = a < 0 ? 0 : (a > 3 ? 3 : a);
             if (a != (dir ^ 1)) dir = a;
             const int x = head & 15, y = head >> 4;

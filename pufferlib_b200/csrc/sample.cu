@@ -14,9 +14,9 @@ namespace {
 
 constexpr int MAX_ACT = 32;
 
-__global__ void __launch_bounds__(256) k_sample_logits(const float* __restrict__ logits, int64_t n, int n_act,
+__global__ void __launch_bounds__(256) k_sample_logits(const float* __restrict__ logits, int64_t lstride, int64_t n, int n_act,
                                                       uint64_t seed, uint64_t offset, const uint64_t* __restrict__ offset_dev,
-                                                      int64_t* actions, float* logprobs, float* entropies, const float* value,
+                                                      int64_t* actions, float* logprobs, float* entropies, const float* value, int64_t vstride,
                                                       float* values_row, float* logprobs_row, int64_t* actions_row) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) k_sample_logits(const float* __restrict__
     float m = -INFINITY;
 #pragma unroll
     for (int k = 0; k < MAX_ACT; ++k)
-        if (k < n_act) { l[k] = logits[i * n_act + k]; m = fmaxf(m, l[k]); }
+        if (k < n_act) { l[k] = logits[i * lstride + k]; m = fmaxf(m, l[k]); }
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < MAX_ACT; ++k)
@@ -56,22 +56,24 @@ __global__ void __launch_bounds__(256) k_sample_logits(const float* __restrict__
     if (entropies) entropies[i] = ent;
     if (actions_row) actions_row[i] = a;
     if (logprobs_row) logprobs_row[i] = lp_a;
-    if (values_row && value) values_row[i] = value[i];
+    if (values_row && value) values_row[i] = value[i * vstride];
 }
 
 }  // namespace
 
-extern "C" int pb_sample_logits(const float* logits, int64_t n, int32_t n_act, uint64_t seed, uint64_t offset,
-                                const uint64_t* offset_dev, int64_t* actions, float* logprobs, float* entropies,
-                                const float* value,
+extern "C" int pb_sample_logits(const float* logits, int64_t logits_stride, int64_t n, int32_t n_act, uint64_t seed,
+                                uint64_t offset, const uint64_t* offset_dev, int64_t* actions, float* logprobs,
+                                float* entropies, const float* value, int64_t value_stride,
                                 float* values_row, float* logprobs_row, int64_t* actions_row, void* stream) {
     PB_REQUIRE(n >= 0, PB_ERR_INVALID, "pb_sample_logits: negative n");
     if (n == 0) return PB_OK;
     PB_REQUIRE(logits, PB_ERR_INVALID, "pb_sample_logits: null logits");
     PB_REQUIRE(n_act >= 1 && n_act <= MAX_ACT, PB_ERR_UNSUPPORTED, "pb_sample_logits: n_act must be in [1, %d]", MAX_ACT);
     PB_REQUIRE(!values_row || value, PB_ERR_INVALID, "pb_sample_logits: values_row given without value");
+    PB_REQUIRE(logits_stride >= n_act, PB_ERR_INVALID, "pb_sample_logits: logits_stride < n_act");
     k_sample_logits<<<(unsigned)pb_ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
-        logits, n, n_act, seed, offset, offset_dev, actions, logprobs, entropies, value, values_row, logprobs_row, actions_row);
+        logits, logits_stride, n, n_act, seed, offset, offset_dev, actions, logprobs, entropies, value, value_stride,
+        values_row, logprobs_row, actions_row);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

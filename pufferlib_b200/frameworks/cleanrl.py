@@ -49,27 +49,38 @@ class Policy(torch.nn.Module):
         _, value = self.policy(x)
         return value
 
-    def get_action_and_value(self, x, action=None):
+    def get_action_and_value(self, x, action=None, out=None):
+        """``out`` (optional, sampling only): (values_row, logprobs_row, actions_row) rollout row views the fused
+        epilogue writes into directly -- the policy-output part of Experience.store without a copy kernel."""
         logits, value = self.policy(x)
         if action is None and self.fused_sample and not torch.is_grad_enabled():
-            return (*self._sample_fused(logits), value)
+            return self._sample_fused(logits, value, out)
         action, logprob, ent = sample_logits(logits, action)
         return action, logprob, ent, value
 
-    def _sample_fused(self, logits):
-        logits = logits.float().contiguous()
+    def _sample_fused(self, logits, value, out=None):
+        if logits.dtype != torch.float32 or logits.stride(1) != 1:
+            logits = logits.float().contiguous()
         n, a = logits.shape
-        actions = torch.empty(n, dtype=torch.int64, device=logits.device)
-        logprob = torch.empty(n, dtype=torch.float32, device=logits.device)
-        ent = torch.empty(n, dtype=torch.float32, device=logits.device)
+        dev = logits.device
+        if out is None:
+            actions = torch.empty(n, dtype=torch.int64, device=dev)
+            logprob = torch.empty(n, dtype=torch.float32, device=dev)
+            rows = (None, None, None)
+            value_out = value
+        else:
+            value_out, logprob, actions = out
+            rows = (_native.ptr(value_out), None, None)     # logprob / action rows ARE the primary outputs
+        ent = torch.empty(n, dtype=torch.float32, device=dev)
         if self._counter is None:
-            self._counter = torch.zeros(1, dtype=torch.int64, device=logits.device)
+            self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        v2 = value.reshape(n, -1)
         _native.check(_native.lib().pb_sample_logits(
-            _native.ptr(logits), n, a, C.c_uint64(self._seed), C.c_uint64(0), _native.ptr(self._counter),
-            _native.ptr(actions), _native.ptr(logprob), _native.ptr(ent), None, None, None, None,
-            _native.stream_ptr()))
+            _native.ptr(logits), logits.stride(0), n, a, C.c_uint64(self._seed), C.c_uint64(0),
+            _native.ptr(self._counter), _native.ptr(actions), _native.ptr(logprob), _native.ptr(ent),
+            _native.ptr(v2), v2.stride(0), rows[0], rows[1], rows[2], _native.stream_ptr()))
         self._counter.add_(1)
-        return actions, logprob, ent
+        return actions, logprob, ent, value_out
 
-    def forward(self, x, action=None):
-        return self.get_action_and_value(x, action)
+    def forward(self, x, action=None, out=None):
+        return self.get_action_and_value(x, action, out)

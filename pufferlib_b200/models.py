@@ -8,6 +8,7 @@ Same architecture and call convention as the reference (adjacent to the hot path
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional  # noqa: F401
 
 
 def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
@@ -33,7 +34,13 @@ class Default(nn.Module):
         return torch.relu(self.encoder(observations.float())), None
 
     def decode_actions(self, hidden, lookup, concat=True):
-        return self.decoder(hidden), self.value_head(hidden)
+        # both heads out of ONE GEMM (same parameters, same math as two nn.Linear calls): the value head is a
+        # 1-column GEMV that would otherwise re-read `hidden`
+        n_act = self.decoder.out_features
+        w = torch.cat([self.decoder.weight, self.value_head.weight], dim=0)
+        b = torch.cat([self.decoder.bias, self.value_head.bias], dim=0)
+        out = torch.nn.functional.linear(hidden, w, b)
+        return out[:, :n_act], out[:, n_act:]
 
 
 class Convolutional(nn.Module):

@@ -52,8 +52,8 @@ def test_sample_logits_logprob_entropy_match_torch(n, n_act):
     value = torch.randn(n, device=dev)
     vr, lr, ar = torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros(n, dtype=torch.int64, device=dev)
     _native.check(_native.lib().pb_sample_logits(
-        _native.ptr(logits), n, n_act, C.c_uint64(7), C.c_uint64(3), None, _native.ptr(actions), _native.ptr(logprob),
-        _native.ptr(ent), _native.ptr(value), _native.ptr(vr), _native.ptr(lr), _native.ptr(ar), _native.stream_ptr()))
+        _native.ptr(logits), n_act, n, n_act, C.c_uint64(7), C.c_uint64(3), None, _native.ptr(actions), _native.ptr(logprob),
+        _native.ptr(ent), _native.ptr(value), 1, _native.ptr(vr), _native.ptr(lr), _native.ptr(ar), _native.stream_ptr()))
     assert int(actions.min()) >= 0 and int(actions.max()) < n_act
     _, ref_lp, ref_ent = cleanrl.sample_logits(logits, action=actions)      # torch formulation, same actions
     assert torch.allclose(logprob, ref_lp, rtol=1e-5, atol=1e-5)
@@ -71,10 +71,36 @@ def test_sample_logits_distribution():
     acts = []
     for off in (0, 1):
         a = torch.empty(n, dtype=torch.int64, device=dev)
-        _native.check(_native.lib().pb_sample_logits(_native.ptr(logits), n, n_act, C.c_uint64(1), C.c_uint64(off), None,
-                                                     _native.ptr(a), None, None, None, None, None, None,
+        _native.check(_native.lib().pb_sample_logits(_native.ptr(logits), n_act, n, n_act, C.c_uint64(1), C.c_uint64(off), None,
+                                                     _native.ptr(a), None, None, None, 1, None, None, None,
                                                      _native.stream_ptr()))
         acts.append(a)
         freq = np.bincount(a.cpu().numpy(), minlength=n_act) / n
         assert np.abs(freq - p).max() < 5 * np.sqrt(p.max() / n) + 1e-3
     assert not torch.equal(acts[0], acts[1])
+
+
+def test_fused_policy_writes_rollout_rows_and_strided_heads():
+    """cleanrl.Policy(fused_sample=True): both heads come out of one GEMM (strided logits / value) and the epilogue
+    writes value / logprob / action straight into the given rollout rows."""
+    import pufferlib_b200.vector as pvec
+    from pufferlib_b200 import models
+    from pufferlib_b200.environments import ocean
+    vec = pvec.make(ocean.env_creator('breakout'), num_envs=257, backend=pvec.B200)
+    torch.manual_seed(0)
+    pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=3).cuda()
+    obs = torch.randn(257, 128, device='cuda')
+    vr, lr = torch.zeros(257, device='cuda'), torch.zeros(257, device='cuda')
+    ar = torch.full((257,), -1, dtype=torch.int64, device='cuda')
+    with torch.no_grad():
+        a, lp, ent, v = pol(obs, out=(vr, lr, ar))
+        assert a.data_ptr() == ar.data_ptr() and lp.data_ptr() == lr.data_ptr() and v.data_ptr() == vr.data_ptr()
+        _, ref_lp, ref_ent, ref_v = pol(obs, action=ar)           # torch formulation on the same actions
+    assert int(ar.min()) >= 0 and int(ar.max()) < 4
+    assert torch.allclose(lr, ref_lp, atol=1e-5) and torch.allclose(ent, ref_ent, atol=1e-5)
+    assert torch.allclose(vr, ref_v.flatten(), atol=1e-6)
+    # two heads in one GEMM == two separate Linear layers
+    hid = torch.relu(pol.policy.encoder(obs))
+    assert torch.allclose(pol.policy.decode_actions(hid, None)[0], pol.policy.decoder(hid), atol=1e-4)
+    assert torch.allclose(pol.policy.decode_actions(hid, None)[1], pol.policy.value_head(hid), atol=1e-4)
+    vec.close()
