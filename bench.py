@@ -236,8 +236,16 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
         v['share_s'] = v['seconds'] * v['launches_per_step']
     dom = max(out, key=lambda k: out[k]['share_s'])
     d = out[dom]
+    # DRAM traffic per launch from the committed `ncu --set full` capture of this workload (profiles/), else null
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic_r01.json')))['bytes_per_launch']
+        if args.env == 'breakout' and n == 16384 and h == 128:
+            traffic = tr.get({'env_step': 'breakout', 'gae': 'gae', 'obs_gather': 'gather'}[dom])
+    except Exception:
+        pass
     roof = {'bound': 'hbm', 'kernel': d['kernel'], 'achieved': round(d['achieved'], 1), 'peak': peak_gbs,
-            'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(d['frac'], 4), 'traffic': None,
+            'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(d['frac'], 4), 'traffic': traffic,
             'algorithmic_bytes_per_launch': d['bytes_per_launch'], 'avg_launch_us': round(d['seconds'] * 1e6, 2)}
     others = {k: {'kernel': v['kernel'], 'achieved': round(v['achieved'], 1), 'frac': round(v['frac'], 4),
                   'avg_launch_us': round(v['seconds'] * 1e6, 2), 'algorithmic_bytes_per_launch': v['bytes_per_launch']}

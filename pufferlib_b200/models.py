@@ -37,10 +37,11 @@ class Default(nn.Module):
         # both heads out of ONE GEMM (same parameters, same math as two nn.Linear calls): the value head is a
         # 1-column GEMV that would otherwise re-read `hidden`
         n_act = self.decoder.out_features
-        w = torch.cat([self.decoder.weight, self.value_head.weight], dim=0)
-        b = torch.cat([self.decoder.bias, self.value_head.bias], dim=0)
+        pad = (-(n_act + 1)) % 8          # zero rows up to a multiple of 8 columns: keeps the aligned GEMM kernels
+        w = torch.cat([self.decoder.weight, self.value_head.weight, hidden.new_zeros(pad, hidden.shape[1])], dim=0)
+        b = torch.cat([self.decoder.bias, self.value_head.bias, hidden.new_zeros(pad)], dim=0)
         out = torch.nn.functional.linear(hidden, w, b)
-        return out[:, :n_act], out[:, n_act:]
+        return out[:, :n_act], out[:, n_act:n_act + 1]
 
 
 class Convolutional(nn.Module):
