@@ -191,6 +191,22 @@ int pb_sample_logits(const float* logits, int64_t logits_stride, int64_t n, int3
                      const float* value, int64_t value_stride, float* values_row, float* logprobs_row,
                      int64_t* actions_row, void* stream);
 
+/* -- structured observation pack / unpack --------------------------------------------------------
+ * Replaces, for N samples at once, `emulate` / `nativize` (pufferlib/extensions.pyx:19-30, 32-49): leaf tensors
+ * [N][nbytes[k]] <-> C-aligned records [N][record_bytes] whose layout is `np.dtype(..., align=True)` of the space
+ * (pufferlib/emulation.py:68-80; computed by the host layer).  Padding bytes are packed as zero.  `leaves_host` is a
+ * HOST array of n_leaves DEVICE pointers.  Up to 32 leaves. */
+typedef struct {
+    int32_t n_leaves;
+    int32_t record_bytes;
+    int32_t offset[32]; /* byte offset of leaf k inside a record */
+    int32_t nbytes[32]; /* byte size of leaf k */
+} pb_struct_layout;
+int pb_struct_pack(const pb_struct_layout* layout, const void* const* leaves_host, void* records, int64_t record_stride,
+                   int64_t n, void* stream);
+int pb_struct_unpack(const pb_struct_layout* layout, const void* records, int64_t record_stride,
+                     void* const* leaves_host, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,8 +103,6 @@ class Experience:
             minibatch_size = batch_size
         if cpu_offload:
             raise NotImplementedError('cpu_offload: the B200 rollout is device-resident by design')
-        if lstm is not None:
-            raise NotImplementedError('LSTM policies are not on the device path yet (SURVEY §8f-4)')
         if len(tuple(atn_shape)) != 0:
             raise NotImplementedError('only Discrete action spaces are on the device path')
         obs_dtype = numpy_to_torch_dtype_dict[np.dtype(obs_dtype)]
@@ -121,6 +119,11 @@ class Experience:
         self.truncateds = torch.zeros(batch_size, **z)   # never written, as in the reference
         self.values = torch.zeros(batch_size, **z)
         self.lstm_h = self.lstm_c = None
+        if lstm is not None:     # clean_pufferl.py:407-412
+            assert lstm_total_agents > 0
+            shape = (lstm.num_layers, lstm_total_agents, lstm.hidden_size)
+            self.lstm_h = torch.zeros(shape, **z)
+            self.lstm_c = torch.zeros(shape, **z)
 
         num_minibatches = batch_size / minibatch_size
         self.num_minibatches = int(num_minibatches)
@@ -355,7 +358,12 @@ def _rollout_loop(data, infos):
                 io.h2d += o.nbytes + r.nbytes + d.nbytes
 
         with profile.eval_forward, torch.no_grad():
-            if data.fused_rows and experience.num_envs is not None:
+            if experience.lstm_h is not None:
+                # clean_pufferl.py:100-105 with env_id == every env: the state tensors are updated in place
+                actions, logprob, _, value, (h, c) = policy(o_device, (experience.lstm_h, experience.lstm_c))
+                experience.lstm_h.copy_(h)
+                experience.lstm_c.copy_(c)
+            elif data.fused_rows and experience.num_envs is not None:
                 actions, logprob, _, value = policy(o_device, out=experience.rows())
             else:
                 actions, logprob, _, value = policy(o_device)
@@ -443,6 +451,7 @@ def train(data):
     acc = torch.zeros(6, device=device)       # policy, value, entropy, old_kl, kl, clipfrac
     obs_shape = data.vecenv.single_observation_space.shape
     for epoch in range(config.update_epochs):
+        lstm_state = None
         for mb in range(n_mb):
             with profile.train_misc:
                 obs = experience.b_obs[mb]
@@ -453,7 +462,11 @@ def train(data):
                 ret = experience.b_returns[mb]
 
             with profile.train_forward:
-                _, newlogprob, entropy, newvalue = data.policy(obs.reshape(-1, *obs_shape), action=atn)
+                if experience.lstm_h is not None:       # clean_pufferl.py:188-191: [rows, bptt, *obs] segments
+                    _, newlogprob, entropy, newvalue, lstm_state = data.policy(obs, state=lstm_state, action=atn)
+                    lstm_state = (lstm_state[0].detach(), lstm_state[1].detach())
+                else:
+                    _, newlogprob, entropy, newvalue = data.policy(obs.reshape(-1, *obs_shape), action=atn)
 
             with profile.train_misc:
                 logratio = newlogprob - log_probs.reshape(-1)

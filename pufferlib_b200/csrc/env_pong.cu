@@ -83,6 +83,15 @@ __global__ void __launch_bounds__(PG_THREADS) k_pong(PongState st, int n, const 
         const int s = it % PG_STAGES;
         unsigned char* buf = smem + (size_t)s * STAGE_BYTES;
         unsigned char* frame = buf + 3 * FRAME;
+        // refill the stage that was stored one iteration ago: by now its bulk store has long read shared memory, so
+        // this wait does not stall, and the load gets PG_STAGES - 1 iterations of lead time
+        if (tid == 0 && it > 0) {
+            const int64_t e_next = e + step * (PG_STAGES - 1);
+            if (e_next < n) {
+                tma_wait_read<0>();
+                issue_load((it - 1) % PG_STAGES, e_next);
+            }
+        }
         // ---- integer physics, computed redundantly by every thread (same inputs: broadcast loads)
         const uint64_t seed_e = st.seed + (uint64_t)e;
         PongEnv p;
@@ -165,15 +174,10 @@ __global__ void __launch_bounds__(PG_THREADS) k_pong(PongState st, int n, const 
                 for (int k = 0; k < 4; ++k) tma_store_1d(row + (size_t)k * FRAME, frame, FRAME);
             }
             tma_commit();
-            const int64_t e_next = e + step * PG_STAGES;
-            if (e_next < n) {
-                tma_wait_read<0>();                // this stage's shared memory has been read by its store
-                issue_load(s, e_next);
-            }
         }
         if (loaded) phase[s] ^= 1;
-        // no trailing barrier: the next iteration uses another stage; this stage is rewritten only after
-        // PG_STAGES - 1 further iterations, each of which contains block barriers after thread 0's wait_read
+        // no trailing barrier: the next iteration uses another stage; this stage is refilled by thread 0 at the top of
+        // the next iteration (after wait_read) and rendered into PG_STAGES iterations later, behind block barriers
     }
     if (tid == 0) tma_wait_all<0>();
 }

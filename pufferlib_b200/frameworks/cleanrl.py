@@ -84,3 +84,28 @@ class Policy(torch.nn.Module):
 
     def forward(self, x, action=None, out=None):
         return self.get_action_and_value(x, action, out)
+
+
+class RecurrentPolicy(torch.nn.Module):
+    """Wrap a recurrent model (reference: pufferlib/frameworks/cleanrl.py:69-93):
+    forward(x, state=None, action=None) -> (action, logprob, entropy, value, state)."""
+
+    def __init__(self, policy):
+        super().__init__()
+        self.policy = policy
+
+    @property
+    def lstm(self):
+        if hasattr(self.policy, 'recurrent'):
+            return self.policy.recurrent
+        if hasattr(self.policy, 'lstm'):
+            return self.policy.lstm
+        raise ValueError('Policy must have a subnetwork named lstm or recurrent')
+
+    def get_action_and_value(self, x, state=None, action=None):
+        logits, value, state = self.policy(x, state)
+        action, logprob, ent = sample_logits(logits, action)
+        return action, logprob, ent, value, state
+
+    def forward(self, x, state=None, action=None):
+        return self.get_action_and_value(x, state, action)

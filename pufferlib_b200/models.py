@@ -44,6 +44,40 @@ class Default(nn.Module):
         return out[:, :n_act], out[:, n_act:n_act + 1]
 
 
+class LSTMWrapper(nn.Module):
+    """Recurrent wrapper around a policy that defines encode_observations / decode_actions (reference:
+    pufferlib/models.py:64-111): obs [B, *obs] or [B, T, *obs] -> encode -> nn.LSTM (cuDNN) over T -> decode.
+    Returns (logits, value, state)."""
+
+    def __init__(self, env, policy, input_size=128, hidden_size=128, num_layers=1):
+        super().__init__()
+        self.obs_shape = tuple(env.single_observation_space.shape)
+        self.policy = policy
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.recurrent = nn.LSTM(input_size, hidden_size, num_layers)
+        for name, param in self.recurrent.named_parameters():
+            if 'bias' in name:
+                nn.init.constant_(param, 0)
+            elif 'weight' in name:
+                nn.init.orthogonal_(param, 1.0)
+
+    def forward(self, x, state):
+        nd = len(self.obs_shape)
+        if tuple(x.shape[-nd:]) != self.obs_shape or x.dim() not in (nd + 1, nd + 2):
+            raise ValueError('Invalid input tensor shape', x.shape)
+        batch, steps = (x.shape[0], 1) if x.dim() == nd + 1 else (x.shape[0], x.shape[1])
+        if state is not None:
+            assert state[0].shape[1] == state[1].shape[1] == batch
+        hidden, lookup = self.policy.encode_observations(x.reshape(batch * steps, *self.obs_shape))
+        assert hidden.shape == (batch * steps, self.input_size)
+        seq = hidden.reshape(batch, steps, self.input_size).transpose(0, 1)       # [T, B, F] for nn.LSTM
+        seq, state = self.recurrent(seq, state)
+        flat = seq.transpose(0, 1).reshape(batch * steps, self.hidden_size)
+        logits, value = self.policy.decode_actions(flat, lookup)
+        return logits, value, state
+
+
 class Convolutional(nn.Module):
     def __init__(self, env, *args, framestack=4, flat_size=64 * 7 * 7, input_size=512, hidden_size=512,
                  output_size=512, channels_last=False, downsample=1, **kwargs):

@@ -72,3 +72,58 @@ class MultiDiscrete:
 
     def __repr__(self):
         return f'MultiDiscrete(n={self.nvec[0] if self.nvec.size else 0} x {self.nvec.size})'
+
+
+class Dict:
+    """Ordered mapping of sub-spaces (gymnasium.spaces.Dict surface used by emulation.dtype_from_space)."""
+
+    def __init__(self, spaces=None, **kw):
+        self.spaces = dict(spaces or {}, **kw)
+
+    def items(self):
+        return self.spaces.items()
+
+    def values(self):
+        return self.spaces.values()
+
+    def keys(self):
+        return self.spaces.keys()
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+    def __iter__(self):
+        return iter(self.spaces)
+
+    def sample(self):
+        return {k: s.sample() for k, s in self.spaces.items()}
+
+    def contains(self, x):
+        return isinstance(x, dict) and all(k in x and s.contains(x[k]) for k, s in self.spaces.items())
+
+    def __eq__(self, other):
+        return isinstance(other, Dict) and self.spaces == other.spaces
+
+
+class Tuple:
+    def __init__(self, spaces):
+        self.spaces = tuple(spaces)
+
+    def __iter__(self):
+        return iter(self.spaces)
+
+    def __len__(self):
+        return len(self.spaces)
+
+    def __getitem__(self, i):
+        return self.spaces[i]
+
+    def sample(self):
+        return tuple(s.sample() for s in self.spaces)
+
+    def contains(self, x):
+        return isinstance(x, tuple) and len(x) == len(self.spaces) and all(
+            s.contains(v) for s, v in zip(self.spaces, x))
+
+    def __eq__(self, other):
+        return isinstance(other, Tuple) and self.spaces == other.spaces

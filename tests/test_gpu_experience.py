@@ -144,3 +144,67 @@ def test_copy_rows_and_store():
     _native.check(lib.pb_rollout_store(_native.ptr(v), _native.ptr(lp), _native.ptr(a), _native.ptr(vr), _native.ptr(lr),
                                        _native.ptr(ar), n, _native.stream_ptr()))
     assert torch.equal(v, vr) and torch.equal(lp, lr) and torch.equal(a, ar)
+
+
+def make_config(n, h, **kw):
+    import pufferlib_b200
+    cfg = dict(seed=1, torch_deterministic=True, env='squared', batch_size=n * h, bptt_horizon=8, minibatch_size=n * h // 2,
+               cpu_offload=False, device='cuda', compile=False, learning_rate=2.5e-4, gamma=0.99, gae_lambda=0.95,
+               update_epochs=2, norm_adv=True, clip_coef=0.1, clip_vloss=True, vf_clip_coef=0.1, vf_coef=0.5,
+               ent_coef=0.01, max_grad_norm=0.5, target_kl=None, anneal_lr=False, total_timesteps=10 ** 9)
+    cfg.update(kw)
+    return pufferlib_b200.namespace(**cfg)
+
+
+def test_evaluate_train_loop_eager_graph_and_host_modes():
+    """create / evaluate / train with the reference signatures: eager device rollout, CUDA-graph rollout and the
+    host-buffer (numpy in/out) mode all produce finite losses, and the rollout they store replays bit-exactly
+    through the oracle (same actions -> same obs / rewards / dones)."""
+    from pufferlib_b200 import models
+    from pufferlib_b200.frameworks import cleanrl
+    from oracle.squared import SquaredSerial
+    n, h = 64, 32
+    for mode in ('eager', 'graph', 'host'):
+        backend = pvec.B200.options(host_buffers=(mode == 'host'))
+        vec = pvec.make(ocean.env_creator('squared'), num_envs=n, backend=backend)
+        torch.manual_seed(0)
+        pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=(mode != 'host'), seed=1).cuda()
+        data = clean_pufferl.create(make_config(n, h, cuda_graph=(mode == 'graph')), vec, pol)
+        ora = SquaredSerial(n)
+        ora.async_reset(1)
+        for it in range(3):                      # iteration 2 is the first graph replay
+            stats, infos = clean_pufferl.evaluate(data)
+            exp = data.experience
+            acts = cpu(exp.actions).reshape(h, n)
+            obs, rew, don = cpu(exp.obs).reshape(h, n, 7, 7), cpu(exp.rewards).reshape(h, n), cpu(exp.dones).reshape(h, n)
+            for t in range(h):
+                o, r, d, _, _, _, _ = ora.recv()
+                assert np.array_equal(o, obs[t]) and np.array_equal(r, rew[t]) and np.array_equal(d, don[t] > 0), (mode, it, t)
+                ora.send(acts[t])
+            clean_pufferl.train(data)
+            assert np.isfinite(data.losses.policy_loss) and np.isfinite(data.losses.value_loss)
+            assert data.global_step == (it + 1) * n * h
+            assert 'episode_return' in stats
+        if mode == 'graph':
+            assert data.graph_replays == 2 and data.graph_launches > 0
+        clean_pufferl.close(data)
+
+
+def test_lstm_policy_path():
+    """Recurrent policies (LSTMWrapper + RecurrentPolicy): state carried across env steps in evaluate and across
+    bptt segments in train (clean_pufferl.py:100-105, 188-191)."""
+    from pufferlib_b200 import models
+    from pufferlib_b200.frameworks import cleanrl
+    n, h = 32, 16
+    vec = pvec.make(ocean.env_creator('squared'), num_envs=n, backend=pvec.B200)
+    torch.manual_seed(0)
+    net = models.LSTMWrapper(vec.driver_env, models.Default(vec.driver_env), input_size=128, hidden_size=128)
+    pol = cleanrl.RecurrentPolicy(net).cuda()
+    data = clean_pufferl.create(make_config(n, h), vec, pol)
+    assert data.experience.lstm_h.shape == (1, n, 128)
+    for _ in range(2):
+        clean_pufferl.evaluate(data)
+        assert float(data.experience.lstm_h.abs().sum()) > 0
+        clean_pufferl.train(data)
+        assert np.isfinite(data.losses.policy_loss) and np.isfinite(data.losses.entropy)
+    clean_pufferl.close(data)
