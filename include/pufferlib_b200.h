@@ -80,8 +80,8 @@ typedef struct {
     int64_t obs_stride;   /* bytes between consecutive envs' rows (>= obs_bytes) */
     float* rewards;       /* [N] fp32                          (buf.rewards,     emulation.py:219-221) */
     uint8_t* terminals;   /* [N] bool as one byte               (buf.terminals)   */
-    uint8_t* truncations; /* [N] bool, always 0 for these envs  (buf.truncations) */
-    uint8_t* masks;       /* [N] bool, always 1                 (buf.masks)       */
+    uint8_t* truncations; /* [N] bool, always 0 for these envs  (buf.truncations); constants: written by reset, and by */
+    uint8_t* masks;       /* [N] bool, always 1 (buf.masks)       a step only into buffers other than the previous call's */
     float* dones_f32;     /* optional [N]: terminal as 0.f/1.f  (Experience.dones, clean_pufferl.py:395,447); may be NULL */
 } pb_env_out;
 

@@ -126,9 +126,12 @@ extern "C" int pb_env_reset(pb_env* env, uint64_t seed, const pb_env_out* out, v
     int rc = check_out(env, out, "pb_env_reset");
     if (rc) return rc;
     PB_CUDA(cudaSetDevice(env->cfg.device));
+    env->write_const = true;
     rc = env->vt->reset(env, seed, out, (cudaStream_t)stream);
     if (rc == PB_OK) {
         env->was_reset = true;
+        env->const_trunc = out->truncations;
+        env->const_masks = out->masks;
         env->cur_obs = out->obs;
         env->cur_obs_stride = out->obs_stride;
     }
@@ -142,8 +145,11 @@ extern "C" int pb_env_step(pb_env* env, const int64_t* actions, const pb_env_out
     int rc = check_out(env, out, "pb_env_step");
     if (rc) return rc;
     PB_CUDA(cudaSetDevice(env->cfg.device));
+    env->write_const = out->truncations != env->const_trunc || out->masks != env->const_masks;
     rc = env->vt->step(env, actions, out, (cudaStream_t)stream);
     if (rc == PB_OK) {
+        env->const_trunc = out->truncations;
+        env->const_masks = out->masks;
         env->cur_obs = out->obs;
         env->cur_obs_stride = out->obs_stride;
     }

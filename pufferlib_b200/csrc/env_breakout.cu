@@ -31,6 +31,7 @@ struct BkOut {
     uint8_t* truncations;
     uint8_t* masks;
     float* dones_f32;
+    bool write_const;
 };
 
 __device__ __forceinline__ uint32_t bk_draw(uint64_t seed_e, uint32_t& ctr) {
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(128) k_breakout(BreakoutState st, int n, const
         done[e] = terminal ? 1 : 0;
         out.rewards[e] = (float)reward;
         out.terminals[e] = terminal ? 1 : 0;
-        out.truncations[e] = 0;
-        out.masks[e] = 1;
+        if (out.write_const) out.truncations[e] = 0;
+        if (out.write_const) out.masks[e] = 1;
         if (out.dones_f32) out.dones_f32[e] = terminal ? 1.f : 0.f;
     }
     episode_update(acc, e, active, reset_row, (double)reward, terminal, score);
@@ -168,7 +169,8 @@ int breakout_launch(pb_env* env, int mode, const int64_t* actions, const pb_env_
     PB_REQUIRE(out->obs_stride % 16 == 0 && ((uintptr_t)out->obs & 15) == 0, PB_ERR_INVALID,
                "breakout: obs pointer/stride must be 16-byte aligned");
     BkOut o{(float*)out->obs, out->obs_stride / 4, out->rewards, out->terminals, out->truncations, out->masks,
-            out->dones_f32};
+            out->dones_f32,
+            env->write_const};
     const int blocks = (int)pb_ceil_div(n, (128 / 32) * EPW);
     if (mode == 0) k_breakout<0><<<blocks, 128, 0, s>>>(*st, n, actions, env->d_done, o, pb_episode_acc(env));
     else k_breakout<1><<<blocks, 128, 0, s>>>(*st, n, actions, env->d_done, o, pb_episode_acc(env));

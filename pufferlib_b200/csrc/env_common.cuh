@@ -32,6 +32,11 @@ struct pb_env {
     // where the previous call wrote the observations (snake / pong carry state in the obs rows)
     const void* cur_obs;
     int64_t cur_obs_stride;
+    // truncations (always 0) and masks (always 1) are constants: a step rewrites them only into buffers it has not
+    // filled before (saves two scattered [N] stores per env per step)
+    const void* const_trunc;
+    const void* const_masks;
+    bool write_const;
     void* kind;              // kind-specific state
 };
 

@@ -36,6 +36,7 @@ struct PgOut {
     uint8_t* truncations;
     uint8_t* masks;
     float* dones_f32;
+    bool write_const;
 };
 
 struct PongEnv {
@@ -149,8 +150,8 @@ __global__ void __launch_bounds__(PG_THREADS) k_pong(PongState st, int n, const 
             done[e] = terminal ? 1 : 0;
             out.rewards[e] = reward;
             out.terminals[e] = terminal ? 1 : 0;
-            out.truncations[e] = 0;
-            out.masks[e] = 1;
+            if (out.write_const) out.truncations[e] = 0;
+            if (out.write_const) out.masks[e] = 1;
             if (out.dones_f32) out.dones_f32[e] = terminal ? 1.f : 0.f;
             // EpisodeStats (postprocess.py:22-54), scalar form
             if (!loaded) { acc.ep_return[e] = 0.0; acc.ep_length[e] = 0; }
@@ -188,7 +189,8 @@ int pong_launch(pb_env* env, int mode, const int64_t* actions, const pb_env_out*
     PB_REQUIRE(out->obs_stride % 16 == 0 && ((uintptr_t)out->obs & 15) == 0, PB_ERR_INVALID,
                "pong: obs pointer/stride must be 16-byte aligned");
     PgOut o{(unsigned char*)out->obs, out->obs_stride, out->rewards, out->terminals, out->truncations, out->masks,
-            out->dones_f32};
+            out->dones_f32,
+            env->write_const};
     int grid = PB_NUM_SMS * 2;
     if (grid > n) grid = n;
     const size_t smem = (size_t)PG_STAGES * STAGE_BYTES;

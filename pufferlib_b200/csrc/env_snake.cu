@@ -29,6 +29,7 @@ struct SnOut {
     uint8_t* truncations;
     uint8_t* masks;
     float* dones_f32;
+    bool write_const;
 };
 
 __device__ __forceinline__ uint32_t get_word(const uint4& v, int i) {
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(128) k_snake(SnakeState st, int n, const int64
             done[e] = terminal ? 1 : 0;
             out.rewards[e] = reward;
             out.terminals[e] = terminal ? 1 : 0;
-            out.truncations[e] = 0;
-            out.masks[e] = 1;
+            if (out.write_const) out.truncations[e] = 0;
+            if (out.write_const) out.masks[e] = 1;
             if (out.dones_f32) out.dones_f32[e] = terminal ? 1.f : 0.f;
         }
     }
@@ -167,7 +168,8 @@ int snake_launch(pb_env* env, int mode, const int64_t* actions, const pb_env_out
     PB_REQUIRE(out->obs_stride % 16 == 0 && ((uintptr_t)out->obs & 15) == 0, PB_ERR_INVALID,
                "snake: obs pointer/stride must be 16-byte aligned");
     SnOut o{(uint8_t*)out->obs, out->obs_stride, out->rewards, out->terminals, out->truncations, out->masks,
-            out->dones_f32};
+            out->dones_f32,
+            env->write_const};
     const int blocks = (int)pb_ceil_div((int64_t)n * 16, 128);
     if (mode == 0)
         k_snake<0><<<blocks, 128, 0, s>>>(*st, n, actions, env->d_done, nullptr, 0, o, pb_episode_acc(env));

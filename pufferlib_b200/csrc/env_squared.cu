@@ -206,6 +206,7 @@ struct SqOut {
     uint8_t* truncations;
     uint8_t* masks;
     float* dones_f32;
+    bool write_const;
 };
 
 // mode 0: write reset rows for every env (after k_sq_seed); mode 1: vectoriser send (reset-or-step)
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(128) k_sq_step(SquaredState st, int n, const i
         }
         out.rewards[e] = reward;
         out.terminals[e] = terminal ? 1 : 0;
-        out.truncations[e] = 0;
-        out.masks[e] = 1;
+        if (out.write_const) out.truncations[e] = 0;
+        if (out.write_const) out.masks[e] = 1;
         if (out.dones_f32) out.dones_f32[e] = terminal ? 1.f : 0.f;
     }
     episode_update(acc, e, active, reset_row, reward_d, terminal, (float)hit);
@@ -275,7 +276,8 @@ int squared_launch(pb_env* env, int mode, const int64_t* actions, const pb_env_o
     PB_REQUIRE(out->obs_stride % 4 == 0 && ((uintptr_t)out->obs & 3) == 0, PB_ERR_INVALID,
                "squared: obs pointer/stride must be 4-byte aligned");
     SqOut o{(float*)out->obs, out->obs_stride / 4, out->rewards, out->terminals, out->truncations, out->masks,
-            out->dones_f32};
+            out->dones_f32,
+            env->write_const};
     const int blocks = (int)pb_ceil_div(n, 128);
     if (mode == 0)
         k_sq_step<0><<<blocks, 128, 0, s>>>(*st, n, actions, env->d_done, o, pb_episode_acc(env));
