@@ -191,6 +191,20 @@ int pb_sample_logits(const float* logits, int64_t logits_stride, int64_t n, int3
                      const float* value, int64_t value_stride, float* values_row, float* logprobs_row,
                      int64_t* actions_row, void* stream);
 
+/* -- PPO minibatch loss, forward + backward --------------------------------------------------------------------------
+ * Replaces the loss block of train (clean_pufferl.py:202-238) and the action-given branch of sample_logits
+ * (frameworks/cleanrl.py:25-47) for one Discrete head, for a minibatch of m rows: one pass computes
+ *   stats8[0..5] = SUMS over rows of {max(pg1,pg2), max(v_unclipped, v_clipped) (no 0.5 yet), entropy, -logratio,
+ *                  (ratio-1)-logratio, |ratio-1| > clip_coef}                      (fp64; caller divides by m)
+ * and the analytic gradients of  loss = mean(pg) - ent_coef*mean(entropy) + vf_coef*0.5*mean(v)  with respect to the
+ * logits [m][n_act] and the value [m] (already scaled by 1/m), following ATen's tie rules for maximum / clamp.
+ * `advantages` are the (already normalised, clean_pufferl.py:211-213) minibatch advantages.  Strides in floats. */
+int pb_ppo_loss(const float* logits, int64_t logits_stride, const float* value, int64_t value_stride,
+                const int64_t* actions, const float* old_logprobs, const float* advantages, const float* returns,
+                const float* old_values, int64_t m, int32_t n_act, float clip_coef, int32_t clip_vloss,
+                float vf_clip_coef, float vf_coef, float ent_coef, float* grad_logits, int64_t grad_logits_stride,
+                float* grad_value, int64_t grad_value_stride, double* stats8, void* stream);
+
 /* -- structured observation pack / unpack --------------------------------------------------------
  * Replaces, for N samples at once, `emulate` / `nativize` (pufferlib/extensions.pyx:19-30, 32-49): leaf tensors
  * [N][nbytes[k]] <-> C-aligned records [N][record_bytes] whose layout is `np.dtype(..., align=True)` of the space

@@ -94,6 +94,47 @@ class Profile:
         return True
 
 
+class _FusedPPOLoss(torch.autograd.Function):
+    """clean_pufferl.py:202-238 as ONE kernel (pb_ppo_loss): forward returns (loss, stats[6]) and stashes the analytic
+    gradients w.r.t. logits / value that backward hands to autograd for the network backward."""
+
+    @staticmethod
+    def forward(ctx, logits, value, actions, old_logprobs, adv, returns, old_values, cfg):
+        clip_coef, clip_vloss, vf_clip_coef, vf_coef, ent_coef = cfg
+        m, n_act = logits.shape
+        v2 = value.reshape(m, -1)
+        if logits.stride(1) != 1 or logits.dtype != torch.float32:
+            logits = logits.float().contiguous()
+        grad_logits = torch.empty(m, n_act, dtype=torch.float32, device=logits.device)
+        grad_value = torch.empty(m, dtype=torch.float32, device=logits.device)
+        stats = torch.empty(8, dtype=torch.float64, device=logits.device)
+        _native.check(_native.lib().pb_ppo_loss(
+            _native.ptr(logits), logits.stride(0), _native.ptr(v2), v2.stride(0),
+            _native.ptr(actions.reshape(-1).contiguous()), _native.ptr(old_logprobs.reshape(-1).contiguous()),
+            _native.ptr(adv.reshape(-1).contiguous()), _native.ptr(returns.reshape(-1).contiguous()),
+            _native.ptr(old_values.reshape(-1).contiguous()), m, n_act, C.c_float(clip_coef), int(bool(clip_vloss)),
+            C.c_float(vf_clip_coef), C.c_float(vf_coef), C.c_float(ent_coef), _native.ptr(grad_logits), n_act,
+            _native.ptr(grad_value), 1, _native.ptr(stats), _native.stream_ptr()))
+        means = stats[:6] / m
+        means[1] *= 0.5                                  # v_loss = 0.5 * mean(max(...))
+        loss = (means[0] - ent_coef * means[2] + vf_coef * means[1]).float()
+        ctx.save_for_backward(grad_logits, grad_value)
+        ctx.value_shape = value.shape
+        return loss, means.float()
+
+    @staticmethod
+    def backward(ctx, g_loss, g_stats):
+        grad_logits, grad_value = ctx.saved_tensors
+        return g_loss * grad_logits, (g_loss * grad_value).view(ctx.value_shape), None, None, None, None, None, None
+
+
+def fused_ppo_loss(logits, value, actions, old_logprobs, adv, returns, old_values, config):
+    """-> (loss, stats) with stats = [pg_loss, v_loss, entropy, old_approx_kl, approx_kl, clipfrac] (detached)."""
+    cfg = (float(config.clip_coef), bool(config.clip_vloss), float(config.vf_clip_coef), float(config.vf_coef),
+           float(config.ent_coef))
+    return _FusedPPOLoss.apply(logits, value, actions, old_logprobs, adv, returns, old_values, cfg)
+
+
 class Experience:
     """Flat tensor storage in arrival order, on the device (reference: clean_pufferl.py:380-482)."""
 
@@ -333,6 +374,9 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         graph_launches=0, graph_replays=0,
         fused_rows=bool(getattr(policy, 'fused_sample', False)) and hasattr(vecenv, 'bind_rollout')
         and not getattr(vecenv, 'host_buffers', False),
+        # one-kernel PPO loss (pb_ppo_loss): needs a wrapper exposing .policy(obs) -> (logits, value), one Discrete head
+        fused_loss=bool(getattr(config, 'fused_loss', True)) and hasattr(policy, 'policy')
+        and not hasattr(policy, 'lstm') and len(tuple(vecenv.single_action_space.shape)) == 0,
     )
 
 
@@ -461,37 +505,44 @@ def train(data):
                 adv = experience.b_advantages_normalized[mb] if config.norm_adv else experience.b_advantages[mb]
                 ret = experience.b_returns[mb]
 
+            fused = data.fused_loss and experience.lstm_h is None
             with profile.train_forward:
-                if experience.lstm_h is not None:       # clean_pufferl.py:188-191: [rows, bptt, *obs] segments
+                if fused:          # logits / value straight from the model; loss + its gradient in one kernel
+                    logits, newvalue = data.policy.policy(obs.reshape(-1, *obs_shape))
+                elif experience.lstm_h is not None:       # clean_pufferl.py:188-191: [rows, bptt, *obs] segments
                     _, newlogprob, entropy, newvalue, lstm_state = data.policy(obs, state=lstm_state, action=atn)
                     lstm_state = (lstm_state[0].detach(), lstm_state[1].detach())
                 else:
                     _, newlogprob, entropy, newvalue = data.policy(obs.reshape(-1, *obs_shape), action=atn)
 
             with profile.train_misc:
-                logratio = newlogprob - log_probs.reshape(-1)
-                ratio = logratio.exp()
-                with torch.no_grad():
-                    old_approx_kl = (-logratio).mean()
-                    approx_kl = ((ratio - 1) - logratio).mean()
-                    clipfrac = ((ratio - 1.0).abs() > config.clip_coef).float().mean()
-
-                adv = adv.reshape(-1)
-                pg_loss1 = -adv * ratio
-                pg_loss2 = -adv * torch.clamp(ratio, 1 - config.clip_coef, 1 + config.clip_coef)
-                pg_loss = torch.max(pg_loss1, pg_loss2).mean()
-
-                newvalue = newvalue.view(-1)
-                if config.clip_vloss:
-                    v_loss_unclipped = (newvalue - ret) ** 2
-                    v_clipped = val + torch.clamp(newvalue - val, -config.vf_clip_coef, config.vf_clip_coef)
-                    v_loss_clipped = (v_clipped - ret) ** 2
-                    v_loss = 0.5 * torch.max(v_loss_unclipped, v_loss_clipped).mean()
+                if fused:
+                    loss, st = fused_ppo_loss(logits, newvalue, atn, log_probs, adv, ret, val, config)
+                    pg_loss, v_loss, entropy_loss, old_approx_kl, approx_kl, clipfrac = st.unbind(0)
                 else:
-                    v_loss = 0.5 * ((newvalue - ret) ** 2).mean()
+                    logratio = newlogprob - log_probs.reshape(-1)
+                    ratio = logratio.exp()
+                    with torch.no_grad():
+                        old_approx_kl = (-logratio).mean()
+                        approx_kl = ((ratio - 1) - logratio).mean()
+                        clipfrac = ((ratio - 1.0).abs() > config.clip_coef).float().mean()
 
-                entropy_loss = entropy.mean()
-                loss = pg_loss - config.ent_coef * entropy_loss + v_loss * config.vf_coef
+                    adv = adv.reshape(-1)
+                    pg_loss1 = -adv * ratio
+                    pg_loss2 = -adv * torch.clamp(ratio, 1 - config.clip_coef, 1 + config.clip_coef)
+                    pg_loss = torch.max(pg_loss1, pg_loss2).mean()
+
+                    newvalue = newvalue.view(-1)
+                    if config.clip_vloss:
+                        v_loss_unclipped = (newvalue - ret) ** 2
+                        v_clipped = val + torch.clamp(newvalue - val, -config.vf_clip_coef, config.vf_clip_coef)
+                        v_loss_clipped = (v_clipped - ret) ** 2
+                        v_loss = 0.5 * torch.max(v_loss_unclipped, v_loss_clipped).mean()
+                    else:
+                        v_loss = 0.5 * ((newvalue - ret) ** 2).mean()
+
+                    entropy_loss = entropy.mean()
+                    loss = pg_loss - config.ent_coef * entropy_loss + v_loss * config.vf_coef
 
             with profile.learn:
                 if data.grad_bucket is not None:
