@@ -205,6 +205,18 @@ int pb_ppo_loss(const float* logits, int64_t logits_stride, const float* value, 
                 float vf_clip_coef, float vf_coef, float ent_coef, float* grad_logits, int64_t grad_logits_stride,
                 float* grad_value, int64_t grad_value_stride, double* stats8, void* stream);
 
+/* -- policy tail backward ---------------------------------------------------------------------------------------------
+ * For models.Default (pufferlib/models.py:12-62: Linear+ReLU encoder, action head + value head): everything of the
+ * backward pass after the encoder GEMM, in ONE pass over the hidden layer instead of five ATen launches:
+ *   dpre[m][H]      = (dout[m][0..7] @ w_heads[8][H]) * (hidden > 0)                  (heads dX + ReLU backward)
+ *   grads_out       = [ dW_heads (8*H) | db_enc (H) = column sums of dpre | db_heads (8) = column sums of dout ]
+ * dout holds the loss gradient w.r.t. the 8 padded head outputs (n_act logits, the value, zero padding), row stride
+ * dout_stride floats.  Deterministic (two-stage partial sums).  H = 128.  Pointers 16-byte aligned. */
+size_t pb_mlp_tail_workspace_bytes(int64_t m, int32_t hidden_size);
+int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_heads, const float* hidden, int64_t m,
+                         int32_t hidden_size, float* dpre, float* grads_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* -- structured observation pack / unpack --------------------------------------------------------
  * Replaces, for N samples at once, `emulate` / `nativize` (pufferlib/extensions.pyx:19-30, 32-49): leaf tensors
  * [N][nbytes[k]] <-> C-aligned records [N][record_bytes] whose layout is `np.dtype(..., align=True)` of the space

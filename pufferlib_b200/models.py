@@ -11,6 +11,55 @@ import torch.nn as nn
 import torch.nn.functional  # noqa: F401
 
 
+class _DefaultMLPFunction(torch.autograd.Function):
+    """models.Default as one autograd node on the device fast path.
+
+    forward : hidden = relu(x @ W_enc^T + b_enc)  -- bias + ReLU fused into the cuBLASLt GEMM epilogue;
+              out    = hidden @ W_cat^T + b_cat    -- both heads in ONE 8-column GEMM (n_act logits, value, zero pad).
+    backward: pb_mlp_tail_backward reads `hidden` once and produces dPre (heads dX + ReLU backward), dW_heads, db_heads
+              and db_enc; the dense dW_enc = dPre^T @ x stays on cuBLAS tensor cores.  x (the observations) has no grad.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w_enc, b_enc, w_dec, b_dec, w_val, b_val):
+        n_act, hid = w_dec.shape
+        try:
+            hidden = torch._addmm_activation(b_enc, x, w_enc.t(), use_gelu=False)
+        except (AttributeError, RuntimeError):
+            hidden = torch.relu(torch.addmm(b_enc, x, w_enc.t()))
+        w_cat = x.new_zeros(8, hid)
+        w_cat[:n_act] = w_dec
+        w_cat[n_act] = w_val[0]
+        b_cat = x.new_zeros(8)
+        b_cat[:n_act] = b_dec
+        b_cat[n_act] = b_val[0]
+        out = torch.addmm(b_cat, hidden, w_cat.t())
+        ctx.save_for_backward(x, hidden, w_cat)
+        ctx.n_act = n_act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        import ctypes as C
+        from pufferlib_b200 import _native
+        x, hidden, w_cat = ctx.saved_tensors
+        n_act, (m, hid) = ctx.n_act, hidden.shape
+        dout = dout.contiguous()
+        dpre = torch.empty_like(hidden)
+        grads = torch.empty(8 * hid + hid + 8, dtype=torch.float32, device=x.device)
+        lib = _native.lib()
+        ws = torch.empty(lib.pb_mlp_tail_workspace_bytes(m, hid), dtype=torch.uint8, device=x.device)
+        _native.check(lib.pb_mlp_tail_backward(_native.ptr(dout), dout.stride(0), _native.ptr(w_cat), _native.ptr(hidden),
+                                               m, hid, _native.ptr(dpre), _native.ptr(grads), _native.ptr(ws),
+                                               ws.numel(), _native.stream_ptr()))
+        dw_cat = grads[:8 * hid].view(8, hid)
+        db_enc = grads[8 * hid:9 * hid]
+        db_cat = grads[9 * hid:]
+        dw_enc = dpre.t() @ x
+        return (None, dw_enc, db_enc, dw_cat[:n_act], db_cat[:n_act], dw_cat[n_act:n_act + 1],
+                db_cat[n_act:n_act + 1])
+
+
 def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
     torch.nn.init.orthogonal_(layer.weight, std)
     torch.nn.init.constant_(layer.bias, bias_const)
@@ -23,8 +72,16 @@ class Default(nn.Module):
         self.encoder = nn.Linear(int(np.prod(env.single_observation_space.shape)), hidden_size)
         self.decoder = layer_init(nn.Linear(hidden_size, env.single_action_space.n), std=0.01)
         self.value_head = nn.Linear(hidden_size, 1)
+        self.fast_path = True     # fused forward epilogues + pb_mlp_tail_backward (CUDA, hidden 128, <= 7 actions)
 
     def forward(self, observations):
+        x = observations.view(observations.shape[0], -1)
+        n_act, hid = self.decoder.weight.shape
+        if self.fast_path and x.is_cuda and hid == 128 and n_act + 1 <= 8 and not x.requires_grad:
+            out = _DefaultMLPFunction.apply(x.float().contiguous(), self.encoder.weight, self.encoder.bias,
+                                            self.decoder.weight, self.decoder.bias, self.value_head.weight,
+                                            self.value_head.bias)
+            return out[:, :n_act], out[:, n_act:n_act + 1]
         hidden, lookup = self.encode_observations(observations)
         return self.decode_actions(hidden, lookup)
 

@@ -81,3 +81,31 @@ def test_ppo_loss_through_strided_views_and_scaling():
     (3.0 * ref).backward()
     assert torch.allclose(out.grad, out2.grad, rtol=1e-4, atol=1e-7)
     assert float(out.grad[:, n_act + 1:].abs().sum()) == 0.0
+
+
+def test_default_mlp_fast_path_matches_plain_modules():
+    """models.Default fast path (fused GEMM epilogues + pb_mlp_tail_backward) vs the plain nn.Linear / relu composition:
+    same outputs and the same parameter gradients (TF32 tensor-core GEMMs on both sides -> ~1e-3 relative)."""
+    import pufferlib_b200.vector as pvec
+    from pufferlib_b200 import models
+    from pufferlib_b200.environments import ocean
+    dev = torch.device('cuda')
+    vec = pvec.make(ocean.env_creator('breakout'), num_envs=4, backend=pvec.B200)
+    torch.manual_seed(0)
+    net = models.Default(vec.driver_env).to(dev)
+    for m in (1, 37, 4096, 70001):
+        x = torch.randn(m, 128, device=dev)
+        g_logits, g_value = torch.randn(m, 4, device=dev), torch.randn(m, 1, device=dev)
+        grads = []
+        for fast in (True, False):
+            net.fast_path = fast
+            net.zero_grad()
+            logits, value = net(x)
+            ((logits * g_logits).sum() + (value * g_value).sum()).backward()
+            grads.append((logits.detach(), value.detach(), [p.grad.clone() for p in net.parameters()]))
+        (l1, v1, g1), (l0, v0, g0) = grads
+        assert torch.allclose(l1, l0, rtol=2e-3, atol=2e-3) and torch.allclose(v1, v0, rtol=2e-3, atol=2e-3)
+        for a, b in zip(g1, g0):
+            scale = float(b.abs().max()) + 1e-6
+            assert float((a - b).abs().max()) <= 5e-3 * scale, (m, float((a - b).abs().max()), scale)
+    vec.close()
