@@ -99,40 +99,69 @@ class _FusedPPOLoss(torch.autograd.Function):
     gradients w.r.t. logits / value that backward hands to autograd for the network backward."""
 
     @staticmethod
-    def forward(ctx, logits, value, actions, old_logprobs, adv, returns, old_values, cfg):
+    def forward(ctx, logits, value, actions, old_logprobs, adv, returns, old_values, cfg, packed_n_act):
+        """packed_n_act > 0: `logits` is the packed head output [M, 8] (logits | value | zero pad) and `value` is
+        ignored; the gradient comes back as ONE [M, 8] tensor (no slice/cat nodes in the autograd graph)."""
         clip_coef, clip_vloss, vf_clip_coef, vf_coef, ent_coef = cfg
-        m, n_act = logits.shape
-        v2 = value.reshape(m, -1)
-        if logits.stride(1) != 1 or logits.dtype != torch.float32:
-            logits = logits.float().contiguous()
-        grad_logits = torch.empty(m, n_act, dtype=torch.float32, device=logits.device)
-        grad_value = torch.empty(m, dtype=torch.float32, device=logits.device)
-        stats = torch.empty(8, dtype=torch.float64, device=logits.device)
+        dev = logits.device
+        if packed_n_act:
+            out, n_act = logits, packed_n_act
+            m = out.shape[0]
+            assert out.stride(1) == 1 and out.dtype == torch.float32
+            l_ptr, l_stride = out.data_ptr(), out.stride(0)
+            v_ptr, v_stride = out.data_ptr() + 4 * n_act, out.stride(0)
+            grad = torch.zeros_like(out) if out.shape[1] > n_act + 1 else torch.empty_like(out)
+            gl_ptr, gl_stride, gv_ptr, gv_stride = grad.data_ptr(), grad.stride(0), grad.data_ptr() + 4 * n_act, grad.stride(0)
+            ctx.packed = True
+            ctx.save_for_backward(grad)
+        else:
+            m, n_act = logits.shape
+            v2 = value.reshape(m, -1)
+            if logits.stride(1) != 1 or logits.dtype != torch.float32:
+                logits = logits.float().contiguous()
+            grad_logits = torch.empty(m, n_act, dtype=torch.float32, device=dev)
+            grad_value = torch.empty(m, dtype=torch.float32, device=dev)
+            l_ptr, l_stride, v_ptr, v_stride = logits.data_ptr(), logits.stride(0), v2.data_ptr(), v2.stride(0)
+            gl_ptr, gl_stride, gv_ptr, gv_stride = grad_logits.data_ptr(), n_act, grad_value.data_ptr(), 1
+            ctx.packed = False
+            ctx.save_for_backward(grad_logits, grad_value)
+            ctx.value_shape = value.shape
+        stats = torch.empty(8, dtype=torch.float64, device=dev)
+        cp = C.c_void_p
         _native.check(_native.lib().pb_ppo_loss(
-            _native.ptr(logits), logits.stride(0), _native.ptr(v2), v2.stride(0),
+            cp(l_ptr), l_stride, cp(v_ptr), v_stride,
             _native.ptr(actions.reshape(-1).contiguous()), _native.ptr(old_logprobs.reshape(-1).contiguous()),
             _native.ptr(adv.reshape(-1).contiguous()), _native.ptr(returns.reshape(-1).contiguous()),
             _native.ptr(old_values.reshape(-1).contiguous()), m, n_act, C.c_float(clip_coef), int(bool(clip_vloss)),
-            C.c_float(vf_clip_coef), C.c_float(vf_coef), C.c_float(ent_coef), _native.ptr(grad_logits), n_act,
-            _native.ptr(grad_value), 1, _native.ptr(stats), _native.stream_ptr()))
+            C.c_float(vf_clip_coef), C.c_float(vf_coef), C.c_float(ent_coef), cp(gl_ptr), gl_stride, cp(gv_ptr),
+            gv_stride, _native.ptr(stats), _native.stream_ptr()))
         means = stats[:6] / m
         means[1] *= 0.5                                  # v_loss = 0.5 * mean(max(...))
         loss = (means[0] - ent_coef * means[2] + vf_coef * means[1]).float()
-        ctx.save_for_backward(grad_logits, grad_value)
-        ctx.value_shape = value.shape
         return loss, means.float()
 
     @staticmethod
     def backward(ctx, g_loss, g_stats):
+        if ctx.packed:
+            (grad,) = ctx.saved_tensors
+            return g_loss * grad, None, None, None, None, None, None, None, None
         grad_logits, grad_value = ctx.saved_tensors
-        return g_loss * grad_logits, (g_loss * grad_value).view(ctx.value_shape), None, None, None, None, None, None
+        return (g_loss * grad_logits, (g_loss * grad_value).view(ctx.value_shape), None, None, None, None, None, None,
+                None)
 
 
 def fused_ppo_loss(logits, value, actions, old_logprobs, adv, returns, old_values, config):
     """-> (loss, stats) with stats = [pg_loss, v_loss, entropy, old_approx_kl, approx_kl, clipfrac] (detached)."""
     cfg = (float(config.clip_coef), bool(config.clip_vloss), float(config.vf_clip_coef), float(config.vf_coef),
            float(config.ent_coef))
-    return _FusedPPOLoss.apply(logits, value, actions, old_logprobs, adv, returns, old_values, cfg)
+    return _FusedPPOLoss.apply(logits, value, actions, old_logprobs, adv, returns, old_values, cfg, 0)
+
+
+def fused_ppo_loss_packed(out, n_act, actions, old_logprobs, adv, returns, old_values, config):
+    """Same, on the packed head output [M, 8] of models.Default.forward_packed (one [M, 8] gradient back)."""
+    cfg = (float(config.clip_coef), bool(config.clip_vloss), float(config.vf_clip_coef), float(config.vf_coef),
+           float(config.ent_coef))
+    return _FusedPPOLoss.apply(out, None, actions, old_logprobs, adv, returns, old_values, cfg, int(n_act))
 
 
 class Experience:
@@ -358,7 +387,8 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         raise NotImplementedError('torch.compile is not used on the B200 path (no Triton); set compile=False')
 
     if optimizer is None:
-        optimizer = torch.optim.Adam(policy.parameters(), lr=config.learning_rate, eps=1e-5)
+        # same update rule as the reference's Adam (clean_pufferl.py:54-55); fused=True applies it in one kernel
+        optimizer = torch.optim.Adam(policy.parameters(), lr=config.learning_rate, eps=1e-5, fused=True)
 
     grad_bucket = None
     if torch.distributed.is_available() and torch.distributed.is_initialized() and \
@@ -447,6 +477,9 @@ def evaluate(data):
         if data.graph_state == 1:
             torch.cuda.synchronize()
             step0, launches0 = data.global_step, _native.lib().pb_launch_count()
+            cache = getattr(getattr(data.policy, 'policy', None), '_head_cache', None)
+            if cache is not None:
+                cache.clear()                    # anything cached eagerly must be rebuilt inside the capture
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 _rollout_loop(data, infos)       # python-side state advances exactly as in an eager rollout
@@ -507,8 +540,13 @@ def train(data):
 
             fused = data.fused_loss and experience.lstm_h is None
             with profile.train_forward:
+                packed = None
                 if fused:          # logits / value straight from the model; loss + its gradient in one kernel
-                    logits, newvalue = data.policy.policy(obs.reshape(-1, *obs_shape))
+                    model = data.policy.policy
+                    if hasattr(model, 'forward_packed'):
+                        packed = model.forward_packed(obs.reshape(-1, *obs_shape))
+                    if packed is None:
+                        logits, newvalue = model(obs.reshape(-1, *obs_shape))
                 elif experience.lstm_h is not None:       # clean_pufferl.py:188-191: [rows, bptt, *obs] segments
                     _, newlogprob, entropy, newvalue, lstm_state = data.policy(obs, state=lstm_state, action=atn)
                     lstm_state = (lstm_state[0].detach(), lstm_state[1].detach())
@@ -517,7 +555,10 @@ def train(data):
 
             with profile.train_misc:
                 if fused:
-                    loss, st = fused_ppo_loss(logits, newvalue, atn, log_probs, adv, ret, val, config)
+                    if packed is not None:
+                        loss, st = fused_ppo_loss_packed(packed[0], packed[1], atn, log_probs, adv, ret, val, config)
+                    else:
+                        loss, st = fused_ppo_loss(logits, newvalue, atn, log_probs, adv, ret, val, config)
                     pg_loss, v_loss, entropy_loss, old_approx_kl, approx_kl, clipfrac = st.unbind(0)
                 else:
                     logratio = newlogprob - log_probs.reshape(-1)

@@ -21,18 +21,26 @@ class _DefaultMLPFunction(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, w_enc, b_enc, w_dec, b_dec, w_val, b_val):
+    def forward(ctx, x, w_enc, b_enc, w_dec, b_dec, w_val, b_val, cache):
         n_act, hid = w_dec.shape
         try:
             hidden = torch._addmm_activation(b_enc, x, w_enc.t(), use_gelu=False)
         except (AttributeError, RuntimeError):
             hidden = torch.relu(torch.addmm(b_enc, x, w_enc.t()))
-        w_cat = x.new_zeros(8, hid)
-        w_cat[:n_act] = w_dec
-        w_cat[n_act] = w_val[0]
-        b_cat = x.new_zeros(8)
-        b_cat[:n_act] = b_dec
-        b_cat[n_act] = b_val[0]
+        # the 8-row head matrix is rebuilt only when a head parameter changed (in-place optimizer steps bump _version):
+        # once per optimizer step in train, once per rollout in evaluate
+        # (a CUDA-graph capture never reuses a matrix built outside it: the flag is part of the key)
+        key = (w_dec._version, b_dec._version, w_val._version, b_val._version, w_dec.data_ptr(),
+               torch.cuda.is_current_stream_capturing())
+        if cache.get('key') != key:
+            w_cat = x.new_zeros(8, hid)
+            w_cat[:n_act] = w_dec
+            w_cat[n_act] = w_val[0]
+            b_cat = x.new_zeros(8)
+            b_cat[:n_act] = b_dec
+            b_cat[n_act] = b_val[0]
+            cache['key'], cache['w'], cache['b'] = key, w_cat, b_cat
+        w_cat, b_cat = cache['w'], cache['b']
         out = torch.addmm(b_cat, hidden, w_cat.t())
         ctx.save_for_backward(x, hidden, w_cat)
         ctx.n_act = n_act
@@ -57,7 +65,7 @@ class _DefaultMLPFunction(torch.autograd.Function):
         db_cat = grads[9 * hid:]
         dw_enc = dpre.t() @ x
         return (None, dw_enc, db_enc, dw_cat[:n_act], db_cat[:n_act], dw_cat[n_act:n_act + 1],
-                db_cat[n_act:n_act + 1])
+                db_cat[n_act:n_act + 1], None)
 
 
 def layer_init(layer, std=np.sqrt(2), bias_const=0.0):
@@ -73,14 +81,27 @@ class Default(nn.Module):
         self.decoder = layer_init(nn.Linear(hidden_size, env.single_action_space.n), std=0.01)
         self.value_head = nn.Linear(hidden_size, 1)
         self.fast_path = True     # fused forward epilogues + pb_mlp_tail_backward (CUDA, hidden 128, <= 7 actions)
+        self._head_cache = {}
+
+    def _fast_ok(self, x):
+        n_act, hid = self.decoder.weight.shape
+        return self.fast_path and x.is_cuda and hid == 128 and n_act + 1 <= 8 and not x.requires_grad
+
+    def forward_packed(self, observations):
+        """-> (out [M, 8], n_act) with logits = out[:, :n_act], value = out[:, n_act] (zero padding after), or None
+        when the fast path does not apply.  Lets the fused PPO loss hand back ONE [M, 8] gradient."""
+        x = observations.view(observations.shape[0], -1)
+        if not self._fast_ok(x):
+            return None
+        out = _DefaultMLPFunction.apply(x.float().contiguous(), self.encoder.weight, self.encoder.bias,
+                                        self.decoder.weight, self.decoder.bias, self.value_head.weight,
+                                        self.value_head.bias, self._head_cache)
+        return out, self.decoder.weight.shape[0]
 
     def forward(self, observations):
-        x = observations.view(observations.shape[0], -1)
-        n_act, hid = self.decoder.weight.shape
-        if self.fast_path and x.is_cuda and hid == 128 and n_act + 1 <= 8 and not x.requires_grad:
-            out = _DefaultMLPFunction.apply(x.float().contiguous(), self.encoder.weight, self.encoder.bias,
-                                            self.decoder.weight, self.decoder.bias, self.value_head.weight,
-                                            self.value_head.bias)
+        packed = self.forward_packed(observations)
+        if packed is not None:
+            out, n_act = packed
             return out[:, :n_act], out[:, n_act:n_act + 1]
         hidden, lookup = self.encode_observations(observations)
         return self.decode_actions(hidden, lookup)
