@@ -230,6 +230,44 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     t_g = time_launches(gather, 5)
     out['obs_gather'] = dict(kernel='k_minibatch_gather<uint4,4>', bytes_per_launch=2 * n * h * o, seconds=t_g,
                              launches_per_step=1)
+    # train-side kernels at the minibatch size of the workload (rotating buffers > L2 where the working set is small)
+    if args.env != 'pong' and args.hidden == 128:
+        mb = n * h // args.minibatches
+        n_act = vec.single_action_space.n
+        hid = torch.relu(torch.randn(mb, 128, device='cuda'))
+        douts = [torch.randn(mb, 8, device='cuda') for _ in range(4)]
+        w_cat = torch.randn(8, 128, device='cuda')
+        dpre = torch.empty_like(hid)
+        grads = torch.empty(8 * 128 + 128 + 8, device='cuda')
+        ws = torch.empty(lib.pb_mlp_tail_workspace_bytes(mb, 128), dtype=torch.uint8, device='cuda')
+
+        def tail(i):
+            d = douts[i % 4]
+            _native.check(lib.pb_mlp_tail_backward(_native.ptr(d), 8, _native.ptr(w_cat), _native.ptr(hid), mb, 128,
+                                                   _native.ptr(dpre), _native.ptr(grads), _native.ptr(ws), ws.numel(),
+                                                   _native.stream_ptr()))
+        tail(0)
+        t_tail = time_launches(tail, 4)
+        out['mlp_tail_bwd'] = dict(kernel='k_mlp_tail_bwd_tma<128> + k_reduce_partials', seconds=t_tail,
+                                   bytes_per_launch=mb * (2 * 128 * 4 + 32), launches_per_step=args.minibatches * args.epochs)
+        outs = [torch.randn(mb, 8, device='cuda') for _ in range(4)]
+        gouts = torch.zeros(mb, 8, device='cuda')
+        acts = torch.randint(0, n_act, (mb,), device='cuda')
+        f32 = [torch.randn(mb, device='cuda') for _ in range(4)]
+        stats = torch.zeros(8, dtype=torch.float64, device='cuda')
+
+        def loss(i):
+            o = outs[i % 4]
+            _native.check(lib.pb_ppo_loss(_native.ptr(o), 8, C.c_void_p(o.data_ptr() + 4 * n_act), 8, _native.ptr(acts),
+                                          _native.ptr(f32[0]), _native.ptr(f32[1]), _native.ptr(f32[2]), _native.ptr(f32[3]),
+                                          mb, n_act, C.c_float(0.1), 1, C.c_float(0.1), C.c_float(0.5), C.c_float(0.01),
+                                          _native.ptr(gouts), 8, C.c_void_p(gouts.data_ptr() + 4 * n_act), 8,
+                                          _native.ptr(stats), _native.stream_ptr()))
+        loss(0)
+        t_loss = time_launches(loss, 8)
+        out['ppo_loss'] = dict(kernel='k_ppo_loss', seconds=t_loss, bytes_per_launch=mb * (8 * n_act + 32 + 4),
+                               launches_per_step=args.minibatches * args.epochs)
+        del hid, douts, dpre, outs, gouts
     for k, v in out.items():
         v['achieved'] = v['bytes_per_launch'] / v['seconds'] / 1e9
         v['frac'] = v['achieved'] / peak_gbs
@@ -241,7 +279,7 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     try:
         tr = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic_r01.json')))['bytes_per_launch']
         if args.env == 'breakout' and n == 16384 and h == 128:
-            traffic = tr.get({'env_step': 'breakout', 'gae': 'gae', 'obs_gather': 'gather'}[dom])
+            traffic = tr.get({'env_step': 'breakout', 'gae': 'gae', 'obs_gather': 'gather'}.get(dom, dom))
     except Exception:
         pass
     roof = {'bound': 'hbm', 'kernel': d['kernel'], 'achieved': round(d['achieved'], 1), 'peak': peak_gbs,
