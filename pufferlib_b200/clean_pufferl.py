@@ -110,7 +110,8 @@ class _FusedPPOLoss(torch.autograd.Function):
             assert out.stride(1) == 1 and out.dtype == torch.float32
             l_ptr, l_stride = out.data_ptr(), out.stride(0)
             v_ptr, v_stride = out.data_ptr() + 4 * n_act, out.stride(0)
-            grad = torch.zeros_like(out) if out.shape[1] > n_act + 1 else torch.empty_like(out)
+            # [M, 8] rows: the kernel writes whole rows (zero padding included); other widths need the memset
+            grad = torch.empty_like(out) if out.shape[1] == 8 and n_act <= 7 else torch.zeros_like(out)
             gl_ptr, gl_stride, gv_ptr, gv_stride = grad.data_ptr(), grad.stride(0), grad.data_ptr() + 4 * n_act, grad.stride(0)
             ctx.packed = True
             ctx.save_for_backward(grad)
@@ -363,6 +364,15 @@ class _LazyIdxs:
         return self.n * self.h
 
 
+def _set_lr(optimizer, lr):
+    """The learning rate is a device tensor when the optimizer is capturable (graph replays read it in place)."""
+    cur = optimizer.param_groups[0]['lr']
+    if isinstance(cur, torch.Tensor):
+        cur.fill_(lr)
+    else:
+        optimizer.param_groups[0]['lr'] = lr
+
+
 def create(config, vecenv, policy, optimizer=None, wandb=None):
     seed_everything(config.seed, config.torch_deterministic)
     profile = Profile()
@@ -388,7 +398,9 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
 
     if optimizer is None:
         # same update rule as the reference's Adam (clean_pufferl.py:54-55); fused=True applies it in one kernel
-        optimizer = torch.optim.Adam(policy.parameters(), lr=config.learning_rate, eps=1e-5, fused=True)
+        graphed = bool(getattr(config, 'cuda_graph', False))
+        lr = torch.tensor(float(config.learning_rate), device=config.device) if graphed else config.learning_rate
+        optimizer = torch.optim.Adam(policy.parameters(), lr=lr, eps=1e-5, fused=True, capturable=graphed)
 
     grad_bucket = None
     if torch.distributed.is_available() and torch.distributed.is_initialized() and \
@@ -401,7 +413,7 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         experience=experience, profile=profile, losses=losses, wandb=wandb, global_step=0, epoch=0, stats={},
         msg=msg, last_log_time=0, utilization=None, grad_bucket=grad_bucket,
         io=pufferlib_b200.namespace(h2d=0, d2h=0), graph_state=0, rollout_graph=None, graph_steps=0,
-        graph_launches=0, graph_replays=0,
+        graph_launches=0, graph_replays=0, train_graph_state=0, train_graph=None, train_result=None, train_graph_launches=0, train_graph_replays=0,
         fused_rows=bool(getattr(policy, 'fused_sample', False)) and hasattr(vecenv, 'bind_rollout')
         and not getattr(vecenv, 'host_buffers', False),
         # one-kernel PPO loss (pb_ppo_loss): needs a wrapper exposing .policy(obs) -> (logits, value), one Discrete head
@@ -511,10 +523,11 @@ def evaluate(data):
     return data.stats, infos
 
 
-def train(data):
+def _train_device_part(data):
+    """Everything of train() that runs on the device without touching the host: GAE, minibatch construction, the
+    update_epochs x num_minibatches optimizer steps, the loss statistics.  No synchronisation inside, so the whole
+    thing can be captured in a CUDA graph (see train)."""
     config, profile, experience = data.config, data.profile, data.experience
-    data.losses = make_losses()
-    losses = data.losses
     device = experience.device
 
     with profile.train_misc:
@@ -605,18 +618,56 @@ def train(data):
                 break
 
     with profile.train_misc:
-        if config.anneal_lr:
-            frac = 1.0 - data.global_step / config.total_timesteps
-            data.optimizer.param_groups[0]['lr'] = frac * config.learning_rate
-
         # explained variance on the device, same quantities as clean_pufferl.py:266-270
         y_pred, y_true = experience.values, experience.returns
         var_y = y_true.var(unbiased=False)
         ev = 1 - (y_true - y_pred).var(unbiased=False) / var_y
-        host = torch.cat([acc, torch.stack([ev, var_y])]).cpu().numpy()    # the one D2H of train()
+        return torch.cat([acc, torch.stack([ev, var_y])])
+
+
+def train(data):
+    """One PPO update (reference: clean_pufferl.py:156-292).  With ``config.cuda_graph`` (single GPU, no target_kl, no
+    LSTM) the device part is captured once -- after an eager first call that initialises the optimizer state -- and
+    replayed as ONE graph launch; the learning rate lives in a device tensor so annealing works under replay."""
+    config, profile, experience = data.config, data.profile, data.experience
+    data.losses = make_losses()
+    losses = data.losses
+    graphable = bool(getattr(config, 'cuda_graph', False)) and data.grad_bucket is None and \
+        config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
+    if not graphable or data.train_graph_state == 0:
+        result = _train_device_part(data)
+        if graphable:
+            data.train_graph_state = 1
+    else:
+        if data.train_graph_state == 1:
+            try:
+                torch.cuda.synchronize()
+                launches0 = _native.lib().pb_launch_count()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    data.train_result = _train_device_part(data)
+                data.train_graph = graph
+                data.train_graph_launches = _native.lib().pb_launch_count() - launches0
+                data.train_graph_state = 2
+            except Exception as e:          # capture is an optimisation: fall back to eager for good
+                data.train_graph_state = -1
+                data.msg = f'train graph capture failed ({type(e).__name__}: {e}); running eager'
+                torch.cuda.synchronize()
+                result = _train_device_part(data)
+        if data.train_graph_state == 2:
+            with profile.learn:
+                data.train_graph.replay()
+            data.train_graph_replays += 1
+            result = data.train_result
+
+    with profile.train_misc:
+        if config.anneal_lr:
+            frac = 1.0 - data.global_step / config.total_timesteps
+            _set_lr(data.optimizer, frac * config.learning_rate)
+        host = result.cpu().numpy()    # the one D2H of train()
         data.io.d2h += host.nbytes
-        # the reference resets the accumulators every epoch of update_epochs? no: it divides by num_minibatches
-        # and keeps adding over epochs (clean_pufferl.py:249-254); same here.
+        # like the reference the per-minibatch means are divided by num_minibatches and summed over ALL epochs
+        # (clean_pufferl.py:249-254)
         losses.policy_loss, losses.value_loss, losses.entropy = float(host[0]), float(host[1]), float(host[2])
         losses.old_approx_kl, losses.approx_kl, losses.clipfrac = float(host[3]), float(host[4]), float(host[5])
         losses.explained_variance = float('nan') if host[7] == 0 else float(host[6])

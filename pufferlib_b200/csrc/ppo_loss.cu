@@ -38,15 +38,31 @@ struct PpoParams {
     int clip_vloss;
 };
 
+// PACKED: logits / value / grads all live in [m][8] rows (n_act logits | value | zero pad): 128-bit row accesses
+template <bool PACKED>
 __global__ void __launch_bounds__(PL_THREADS) k_ppo_loss(PpoParams p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double s_pg = 0, s_v = 0, s_ent = 0, s_okl = 0, s_kl = 0, s_clip = 0;
     if (i < p.m) {
         float z[PL_MAX_ACT];
         float mx = -INFINITY;
+        float v_packed = 0.f;
+        if (PACKED) {   // one 32-byte row: two 128-bit loads
+            const float4 a0 = *reinterpret_cast<const float4*>(p.logits + i * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(p.logits + i * 8 + 4);
+            const float row[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                z[k] = row[k];
+                if (k == p.n_act) v_packed = row[k];
+            }
+        }
 #pragma unroll
         for (int k = 0; k < PL_MAX_ACT; ++k)
-            if (k < p.n_act) { z[k] = p.logits[i * p.lstride + k]; mx = fmaxf(mx, z[k]); }
+            if (k < p.n_act) {
+                if (!PACKED) z[k] = p.logits[i * p.lstride + k];
+                mx = fmaxf(mx, z[k]);
+            }
         float sum = 0.f;
 #pragma unroll
         for (int k = 0; k < PL_MAX_ACT; ++k)
@@ -80,7 +96,7 @@ __global__ void __launch_bounds__(PL_THREADS) k_ppo_loss(PpoParams p) {
         const float inv_m = 1.0f / (float)p.m;
         const float g_nlp = g_ratio * ratio * inv_m;          // d loss / d newlogprob
         // value loss
-        const float v = p.value[i * p.vstride], ret = p.returns[i];
+        const float v = PACKED ? v_packed : p.value[i * p.vstride], ret = p.returns[i];
         const float dv = v - ret;
         float vl, g_v;
         if (p.clip_vloss) {
@@ -97,15 +113,26 @@ __global__ void __launch_bounds__(PL_THREADS) k_ppo_loss(PpoParams p) {
             vl = dv * dv;
             g_v = 2.f * dv;
         }
-        p.grad_value[i * p.gvstride] = 0.5f * p.vf_coef * g_v * inv_m;
+        const float gv_out = 0.5f * p.vf_coef * g_v * inv_m;
+        if (!PACKED) p.grad_value[i * p.gvstride] = gv_out;
         // d loss / d logits_j = g_nlp * (delta_ja - p_j) + ent_coef/M * p_j * (nl_j + H)
         const float g_ent = p.ent_coef * inv_m;
+        float gro[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int k = 0; k < PL_MAX_ACT; ++k)
             if (k < p.n_act) {
                 const float pk = expf(z[k]);
-                p.grad_logits[i * p.glstride + k] = g_nlp * ((k == a ? 1.f : 0.f) - pk) + g_ent * pk * (z[k] + ent);
+                const float gk = g_nlp * ((k == a ? 1.f : 0.f) - pk) + g_ent * pk * (z[k] + ent);
+                if (PACKED) { if (k < 8) gro[k] = gk; }
+                else p.grad_logits[i * p.glstride + k] = gk;
             }
+        if (PACKED) {   // the whole 8-column gradient row (zero padding included) in two 128-bit stores
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k == p.n_act) gro[k] = gv_out;
+            *reinterpret_cast<float4*>(p.grad_logits + i * 8) = make_float4(gro[0], gro[1], gro[2], gro[3]);
+            *reinterpret_cast<float4*>(p.grad_logits + i * 8 + 4) = make_float4(gro[4], gro[5], gro[6], gro[7]);
+        }
         s_pg = pg; s_v = vl; s_ent = ent; s_okl = -logratio; s_kl = (ratio - 1.f) - logratio;
         s_clip = fabsf(ratio - 1.f) > p.clip ? 1.0 : 0.0;
     }
@@ -147,7 +174,12 @@ extern "C" int pb_ppo_loss(const float* logits, int64_t logits_stride, const flo
     PpoParams p{logits, logits_stride, value, value_stride, actions, old_logprobs, advantages, returns, old_values,
                 grad_logits, grad_logits_stride, grad_value, grad_value_stride, stats8, m, n_act, clip_coef, vf_clip_coef,
                 vf_coef, ent_coef, clip_vloss};
-    k_ppo_loss<<<(unsigned)pb_ceil_div(m, PL_THREADS), PL_THREADS, 0, s>>>(p);
+    // packed rows: logits, value, and both gradients share [m][8] buffers (value = column n_act of the logits rows)
+    const bool packed = logits_stride == 8 && grad_logits_stride == 8 && n_act <= 7 && value == logits + n_act &&
+                        value_stride == 8 && grad_value == grad_logits + n_act && grad_value_stride == 8 &&
+                        ((uintptr_t)logits & 15) == 0 && ((uintptr_t)grad_logits & 15) == 0;
+    if (packed) k_ppo_loss<true><<<(unsigned)pb_ceil_div(m, PL_THREADS), PL_THREADS, 0, s>>>(p);
+    else k_ppo_loss<false><<<(unsigned)pb_ceil_div(m, PL_THREADS), PL_THREADS, 0, s>>>(p);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

@@ -109,3 +109,25 @@ def test_default_mlp_fast_path_matches_plain_modules():
             scale = float(b.abs().max()) + 1e-6
             assert float((a - b).abs().max()) <= 5e-3 * scale, (m, float((a - b).abs().max()), scale)
     vec.close()
+
+
+@pytest.mark.parametrize('m,n_act', [(1, 4), (4097, 6), (100000, 7)])
+def test_ppo_loss_packed_rows(m, n_act):
+    """Packed [M, 8] rows (n_act logits | value | zero pad): 128-bit row accesses, ONE [M, 8] gradient back."""
+    dev = torch.device('cuda')
+    torch.manual_seed(m)
+    cfg = pufferlib_b200.namespace(clip_coef=0.1, clip_vloss=True, vf_clip_coef=0.1, vf_coef=0.5, ent_coef=0.01)
+    out0 = torch.randn(m, 8, device=dev)
+    out0[:, n_act + 1:] = 0
+    actions = torch.randint(0, n_act, (m,), device=dev)
+    old_lp, adv, ret = -torch.rand(m, device=dev) - 1, torch.randn(m, device=dev), torch.randn(m, device=dev)
+    old_v = out0[:, n_act] + 0.15 * torch.randn(m, device=dev)
+    a = out0.clone().requires_grad_(True)
+    loss, st = clean_pufferl.fused_ppo_loss_packed(a, n_act, actions, old_lp, adv, ret, old_v, cfg)
+    loss.backward()
+    b = out0.clone().requires_grad_(True)
+    ref, st_ref = reference_loss(b[:, :n_act], b[:, n_act:n_act + 1], actions, old_lp, adv, ret, old_v, cfg)
+    ref.backward()
+    assert torch.allclose(loss, ref, rtol=1e-5, atol=1e-6) and torch.allclose(st, st_ref, rtol=1e-5, atol=1e-6)
+    assert float((a.grad - b.grad).abs().max()) <= 1e-5 * float(b.grad.abs().max()) + 1e-10
+    assert float(a.grad[:, n_act + 1:].abs().sum()) == 0.0
