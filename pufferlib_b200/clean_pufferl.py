@@ -626,13 +626,14 @@ def _train_device_part(data):
 
 
 def train(data):
-    """One PPO update (reference: clean_pufferl.py:156-292).  With ``config.cuda_graph`` (single GPU, no target_kl, no
+    """One PPO update (reference: clean_pufferl.py:156-292).  With ``config.cuda_graph`` (no target_kl, no
     LSTM) the device part is captured once -- after an eager first call that initialises the optimizer state -- and
     replayed as ONE graph launch; the learning rate lives in a device tensor so annealing works under replay."""
     config, profile, experience = data.config, data.profile, data.experience
     data.losses = make_losses()
     losses = data.losses
-    graphable = bool(getattr(config, 'cuda_graph', False)) and data.grad_bucket is None and \
+    # multi-GPU: the flat-bucket NCCL all-reduce is captured inside the graph too (NCCL collectives are graph-capturable)
+    graphable = bool(getattr(config, 'cuda_graph', False)) and \
         config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
     if not graphable or data.train_graph_state == 0:
         result = _train_device_part(data)
@@ -658,6 +659,8 @@ def train(data):
             with profile.learn:
                 data.train_graph.replay()
             data.train_graph_replays += 1
+            experience.ptr = 0            # what sort_training_data leaves behind (clean_pufferl.py:461-463)
+            experience.step = 0
             result = data.train_result
 
     with profile.train_misc:

@@ -208,3 +208,31 @@ def test_lstm_policy_path():
         clean_pufferl.train(data)
         assert np.isfinite(data.losses.policy_loss) and np.isfinite(data.losses.entropy)
     clean_pufferl.close(data)
+
+
+def test_graphed_training_matches_eager_training():
+    """CUDA-graph rollout + CUDA-graph train update must be the same computation as the eager loop: identical seeds ->
+    identical stored rollouts and (to fp32 summation noise) identical parameters after several iterations."""
+    from pufferlib_b200 import models
+    from pufferlib_b200.frameworks import cleanrl
+    n, h = 64, 32
+    params, rollouts = {}, {}
+    for mode in ('eager', 'graph'):
+        vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200)
+        torch.manual_seed(0)
+        pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=7).cuda()
+        data = clean_pufferl.create(make_config(n, h, env='breakout', cuda_graph=(mode == 'graph'), anneal_lr=True,
+                                                total_timesteps=20 * n * h), vec, pol)
+        for it in range(5):
+            clean_pufferl.evaluate(data)
+            if it == 4:
+                rollouts[mode] = (cpu(data.experience.actions).copy(), cpu(data.experience.rewards).copy())
+            clean_pufferl.train(data)
+        if mode == 'graph':
+            assert data.train_graph_state == 2 and data.train_graph_replays == 4 and data.graph_replays == 4, data.msg
+        params[mode] = [p.detach().cpu().clone() for p in pol.parameters()]
+        clean_pufferl.close(data)
+    assert np.array_equal(rollouts['eager'][0], rollouts['graph'][0])      # same sampled actions in iteration 5
+    assert np.array_equal(rollouts['eager'][1], rollouts['graph'][1])
+    for a, b in zip(params['eager'], params['graph']):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
