@@ -632,8 +632,9 @@ def train(data):
     config, profile, experience = data.config, data.profile, data.experience
     data.losses = make_losses()
     losses = data.losses
-    # multi-GPU: the flat-bucket NCCL all-reduce is captured inside the graph too (NCCL collectives are graph-capturable)
-    graphable = bool(getattr(config, 'cuda_graph', False)) and \
+    # multi-GPU: capturing the NCCL all-reduce inside the graph hung on this stack (torch 2.11 / NCCL 2.28), so ranks > 1
+    # keep the eager update loop for now
+    graphable = bool(getattr(config, 'cuda_graph', False)) and data.grad_bucket is None and \
         config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
     if not graphable or data.train_graph_state == 0:
         result = _train_device_part(data)
