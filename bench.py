@@ -321,9 +321,11 @@ def run_b200(args):
     if rank == 0:
         clocks.start()
     launches0, replays0, treplays0 = _native.lib().pb_launch_count(), data.graph_replays, data.train_graph_replays
+    seg0 = getattr(data.train_segments, 'replayed_launches', 0)
     ms = timed_steps(data, cp, args.steps, world)
     launches = ((_native.lib().pb_launch_count() - launches0) + (data.graph_replays - replays0) * data.graph_launches
-                + (data.train_graph_replays - treplays0) * data.train_graph_launches)
+                + (data.train_graph_replays - treplays0) * data.train_graph_launches
+                + (getattr(data.train_segments, 'replayed_launches', 0) - seg0))
     clk = clocks.stop() if rank == 0 else None
     value = world * n * h * args.steps / (ms * 1e-3)
     prof = {k: round(v, 4) for k, v in dict(data.profile).items() if k.endswith('_time')}
@@ -363,7 +365,7 @@ def run_b200(args):
                        'bptt_horizon': 16, 'parallelism': f'dp{world} (env shards + 1 NCCL grad all-reduce/step)',
                        'l2': 'inputs larger than L2 (1 GiB rollout rotates; no flush needed)',
                        'cuda_graph_rollout': not args.no_graph,
-                       'cuda_graph_train': data.train_graph_state == 2, 'note': data.msg},
+                       'cuda_graph_train': 'whole' if data.train_graph_state == 2 else ('segments' if data.train_segments else False), 'note': data.msg},
             'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'roofline_kernels': roof_all,
             'cpu_baseline': cpu, 'clocks': clk, 'profile_s': prof, 'env_stats': stats,
         }

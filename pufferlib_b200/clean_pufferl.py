@@ -413,7 +413,7 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         experience=experience, profile=profile, losses=losses, wandb=wandb, global_step=0, epoch=0, stats={},
         msg=msg, last_log_time=0, utilization=None, grad_bucket=grad_bucket,
         io=pufferlib_b200.namespace(h2d=0, d2h=0), graph_state=0, rollout_graph=None, graph_steps=0,
-        graph_launches=0, graph_replays=0, train_graph_state=0, train_graph=None, train_result=None, train_graph_launches=0, train_graph_replays=0,
+        graph_launches=0, graph_replays=0, train_graph_state=0, train_graph=None, train_result=None, train_graph_launches=0, train_graph_replays=0, train_segments=None, train_acc=None,
         fused_rows=bool(getattr(policy, 'fused_sample', False)) and hasattr(vecenv, 'bind_rollout')
         and not getattr(vecenv, 'host_buffers', False),
         # one-kernel PPO loss (pb_ppo_loss): needs a wrapper exposing .policy(obs) -> (logits, value), one Discrete head
@@ -523,10 +523,36 @@ def evaluate(data):
     return data.stats, infos
 
 
-def _train_device_part(data):
+class _SegmentGraphs:
+    """Per-segment CUDA graphs for the multi-GPU update loop: each (forward + loss + backward) minibatch segment and the
+    (clip + Adam) segment is captured once and replayed; the NCCL all-reduce between them stays an ordinary call."""
+
+    def __init__(self):
+        self.graphs = {}
+        self.launches = {}
+        self.replays = 0
+
+    def run(self, key, fn):
+        g = self.graphs.get(key)
+        if g is None:
+            torch.cuda.synchronize()
+            l0 = _native.lib().pb_launch_count()
+            g = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread may poll events while we capture
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                fn()
+            self.graphs[key] = g
+            self.launches[key] = _native.lib().pb_launch_count() - l0
+        g.replay()
+        self.replays += 1
+        self.replayed_launches = getattr(self, 'replayed_launches', 0) + self.launches[key]
+
+
+def _train_device_part(data, seg=None):
     """Everything of train() that runs on the device without touching the host: GAE, minibatch construction, the
     update_epochs x num_minibatches optimizer steps, the loss statistics.  No synchronisation inside, so the whole
-    thing can be captured in a CUDA graph (see train)."""
+    thing can be captured in ONE CUDA graph (single GPU, see train) or, with ``seg``, as per-segment graphs around
+    the gradient all-reduce (multi-GPU)."""
     config, profile, experience = data.config, data.profile, data.experience
     device = experience.device
 
@@ -538,83 +564,105 @@ def _train_device_part(data):
             experience.normalize_advantages()
 
     n_mb = experience.num_minibatches
-    acc = torch.zeros(6, device=device)       # policy, value, entropy, old_kl, kl, clipfrac
+    if seg is not None:                        # persistent accumulator: the segment graphs update it in place
+        if data.train_acc is None:
+            data.train_acc = torch.zeros(6, device=device)
+        acc = data.train_acc
+        acc.zero_()
+    else:
+        acc = torch.zeros(6, device=device)    # policy, value, entropy, old_kl, kl, clipfrac
     obs_shape = data.vecenv.single_observation_space.shape
+    fused = data.fused_loss and experience.lstm_h is None
+    carry = {'lstm_state': None, 'approx_kl': None}
+
+    def forward_backward(mb):
+        obs = experience.b_obs[mb]
+        atn = experience.b_actions[mb]
+        log_probs = experience.b_logprobs[mb]
+        val = experience.b_values[mb]
+        adv = experience.b_advantages_normalized[mb] if config.norm_adv else experience.b_advantages[mb]
+        ret = experience.b_returns[mb]
+
+        with profile.train_forward:
+            packed = None
+            if fused:          # logits / value straight from the model; loss + its gradient in one kernel
+                model = data.policy.policy
+                if hasattr(model, 'forward_packed'):
+                    packed = model.forward_packed(obs.reshape(-1, *obs_shape))
+                if packed is None:
+                    logits, newvalue = model(obs.reshape(-1, *obs_shape))
+            elif experience.lstm_h is not None:       # clean_pufferl.py:188-191: [rows, bptt, *obs] segments
+                _, newlogprob, entropy, newvalue, st_ = data.policy(obs, state=carry['lstm_state'], action=atn)
+                carry['lstm_state'] = (st_[0].detach(), st_[1].detach())
+            else:
+                _, newlogprob, entropy, newvalue = data.policy(obs.reshape(-1, *obs_shape), action=atn)
+
+        with profile.train_misc:
+            if fused:
+                if packed is not None:
+                    loss, st = fused_ppo_loss_packed(packed[0], packed[1], atn, log_probs, adv, ret, val, config)
+                else:
+                    loss, st = fused_ppo_loss(logits, newvalue, atn, log_probs, adv, ret, val, config)
+                pg_loss, v_loss, entropy_loss, old_approx_kl, approx_kl, clipfrac = st.unbind(0)
+            else:
+                logratio = newlogprob - log_probs.reshape(-1)
+                ratio = logratio.exp()
+                with torch.no_grad():
+                    old_approx_kl = (-logratio).mean()
+                    approx_kl = ((ratio - 1) - logratio).mean()
+                    clipfrac = ((ratio - 1.0).abs() > config.clip_coef).float().mean()
+
+                adv = adv.reshape(-1)
+                pg_loss1 = -adv * ratio
+                pg_loss2 = -adv * torch.clamp(ratio, 1 - config.clip_coef, 1 + config.clip_coef)
+                pg_loss = torch.max(pg_loss1, pg_loss2).mean()
+
+                newvalue = newvalue.view(-1)
+                if config.clip_vloss:
+                    v_loss_unclipped = (newvalue - ret) ** 2
+                    v_clipped = val + torch.clamp(newvalue - val, -config.vf_clip_coef, config.vf_clip_coef)
+                    v_loss_clipped = (v_clipped - ret) ** 2
+                    v_loss = 0.5 * torch.max(v_loss_unclipped, v_loss_clipped).mean()
+                else:
+                    v_loss = 0.5 * ((newvalue - ret) ** 2).mean()
+
+                entropy_loss = entropy.mean()
+                loss = pg_loss - config.ent_coef * entropy_loss + v_loss * config.vf_coef
+
+        with profile.learn:
+            if data.grad_bucket is not None:
+                data.grad_bucket.zero()                     # grads are views into one flat buffer
+            else:
+                data.optimizer.zero_grad()
+            loss.backward()
+
+        with profile.train_misc, torch.no_grad():
+            acc.add_(torch.stack([pg_loss.detach(), v_loss.detach(), entropy_loss.detach(), old_approx_kl,
+                                  approx_kl, clipfrac]) / n_mb)
+        carry['approx_kl'] = approx_kl
+
+    def optimizer_step():
+        with profile.learn:
+            torch.nn.utils.clip_grad_norm_(data.policy.parameters(), config.max_grad_norm)
+            data.optimizer.step()
+
     for epoch in range(config.update_epochs):
-        lstm_state = None
+        carry['lstm_state'] = None
         for mb in range(n_mb):
-            with profile.train_misc:
-                obs = experience.b_obs[mb]
-                atn = experience.b_actions[mb]
-                log_probs = experience.b_logprobs[mb]
-                val = experience.b_values[mb]
-                adv = experience.b_advantages_normalized[mb] if config.norm_adv else experience.b_advantages[mb]
-                ret = experience.b_returns[mb]
-
-            fused = data.fused_loss and experience.lstm_h is None
-            with profile.train_forward:
-                packed = None
-                if fused:          # logits / value straight from the model; loss + its gradient in one kernel
-                    model = data.policy.policy
-                    if hasattr(model, 'forward_packed'):
-                        packed = model.forward_packed(obs.reshape(-1, *obs_shape))
-                    if packed is None:
-                        logits, newvalue = model(obs.reshape(-1, *obs_shape))
-                elif experience.lstm_h is not None:       # clean_pufferl.py:188-191: [rows, bptt, *obs] segments
-                    _, newlogprob, entropy, newvalue, lstm_state = data.policy(obs, state=lstm_state, action=atn)
-                    lstm_state = (lstm_state[0].detach(), lstm_state[1].detach())
-                else:
-                    _, newlogprob, entropy, newvalue = data.policy(obs.reshape(-1, *obs_shape), action=atn)
-
-            with profile.train_misc:
-                if fused:
-                    if packed is not None:
-                        loss, st = fused_ppo_loss_packed(packed[0], packed[1], atn, log_probs, adv, ret, val, config)
-                    else:
-                        loss, st = fused_ppo_loss(logits, newvalue, atn, log_probs, adv, ret, val, config)
-                    pg_loss, v_loss, entropy_loss, old_approx_kl, approx_kl, clipfrac = st.unbind(0)
-                else:
-                    logratio = newlogprob - log_probs.reshape(-1)
-                    ratio = logratio.exp()
-                    with torch.no_grad():
-                        old_approx_kl = (-logratio).mean()
-                        approx_kl = ((ratio - 1) - logratio).mean()
-                        clipfrac = ((ratio - 1.0).abs() > config.clip_coef).float().mean()
-
-                    adv = adv.reshape(-1)
-                    pg_loss1 = -adv * ratio
-                    pg_loss2 = -adv * torch.clamp(ratio, 1 - config.clip_coef, 1 + config.clip_coef)
-                    pg_loss = torch.max(pg_loss1, pg_loss2).mean()
-
-                    newvalue = newvalue.view(-1)
-                    if config.clip_vloss:
-                        v_loss_unclipped = (newvalue - ret) ** 2
-                        v_clipped = val + torch.clamp(newvalue - val, -config.vf_clip_coef, config.vf_clip_coef)
-                        v_loss_clipped = (v_clipped - ret) ** 2
-                        v_loss = 0.5 * torch.max(v_loss_unclipped, v_loss_clipped).mean()
-                    else:
-                        v_loss = 0.5 * ((newvalue - ret) ** 2).mean()
-
-                    entropy_loss = entropy.mean()
-                    loss = pg_loss - config.ent_coef * entropy_loss + v_loss * config.vf_coef
-
-            with profile.learn:
-                if data.grad_bucket is not None:
-                    data.grad_bucket.zero()                     # grads are views into one flat buffer
-                else:
-                    data.optimizer.zero_grad()
-                loss.backward()
-                if data.grad_bucket is not None:
+            if seg is not None:
+                seg.run(('fb', mb), lambda: forward_backward(mb))
+            else:
+                forward_backward(mb)
+            if data.grad_bucket is not None:
+                with profile.learn:
                     data.grad_bucket.all_reduce_mean()          # ONE NCCL all-reduce per optimizer step
-                torch.nn.utils.clip_grad_norm_(data.policy.parameters(), config.max_grad_norm)
-                data.optimizer.step()
-
-            with profile.train_misc, torch.no_grad():
-                acc += torch.stack([pg_loss.detach(), v_loss.detach(), entropy_loss.detach(), old_approx_kl,
-                                    approx_kl, clipfrac]) / n_mb
+            if seg is not None:
+                seg.run('opt', optimizer_step)
+            else:
+                optimizer_step()
 
         if config.target_kl is not None:
-            if approx_kl.item() > config.target_kl:
+            if carry['approx_kl'].item() > config.target_kl:
                 break
 
     with profile.train_misc:
@@ -632,13 +680,19 @@ def train(data):
     config, profile, experience = data.config, data.profile, data.experience
     data.losses = make_losses()
     losses = data.losses
-    # multi-GPU: capturing the NCCL all-reduce inside the graph hung on this stack (torch 2.11 / NCCL 2.28), so ranks > 1
-    # keep the eager update loop for now
+    # multi-GPU: capturing the NCCL all-reduce inside one big graph hung on this stack (torch 2.11 / NCCL 2.28); ranks > 1
+    # use per-segment graphs around an ordinary all-reduce call instead (see `segmented`)
     graphable = bool(getattr(config, 'cuda_graph', False)) and data.grad_bucket is None and \
         config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
-    if not graphable or data.train_graph_state == 0:
+    segmented = bool(getattr(config, 'cuda_graph', False)) and data.grad_bucket is not None and \
+        config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
+    if segmented and data.train_graph_state >= 1:
+        if data.train_segments is None:
+            data.train_segments = _SegmentGraphs()
+        result = _train_device_part(data, seg=data.train_segments)
+    elif not graphable or data.train_graph_state == 0:
         result = _train_device_part(data)
-        if graphable:
+        if graphable or segmented:
             data.train_graph_state = 1
     else:
         if data.train_graph_state == 1:
