@@ -478,7 +478,7 @@ def evaluate(data):
     infos = defaultdict(list)
     vecenv = data.vecenv
     on_device = not getattr(vecenv, 'host_buffers', False)
-    use_graph = bool(getattr(config, 'cuda_graph', False)) and on_device and \
+    use_graph = bool(getattr(config, 'cuda_graph_rollout', getattr(config, 'cuda_graph', False))) and on_device and \
         not getattr(vecenv, 'exact_infos', False)
 
     if not use_graph or data.graph_state == 0:
@@ -682,9 +682,10 @@ def train(data):
     losses = data.losses
     # multi-GPU: capturing the NCCL all-reduce inside one big graph hung on this stack (torch 2.11 / NCCL 2.28); ranks > 1
     # use per-segment graphs around an ordinary all-reduce call instead (see `segmented`)
-    graphable = bool(getattr(config, 'cuda_graph', False)) and data.grad_bucket is None and \
+    want_graph = bool(getattr(config, 'cuda_graph_train', getattr(config, 'cuda_graph', False)))
+    graphable = want_graph and data.grad_bucket is None and \
         config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
-    segmented = bool(getattr(config, 'cuda_graph', False)) and data.grad_bucket is not None and \
+    segmented = want_graph and data.grad_bucket is not None and \
         config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
     if segmented and data.train_graph_state >= 1:
         if data.train_segments is None:

@@ -211,10 +211,10 @@ def test_lstm_policy_path():
 
 
 def test_graphed_training_matches_eager_training():
-    """CUDA-graph rollout + CUDA-graph train update must be the same computation as the eager loop.  Not bit-identical:
-    the capturable Adam evaluates its bias corrections in fp32 tensors instead of python doubles, and sampling amplifies
-    1e-7 parameter differences into a few flipped actions; so: parameters agree to 2e-3 after 5 updates, and the 5th
-    rollout's sampled actions agree for > 97 % of the agent-steps."""
+    """CUDA-graph rollout + CUDA-graph train update are the same computation as the eager loop: same config (so the same
+    capturable Adam), graphs on vs off -> the same kernels in the same order, hence the same sampled actions and the
+    same parameters after 5 updates (fp32-identical up to nothing but the unordered fp64 statistics atomics, which do
+    not feed the gradients)."""
     from pufferlib_b200 import models
     from pufferlib_b200.frameworks import cleanrl
     n, h = 64, 32
@@ -223,18 +223,22 @@ def test_graphed_training_matches_eager_training():
         vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200)
         torch.manual_seed(0)
         pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=7).cuda()
-        data = clean_pufferl.create(make_config(n, h, env='breakout', cuda_graph=(mode == 'graph'), anneal_lr=True,
-                                                total_timesteps=20 * n * h), vec, pol)
+        g = mode == 'graph'
+        data = clean_pufferl.create(make_config(n, h, env='breakout', cuda_graph=True, cuda_graph_rollout=g,
+                                                cuda_graph_train=g, anneal_lr=True, total_timesteps=20 * n * h), vec, pol)
         for it in range(5):
             clean_pufferl.evaluate(data)
             if it == 4:
                 rollouts[mode] = (cpu(data.experience.actions).copy(), cpu(data.experience.rewards).copy())
             clean_pufferl.train(data)
-        if mode == 'graph':
+        if g:
             assert data.train_graph_state == 2 and data.train_graph_replays == 4 and data.graph_replays == 4, data.msg
+        else:
+            assert data.train_graph_state != 2 and data.graph_replays == 0
         params[mode] = [p.detach().cpu().clone() for p in pol.parameters()]
         clean_pufferl.close(data)
     agree = float((rollouts['eager'][0] == rollouts['graph'][0]).mean())
-    assert agree > 0.97, agree
+    diffs = [float((a - b).abs().max()) for a, b in zip(params['eager'], params['graph'])]
+    assert agree > 0.999, (agree, diffs)
     for a, b in zip(params['eager'], params['graph']):
-        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5), float((a - b).abs().max())
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6), (agree, diffs)
