@@ -264,12 +264,10 @@ class Experience:
         """clean_pufferl.py:436-450 for an all-True mask with env_id == arange(N) (what the B200 backend
         produces): rows ptr:ptr+N.  Tensors already living in their rollout row (bound vecenv) are not copied."""
         n = value.shape[0]
-        if self.num_envs is None:
-            if self.batch_size % n != 0:
-                raise APIUsageError('batch_size must be a multiple of the agents per step')
+        if self.num_envs is None:            # total agents (create() sets it; pool mode stores batch_size-row chunks)
             self.num_envs = n
-        if n != self.num_envs:
-            raise APIUsageError('store(): the number of agents per step changed')
+        if self.batch_size % n != 0 or self.num_envs % n != 0:
+            raise APIUsageError('batch_size / num_envs must be multiples of the agents per store()')
         ptr, end = self.ptr, self.ptr + n
         if end > self.batch_size:
             raise APIUsageError('store(): rollout buffer is full')
@@ -389,6 +387,7 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
     lstm = policy.lstm if hasattr(policy, 'lstm') else None
     experience = Experience(config.batch_size, config.bptt_horizon, config.minibatch_size, obs_shape, obs_dtype,
                             atn_shape, config.cpu_offload, config.device, lstm, total_agents)
+    experience.num_envs = total_agents      # rows arrive in arrival order t*N + e (also in pool mode: (t, group) blocks)
     if hasattr(vecenv, 'bind_rollout') and not getattr(vecenv, 'host_buffers', False):
         vecenv.bind_rollout(experience)     # env-step kernels write rollout rows directly
 
@@ -468,6 +467,8 @@ def _rollout_loop(data, infos):
                 a_host = actions.cpu().numpy()
                 io.d2h += a_host.nbytes
                 vecenv.send(a_host)
+    if hasattr(vecenv, 'join'):
+        vecenv.join()            # pool mode: side-stream env steps rejoin the caller's stream (and any graph capture)
 
 
 def evaluate(data):

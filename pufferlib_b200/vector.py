@@ -128,13 +128,18 @@ class B200:
     def num_envs(self):
         return self.agents_per_batch
 
+    def __new__(cls, env_creators=None, env_args=None, env_kwargs=None, num_envs=None, **kwargs):
+        # batch_size < num_envs: the reference's pool mode (vector.py:345-390) -> round-robin groups on side streams
+        bs = kwargs.get('batch_size')
+        if cls is B200 and bs is not None and num_envs is not None and bs != num_envs:
+            return B200Pool(env_creators, env_args, env_kwargs, num_envs, **kwargs)
+        return super().__new__(cls)
+
     def __init__(self, env_creators, env_args, env_kwargs, num_envs, host_buffers=False, exact_infos=None,
                  device=None, env_index_offset=0, **kwargs):
         for k in kwargs:
             if k not in ('num_workers', 'batch_size', 'zero_copy', 'backend'):
                 raise APIUsageError(f'Invalid argument: {k}')
-        if kwargs.get('batch_size') not in (None, num_envs):
-            raise NotImplementedError('B200 backend: batch_size < num_envs (pool mode) is not implemented')
         kind, iparam = resolve(env_creators[0], env_args[0], env_kwargs[0])
         for c, a, k in zip(env_creators, env_args, env_kwargs):
             if resolve(c, a, k) != (kind, iparam):
@@ -348,6 +353,123 @@ class B200:
             self.close()
         except Exception:
             pass
+
+
+class B200Pool:
+    """``batch_size < num_envs``: the pool / double-buffering mode of the reference's Multiprocessing backend
+    (vector.py:345-390).  The N envs are split into G = N / batch_size groups (contiguous env ranges, one pb_env handle
+    each, seeded by global env index).  recv() returns the groups round-robin (deterministically, unlike the reference's
+    first-ready order); send() steps the group just received on that group's own CUDA stream, so its env-step kernel
+    overlaps the policy forward of the next group on the caller's stream.  Rows therefore arrive as
+    (step t, group g) blocks = arrival index t*N + e, the layout Experience expects."""
+    reset = reset
+    step = step
+
+    @property
+    def num_envs(self):
+        return self.agents_per_batch
+
+    def __init__(self, env_creators, env_args, env_kwargs, num_envs, host_buffers=False, exact_infos=None,
+                 device=None, env_index_offset=0, **kwargs):
+        b = int(kwargs.pop('batch_size'))
+        for k in kwargs:
+            if k not in ('num_workers', 'zero_copy', 'backend'):
+                raise APIUsageError(f'Invalid argument: {k}')
+        if b < 1 or num_envs % b != 0:
+            raise APIUsageError('num_envs must be divisible by batch_size')
+        g = num_envs // b
+        self.groups = [B200(env_creators[i * b:(i + 1) * b], env_args[i * b:(i + 1) * b], env_kwargs[i * b:(i + 1) * b], b,
+                            host_buffers=host_buffers, exact_infos=exact_infos, device=device,
+                            env_index_offset=env_index_offset + i * b) for i in range(g)]
+        first = self.groups[0]
+        self.device = first.device
+        self.host_buffers, self.exact_infos = first.host_buffers, first.exact_infos
+        self.single_observation_space, self.single_action_space = first.single_observation_space, first.single_action_space
+        self.emulated, self.driver_env, self.obs_bytes = first.emulated, first.driver_env, first.obs_bytes
+        self.agents_per_batch, self.num_agents = b, num_envs
+        self.action_space, self.observation_space = first.action_space, first.observation_space
+        self.agent_ids = np.arange(num_envs)
+        self._ids = [np.arange(i * b, (i + 1) * b) for i in range(g)]
+        self.initialized = False
+        self.flag = RESET
+        self.infos = []
+        with torch.cuda.device(self.device):
+            self._streams = [torch.cuda.Stream() for _ in range(g)]
+            self._events = [torch.cuda.Event() for _ in range(g)]
+        self._next = 0          # group recv() returns next
+        self._pending = None    # group whose actions send() expects
+
+    @property
+    def h2d_bytes(self):
+        return sum(v.h2d_bytes for v in self.groups)
+
+    @property
+    def d2h_bytes(self):
+        return sum(v.d2h_bytes for v in self.groups)
+
+    def pinned(self, array):
+        for v in self.groups:
+            t = v.pinned(array)
+            if t.is_pinned():
+                return t
+        return torch.as_tensor(array)
+
+    def async_reset(self, seed=42):
+        for v in self.groups:
+            v.async_reset(seed)
+        with torch.cuda.device(self.device):
+            for ev in self._events:
+                ev.record()
+        self.flag = RECV
+        self._next, self._pending = 0, None
+
+    def recv(self):
+        recv_precheck(self)
+        g = self._next
+        v = self.groups[g]
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().wait_event(self._events[g])      # group g's last step has finished
+        v.flag = RECV
+        o, r, d, t, infos, _, m = v.recv()
+        self.infos = infos
+        self._pending = g
+        return o, r, d, t, infos, self._ids[g], m
+
+    def send(self, actions):
+        if self.flag != SEND:
+            raise APIUsageError('Call (async) reset + recv before sending')
+        g = self._pending
+        v = self.groups[g]
+        with torch.cuda.device(self.device):
+            side = self._streams[g]
+            side.wait_stream(torch.cuda.current_stream())                # the actions were produced on the caller's stream
+            with torch.cuda.stream(side):
+                v.flag = SEND
+                v.send(actions)
+                self._events[g].record(side)
+        self.initialized = v.initialized
+        self.flag = RECV
+        self._next = (g + 1) % len(self.groups)
+
+    def join(self):
+        """Make the caller's stream wait for every group's outstanding step (needed before graph capture ends)."""
+        with torch.cuda.device(self.device):
+            for ev in self._events:
+                torch.cuda.current_stream().wait_event(ev)
+
+    def episode_stats(self, clear=True):
+        self.join()
+        tot, cnt = {}, 0
+        for v in self.groups:
+            means, c = v.episode_stats(clear)
+            for k, x in means.items():
+                tot[k] = tot.get(k, 0.0) + x * c
+            cnt += c
+        return ({k: x / cnt for k, x in tot.items()}, cnt) if cnt else ({}, 0)
+
+    def close(self):
+        for v in self.groups:
+            v.close()
 
 
 def _from_device(addr, n, dtype):

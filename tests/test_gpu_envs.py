@@ -110,3 +110,61 @@ def test_observation_spaces():
         assert vec.single_observation_space.shape == shape and vec.single_observation_space.dtype == dtype
         assert vec.single_action_space.n == NUM_ACTIONS[kind]
         vec.close()
+
+
+@pytest.mark.parametrize('kind', ['breakout', 'snake'])
+@pytest.mark.parametrize('groups', [2, 4])
+def test_pool_mode_round_robin_groups(kind, groups):
+    """batch_size < num_envs (reference pool mode, vector.py:345-390): G groups returned round-robin, each stepped on its
+    own stream.  Envs are independent, so every env's trajectory must equal the oracle's for the same per-env action
+    sequence, and ids / shapes follow the reference (agents_per_batch = batch_size)."""
+    n, h = 64, 30
+    b = n // groups
+    vec = pvec.make(ocean.env_creator(kind), env_kwargs=FAST_END[kind], num_envs=n, backend=pvec.B200, batch_size=b)
+    assert isinstance(vec, pvec.B200Pool) and vec.agents_per_batch == b and vec.num_agents == n and vec.num_envs == b
+    ora = OracleVec(kind, n, iparam=IPARAM[kind](FAST_END[kind]))
+    tape = tape_for(kind, h, n, seed=4)
+    vec.async_reset(7)
+    ora.async_reset(7)
+    for t in range(h):
+        oo, orr, ot, _, _, _, _ = ora.recv()
+        for g in range(groups):
+            o, r, term, trunc, infos, ids, mask = vec.recv()
+            lo, hi = g * b, (g + 1) * b
+            assert np.array_equal(ids, np.arange(lo, hi))
+            assert np.array_equal(cpu(o), oo[lo:hi]) and np.array_equal(cpu(r), orr[lo:hi]) and np.array_equal(cpu(term), ot[lo:hi])
+            vec.send(torch.as_tensor(tape[t, lo:hi], device='cuda'))
+        ora.send(tape[t])
+    vec.close()
+
+
+def test_pool_mode_through_evaluate_train():
+    """Pool-mode vecenv through create/evaluate/train: rows land in arrival order t*N + e, so the stored rollout replays
+    through the oracle exactly like the non-pool one."""
+    import pufferlib_b200
+    from pufferlib_b200 import models
+    from pufferlib_b200.frameworks import cleanrl
+    n, h, b = 64, 16, 16
+    vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200, batch_size=b)
+    torch.manual_seed(0)
+    pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=1).cuda()
+    cfg = pufferlib_b200.namespace(
+        seed=1, torch_deterministic=True, env='breakout', batch_size=n * h, bptt_horizon=8, minibatch_size=n * h // 2,
+        cpu_offload=False, device='cuda', compile=False, learning_rate=2.5e-4, gamma=0.99, gae_lambda=0.95,
+        update_epochs=1, norm_adv=True, clip_coef=0.1, clip_vloss=True, vf_clip_coef=0.1, vf_coef=0.5, ent_coef=0.01,
+        max_grad_norm=0.5, target_kl=None, anneal_lr=False, total_timesteps=10 ** 9)
+    data = clean_pufferl.create(cfg, vec, pol)
+    ora = OracleVec('breakout', n)
+    ora.async_reset(1)
+    for it in range(2):
+        clean_pufferl.evaluate(data)
+        exp = data.experience
+        acts, obs = cpu(exp.actions).reshape(h, n), cpu(exp.obs).reshape(h, n, 128)
+        for t in range(h):
+            o, r, d, _, _, _, _ = ora.recv()
+            assert np.array_equal(o, obs[t]), (it, t)
+            ora.send(acts[t])
+        clean_pufferl.train(data)
+        assert np.isfinite(data.losses.policy_loss)
+        assert data.global_step == (it + 1) * n * h
+    clean_pufferl.close(data)
