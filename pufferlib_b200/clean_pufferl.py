@@ -401,6 +401,10 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         lr = torch.tensor(float(config.learning_rate), device=config.device) if graphed else config.learning_rate
         optimizer = torch.optim.Adam(policy.parameters(), lr=lr, eps=1e-5, fused=True, capturable=graphed)
 
+    model = getattr(policy, 'policy', None)
+    if hasattr(model, 'invalidate_cache'):      # cached head matrix of models.Default: stale after every optimizer step
+        optimizer.register_step_post_hook(lambda *a, **k: model.invalidate_cache())
+
     grad_bucket = None
     if torch.distributed.is_available() and torch.distributed.is_initialized() and \
             torch.distributed.get_world_size() > 1:
@@ -471,6 +475,12 @@ def _rollout_loop(data, infos):
         vecenv.join()            # pool mode: side-stream env steps rejoin the caller's stream (and any graph capture)
 
 
+def _invalidate_policy_cache(data):
+    model = getattr(data.policy, 'policy', None)
+    if hasattr(model, 'invalidate_cache'):
+        model.invalidate_cache()
+
+
 def evaluate(data):
     """Collect one rollout.  With ``config.cuda_graph`` (device path only) the whole H-step loop -- env-step
     kernels, policy forward, sampling, rollout stores -- is captured once and replayed as ONE graph launch; the
@@ -479,6 +489,7 @@ def evaluate(data):
     infos = defaultdict(list)
     vecenv = data.vecenv
     on_device = not getattr(vecenv, 'host_buffers', False)
+    _invalidate_policy_cache(data)          # parameters may have changed since the last rollout
     use_graph = bool(getattr(config, 'cuda_graph_rollout', getattr(config, 'cuda_graph', False))) and on_device and \
         not getattr(vecenv, 'exact_infos', False)
 
@@ -490,9 +501,7 @@ def evaluate(data):
         if data.graph_state == 1:
             torch.cuda.synchronize()
             step0, launches0 = data.global_step, _native.lib().pb_launch_count()
-            cache = getattr(getattr(data.policy, 'policy', None), '_head_cache', None)
-            if cache is not None:
-                cache.clear()                    # anything cached eagerly must be rebuilt inside the capture
+            _invalidate_policy_cache(data)       # anything cached eagerly must be rebuilt inside the capture
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 _rollout_loop(data, infos)       # python-side state advances exactly as in an eager rollout
@@ -720,6 +729,7 @@ def train(data):
             experience.step = 0
             result = data.train_result
 
+    _invalidate_policy_cache(data)          # graph replays update the parameters without running python hooks
     with profile.train_misc:
         if config.anneal_lr:
             frac = 1.0 - data.global_step / config.total_timesteps

@@ -27,20 +27,22 @@ class _DefaultMLPFunction(torch.autograd.Function):
             hidden = torch._addmm_activation(b_enc, x, w_enc.t(), use_gelu=False)
         except (AttributeError, RuntimeError):
             hidden = torch.relu(torch.addmm(b_enc, x, w_enc.t()))
-        # the 8-row head matrix is rebuilt only when a head parameter changed (in-place optimizer steps bump _version):
-        # once per optimizer step in train, once per rollout in evaluate
-        # (a CUDA-graph capture never reuses a matrix built outside it: the flag is part of the key)
-        key = (w_dec._version, b_dec._version, w_val._version, b_val._version, w_dec.data_ptr(),
-               torch.cuda.is_current_stream_capturing())
-        if cache.get('key') != key:
+        # the 8-row head matrix: rebuilt on every forward that records gradients (the parameters change every optimizer
+        # step, and fused optimizers do NOT bump tensor._version, so it cannot be cached across steps); under no_grad
+        # (the rollout: 128 forwards with frozen parameters) it is built once and reused until invalidate_cache()
+        use_cache = not torch.is_grad_enabled()
+        key = (w_dec.data_ptr(), torch.cuda.is_current_stream_capturing())
+        if use_cache and cache.get('key') == key:
+            w_cat, b_cat = cache['w'], cache['b']
+        else:
             w_cat = x.new_zeros(8, hid)
             w_cat[:n_act] = w_dec
             w_cat[n_act] = w_val[0]
             b_cat = x.new_zeros(8)
             b_cat[:n_act] = b_dec
             b_cat[n_act] = b_val[0]
-            cache['key'], cache['w'], cache['b'] = key, w_cat, b_cat
-        w_cat, b_cat = cache['w'], cache['b']
+            if use_cache:
+                cache['key'], cache['w'], cache['b'] = key, w_cat, b_cat
         out = torch.addmm(b_cat, hidden, w_cat.t())
         ctx.save_for_backward(x, hidden, w_cat)
         ctx.n_act = n_act
@@ -88,6 +90,11 @@ class Default(nn.Module):
         self.value_head = nn.Linear(hidden_size, 1)
         self.fast_path = True     # fused forward epilogues + pb_mlp_tail_backward (CUDA, hidden 128, <= 7 actions)
         self._head_cache = {}
+
+    def invalidate_cache(self):
+        """Call after the parameters changed (clean_pufferl does: optimizer post-step hook, start of evaluate, end of
+        train)."""
+        self._head_cache.clear()
 
     def _fast_ok(self, x):
         n_act, hid = self.decoder.weight.shape
