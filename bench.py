@@ -279,7 +279,7 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     try:
         tr = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic_r01.json')))['bytes_per_launch']
         if args.env == 'breakout' and n == 16384 and h == 128:
-            traffic = tr.get({'env_step': 'breakout', 'gae': 'gae', 'obs_gather': 'gather'}.get(dom, dom))
+            traffic = tr.get({'env_step': 'breakout', 'obs_gather': 'gather'}.get(dom, dom))
     except Exception:
         pass
     roof = {'bound': 'hbm', 'kernel': d['kernel'], 'achieved': round(d['achieved'], 1), 'peak': peak_gbs,
