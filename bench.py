@@ -230,6 +230,19 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     t_g = time_launches(gather, 5)
     out['obs_gather'] = dict(kernel='k_minibatch_gather<uint4,4>', bytes_per_launch=2 * n * h * o, seconds=t_g,
                              launches_per_step=1)
+    # fused rollout-time policy step (encoder + ReLU + heads + sampling), launched on the rollout rows
+    pol = data.policy
+    if hasattr(pol, '_policy_step_fused') and args.env == 'breakout':
+        obs_rows = [exp.obs[t * n:(t + 1) * n] for t in range(h)]
+        outs3 = (torch.empty(n, device='cuda'), torch.empty(n, device='cuda'), torch.empty(n, dtype=torch.int64, device='cuda'))
+
+        def pstep(i):
+            with torch.no_grad():
+                pol._policy_step_fused(obs_rows[i % h], outs3)
+        pstep(0)
+        t_pol = time_launches(pstep, h)
+        out['policy_step'] = dict(kernel='k_policy_mlp_sample + counter add', seconds=t_pol,
+                                  bytes_per_launch=n * (o + 16) + 128 * 128 * 4, launches_per_step=h)
     # train-side kernels at the minibatch size of the workload (rotating buffers > L2 where the working set is small)
     if args.env != 'pong' and args.hidden == 128:
         mb = n * h // args.minibatches

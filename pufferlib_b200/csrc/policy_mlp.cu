@@ -14,12 +14,12 @@
 //     entropy and writes action, logprob, value straight into the rollout rows.
 // Tensor-core path note: this is a 128x128x128 tile per CTA, far below the size where tcgen05/TMEM pays; the large
 // training GEMMs stay on cuBLAS (tcgen05 inside the library).
+#include <stdlib.h>
+
 #include "pb_common.cuh"
 
 namespace {
 
-constexpr int PM_THREADS = 256;
-constexpr int PM_ROWS = 128;        // rows per CTA
 constexpr int PM_K = 128;           // obs features
 constexpr int PM_H = 128;           // hidden units
 constexpr int PM_PITCH = PM_K + 4;  // shared row pitch in floats: banks 4*row + col -> conflict-free fragment loads
@@ -48,7 +48,10 @@ struct PolicyParams {
     int64_t* actions; float* logprobs; float* values; float* entropies;   // [M] each (entropies may be null)
 };
 
-__global__ void __launch_bounds__(PM_THREADS, 1) k_policy_mlp_sample(PolicyParams p) {
+// PM_ROWS rows per CTA, one warp per 16 rows (PM_ROWS = 64: 128 threads, 101 KB shared -> 2 CTAs per SM)
+template <int PM_ROWS>
+__global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams p) {
+    constexpr int PM_THREADS = PM_ROWS * 2;
     extern __shared__ __align__(16) float smem[];
     float* sX = smem;                              // [128][132]
     float* sW = smem + PM_ROWS * PM_PITCH;         // [128][132]  (row = hidden unit, col = input feature)
@@ -64,6 +67,9 @@ __global__ void __launch_bounds__(PM_THREADS, 1) k_policy_mlp_sample(PolicyParam
         const int r = i >> 5, q = i & 31;
         if (row0 + r < p.m) cp16(sX + r * PM_PITCH + 4 * q, p.obs + (row0 + r) * p.obs_stride + 4 * q);
         else *reinterpret_cast<float4*>(sX + r * PM_PITCH + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < PM_H * (PM_K / 4); i += PM_THREADS) {
+        const int r = i >> 5, q = i & 31;
         cp16(sW + r * PM_PITCH + 4 * q, p.w_enc + r * PM_K + 4 * q);
     }
     for (int i = tid; i < 8 * PM_H; i += PM_THREADS) sWh[i >> 7][i & 127] = p.w_heads[i];
@@ -172,11 +178,18 @@ extern "C" int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const 
                "pb_policy_mlp_sample: null pointer");
     PB_REQUIRE(obs_stride >= PM_K && obs_stride % 4 == 0 && ((uintptr_t)obs & 15) == 0 && ((uintptr_t)w_enc & 15) == 0,
                PB_ERR_INVALID, "pb_policy_mlp_sample: obs / w_enc must be 16-byte aligned, stride a multiple of 4");
-    const size_t smem = (size_t)2 * PM_ROWS * PM_PITCH * sizeof(float);
-    PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PolicyParams p{obs, obs_stride, w_enc, b_enc, w_heads, b_heads, m, n_act, seed, counter_dev,
                    actions, logprobs, values, entropies};
-    k_policy_mlp_sample<<<(unsigned)pb_ceil_div(m, PM_ROWS), PM_THREADS, smem, (cudaStream_t)stream>>>(p);
+    static const int rows_cfg = [] { const char* e = getenv("PB_POLICY_ROWS"); return e ? atoi(e) : 64; }();
+    if (rows_cfg == 128) {
+        const size_t smem = (size_t)(128 + PM_H) * PM_PITCH * sizeof(float);
+        PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_policy_mlp_sample<128><<<(unsigned)pb_ceil_div(m, 128), 256, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        const size_t smem = (size_t)(64 + PM_H) * PM_PITCH * sizeof(float);
+        PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_policy_mlp_sample<64><<<(unsigned)pb_ceil_div(m, 64), 128, smem, (cudaStream_t)stream>>>(p);
+    }
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

@@ -97,8 +97,9 @@ def test_fused_policy_writes_rollout_rows_and_strided_heads():
         assert a.data_ptr() == ar.data_ptr() and lp.data_ptr() == lr.data_ptr() and v.data_ptr() == vr.data_ptr()
         _, ref_lp, ref_ent, ref_v = pol(obs, action=ar)           # torch formulation on the same actions
     assert int(ar.min()) >= 0 and int(ar.max()) < 4
-    assert torch.allclose(lr, ref_lp, atol=1e-5) and torch.allclose(ent, ref_ent, atol=1e-5)
-    assert torch.allclose(vr, ref_v.flatten(), atol=1e-6)
+    # the fused step evaluates the MLP with mma.sync TF32 tiles, the torch path with cuBLAS TF32: ~1e-3 agreement
+    assert torch.allclose(lr, ref_lp, atol=3e-3) and torch.allclose(ent, ref_ent, atol=3e-3)
+    assert torch.allclose(vr, ref_v.flatten(), atol=3e-3)
     # two heads in one GEMM == two separate Linear layers (TF32 tensor-core GEMMs: ~1e-3 relative)
     hid = torch.relu(pol.policy.encoder(obs))
     assert torch.allclose(pol.policy.decode_actions(hid, None)[0], pol.policy.decoder(hid), atol=5e-3)
