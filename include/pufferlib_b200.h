@@ -210,11 +210,13 @@ int pb_ppo_loss(const float* logits, int64_t logits_stride, const float* value, 
  * both heads, sample_logits (frameworks/cleanrl.py:25-47) and the value / logprob / action row stores of
  * Experience.store (clean_pufferl.py:443-446) in ONE launch per env step; the hidden layer never leaves the SM
  * (mma.sync TF32 tensor-core tiles, fp32 accumulate).  w_heads / b_heads: the 8-row padded head matrix
- * (n_act logits | value | zeros).  Sampling: counter-based inverse CDF on (seed, *counter_dev, row). */
+ * (n_act logits | value | zeros).  Sampling: counter-based inverse CDF on (seed, *counter_dev, row).  With a non-null
+ * ticket_dev (one zero-initialised uint32 owned by the caller) the last CTA to finish advances *counter_dev by 1, so a
+ * captured rollout graph needs no separate counter update per env step. */
 int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const float* w_enc, const float* b_enc,
                          const float* w_heads, const float* b_heads, int64_t m, int32_t in_features, int32_t hidden_size,
-                         int32_t n_act, uint64_t seed, const uint64_t* counter_dev, int64_t* actions, float* logprobs,
-                         float* values, float* entropies, void* stream);
+                         int32_t n_act, uint64_t seed, uint64_t* counter_dev, uint32_t* ticket_dev, int64_t* actions,
+                         float* logprobs, float* values, float* entropies, void* stream);
 
 /* -- policy tail backward ---------------------------------------------------------------------------------------------
  * For models.Default (pufferlib/models.py:12-62: Linear+ReLU encoder, action head + value head): everything of the

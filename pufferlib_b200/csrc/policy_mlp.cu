@@ -44,7 +44,7 @@ struct PolicyParams {
     const float* w_enc; const float* b_enc;    // [128][128], [128]
     const float* w_heads; const float* b_heads;  // [8][128], [8]  (n_act logits | value | zero pad)
     int64_t m; int n_act;
-    uint64_t seed; const uint64_t* counter;
+    uint64_t seed; uint64_t* counter; unsigned int* ticket;
     int64_t* actions; float* logprobs; float* values; float* entropies;   // [M] each (entropies may be null)
 };
 
@@ -62,38 +62,52 @@ __global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams 
     const int g = lane >> 2, t = lane & 3;
     const int64_t row0 = (int64_t)blockIdx.x * PM_ROWS;
 
-    // ---- stage the observation tile and the weights (16-byte async copies; rows past M are zero-filled)
-    for (int i = tid; i < PM_ROWS * (PM_K / 4); i += PM_THREADS) {
-        const int r = i >> 5, q = i & 31;
-        if (row0 + r < p.m) cp16(sX + r * PM_PITCH + 4 * q, p.obs + (row0 + r) * p.obs_stride + 4 * q);
-        else *reinterpret_cast<float4*>(sX + r * PM_PITCH + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    for (int i = tid; i < PM_H * (PM_K / 4); i += PM_THREADS) {
-        const int r = i >> 5, q = i & 31;
-        cp16(sW + r * PM_PITCH + 4 * q, p.w_enc + r * PM_K + 4 * q);
+    const uint64_t offset = p.counter ? *p.counter : 0ull;   // every CTA reads it before taking its exit ticket
+
+    // ---- stage the observation tile and the weights: 16-byte async copies in 4 commit groups of 32 k-columns each,
+    //      so the first k-steps of the product start while the later columns are still in flight
+    //      (rows past M are zero-filled)
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) {
+        for (int i = tid; i < PM_ROWS * 8; i += PM_THREADS) {
+            const int r = i >> 3, q = 8 * kc + (i & 7);
+            if (row0 + r < p.m) cp16(sX + r * PM_PITCH + 4 * q, p.obs + (row0 + r) * p.obs_stride + 4 * q);
+            else *reinterpret_cast<float4*>(sX + r * PM_PITCH + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int i = tid; i < PM_H * 8; i += PM_THREADS) {
+            const int r = i >> 3, q = 8 * kc + (i & 7);
+            cp16(sW + r * PM_PITCH + 4 * q, p.w_enc + r * PM_K + 4 * q);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int i = tid; i < 8 * PM_H; i += PM_THREADS) sWh[i >> 7][i & 127] = p.w_heads[i];
     if (tid < PM_H) sBe[tid] = p.b_enc[tid];
     if (tid < 8) sBh[tid] = p.b_heads[tid];
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
 
     // ---- hidden tile: warp w owns rows 16w..16w+15, all 128 columns (16 n-tiles), K = 128 (16 k-steps)
     float acc[16][4];
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
     const float* xa = sX + (16 * warp + g) * PM_PITCH + t;
-#pragma unroll 4
-    for (int ks = 0; ks < 16; ++ks) {
-        uint32_t a[4];
-        a[0] = to_tf32(xa[8 * ks]);                       // (row g,   k = 8ks + t)
-        a[1] = to_tf32(xa[8 * PM_PITCH + 8 * ks]);        // (row g+8, k = 8ks + t)
-        a[2] = to_tf32(xa[8 * ks + 4]);                   // (row g,   k = 8ks + t + 4)
-        a[3] = to_tf32(xa[8 * PM_PITCH + 8 * ks + 4]);    // (row g+8, k = 8ks + t + 4)
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt) {
-            const float* wb = sW + (8 * nt + g) * PM_PITCH + 8 * ks + t;   // B[k][n] = W[n][k]
-            mma_tf32(acc[nt], a, to_tf32(wb[0]), to_tf32(wb[4]));
+    for (int kc = 0; kc < 4; ++kc) {
+        if (kc == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (kc == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (kc == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll 2
+        for (int ks = 4 * kc; ks < 4 * kc + 4; ++ks) {
+            uint32_t a[4];
+            a[0] = to_tf32(xa[8 * ks]);                       // (row g,   k = 8ks + t)
+            a[1] = to_tf32(xa[8 * PM_PITCH + 8 * ks]);        // (row g+8, k = 8ks + t)
+            a[2] = to_tf32(xa[8 * ks + 4]);                   // (row g,   k = 8ks + t + 4)
+            a[3] = to_tf32(xa[8 * PM_PITCH + 8 * ks + 4]);    // (row g+8, k = 8ks + t + 4)
+#pragma unroll
+            for (int nt = 0; nt < 16; ++nt) {
+                const float* wb = sW + (8 * nt + g) * PM_PITCH + 8 * ks + t;   // B[k][n] = W[n][k]
+                mma_tf32(acc[nt], a, to_tf32(wb[0]), to_tf32(wb[4]));
+            }
         }
     }
     // ---- bias + ReLU on the accumulators; heads = hidden @ Wh^T as a second mma with A = the C fragments:
@@ -124,7 +138,9 @@ __global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams 
     if (t < 2) {
         const int64_t r = row0 + 16 * warp + g + 8 * t;
         if (r < p.m) {
-            const float* z = rowv[t];
+            float z[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) z[k] = t ? rowv[1][k] : rowv[0][k];
             float mx = -INFINITY;
 #pragma unroll
             for (int k = 0; k < 8; ++k) if (k < p.n_act) mx = fmaxf(mx, z[k]);
@@ -132,7 +148,6 @@ __global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams 
 #pragma unroll
             for (int k = 0; k < 8; ++k) if (k < p.n_act) sum += expf(z[k] - mx);
             const float lse = mx + logf(sum);
-            const uint64_t offset = p.counter ? *p.counter : 0ull;
             const uint32_t rnd = pb_mix32(p.seed * 0x9E3779B97F4A7C15ull + offset * 0xD1B54A32D192ED03ull +
                                           (uint64_t)r * 0x2545F4914F6CDD1Dull);
             const float u = (float)(rnd >> 8) * (1.0f / 16777216.0f);
@@ -160,14 +175,27 @@ __global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams 
             if (p.entropies) p.entropies[r] = ent;
         }
     }
+    // ---- the last CTA to leave advances the stream counter (every CTA read it before its ticket): the host does not
+    //      need a separate "counter += 1" launch per env step
+    if (p.ticket) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(p.ticket, 1u) == gridDim.x - 1) {
+                *p.ticket = 0u;
+                *p.counter = offset + 1ull;
+                __threadfence();
+            }
+        }
+    }
 }
 
 }  // namespace
 
 extern "C" int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const float* w_enc, const float* b_enc,
                                     const float* w_heads, const float* b_heads, int64_t m, int32_t in_features,
-                                    int32_t hidden_size, int32_t n_act, uint64_t seed, const uint64_t* counter_dev,
-                                    int64_t* actions, float* logprobs, float* values, float* entropies, void* stream) {
+                                    int32_t hidden_size, int32_t n_act, uint64_t seed, uint64_t* counter_dev,
+                                    uint32_t* ticket_dev, int64_t* actions, float* logprobs, float* values, float* entropies, void* stream) {
     PB_REQUIRE(m >= 0, PB_ERR_INVALID, "pb_policy_mlp_sample: negative m");
     if (m == 0) return PB_OK;
     PB_REQUIRE(in_features == PM_K && hidden_size == PM_H, PB_ERR_UNSUPPORTED,
@@ -178,7 +206,8 @@ extern "C" int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const 
                "pb_policy_mlp_sample: null pointer");
     PB_REQUIRE(obs_stride >= PM_K && obs_stride % 4 == 0 && ((uintptr_t)obs & 15) == 0 && ((uintptr_t)w_enc & 15) == 0,
                PB_ERR_INVALID, "pb_policy_mlp_sample: obs / w_enc must be 16-byte aligned, stride a multiple of 4");
-    PolicyParams p{obs, obs_stride, w_enc, b_enc, w_heads, b_heads, m, n_act, seed, counter_dev,
+    PB_REQUIRE(!ticket_dev || counter_dev, PB_ERR_INVALID, "pb_policy_mlp_sample: ticket_dev needs counter_dev");
+    PolicyParams p{obs, obs_stride, w_enc, b_enc, w_heads, b_heads, m, n_act, seed, counter_dev, ticket_dev,
                    actions, logprobs, values, entropies};
     static const int rows_cfg = [] { const char* e = getenv("PB_POLICY_ROWS"); return e ? atoi(e) : 64; }();
     if (rows_cfg == 128) {

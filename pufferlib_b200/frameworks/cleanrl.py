@@ -44,6 +44,7 @@ class Policy(torch.nn.Module):
         self.fused_sample = fused_sample
         self._seed = int(seed)
         self._counter = None     # device-side draw counter: CUDA-graph replays keep drawing fresh numbers
+        self._ticket = None      # exit ticket of pb_policy_mlp_sample (its last CTA advances the counter)
 
     def get_value(self, x, state=None):
         _, value = self.policy(x)
@@ -83,13 +84,14 @@ class Policy(torch.nn.Module):
         ent = torch.empty(n, dtype=torch.float32, device=dev)
         if self._counter is None:
             self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        if self._ticket is None:
+            self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         w_cat, b_cat = model.head_matrix()
         _native.check(_native.lib().pb_policy_mlp_sample(
             _native.ptr(x2), x2.stride(0), _native.ptr(model.encoder.weight), _native.ptr(model.encoder.bias),
             _native.ptr(w_cat), _native.ptr(b_cat), n, 128, hid, n_act, C.c_uint64(self._seed),
-            _native.ptr(self._counter), _native.ptr(actions), _native.ptr(logprob), _native.ptr(value), _native.ptr(ent),
-            _native.stream_ptr()))
-        self._counter.add_(1)
+            _native.ptr(self._counter), _native.ptr(self._ticket), _native.ptr(actions), _native.ptr(logprob),
+            _native.ptr(value), _native.ptr(ent), _native.stream_ptr()))   # the kernel's last CTA advances the counter
         return actions, logprob, ent, value
 
     def _sample_fused(self, logits, value, out=None):

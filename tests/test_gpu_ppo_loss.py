@@ -164,5 +164,11 @@ def test_fused_policy_step_matches_torch_policy(m):
         freq = torch.bincount(ar, minlength=4).float() / m
         expect = torch.softmax(logits, -1).mean(0)
         assert float((freq - expect).abs().max()) < 0.02
-    a2, _, _, _ = pol(x) if False else (None, None, None, None)
+    # the kernel's last CTA advances the device draw counter: one per call, and the next call draws fresh numbers
+    assert int(pol._counter.item()) == 1 and int(pol._ticket.item()) == 0
+    with torch.no_grad():
+        a2, _, _, _ = pol(x)
+    assert int(pol._counter.item()) == 2 and int(pol._ticket.item()) == 0
+    if m >= 16384:
+        assert 0.3 < float((a2 != ar).float().mean()) < 0.95
     vec.close()
