@@ -49,7 +49,7 @@ struct PolicyParams {
 };
 
 // PM_ROWS rows per CTA, one warp per 16 rows (PM_ROWS = 64: 128 threads, 101 KB shared -> 2 CTAs per SM)
-template <int PM_ROWS>
+template <int PM_ROWS, int NCH>
 __global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams p) {
     constexpr int PM_THREADS = PM_ROWS * 2;
     extern __shared__ __align__(16) float smem[];
@@ -68,14 +68,15 @@ __global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams 
     //      so the first k-steps of the product start while the later columns are still in flight
     //      (rows past M are zero-filled)
 #pragma unroll
-    for (int kc = 0; kc < 4; ++kc) {
-        for (int i = tid; i < PM_ROWS * 8; i += PM_THREADS) {
-            const int r = i >> 3, q = 8 * kc + (i & 7);
+    constexpr int QC = 32 / NCH;   // float4 columns per commit group
+    for (int kc = 0; kc < NCH; ++kc) {
+        for (int i = tid; i < PM_ROWS * QC; i += PM_THREADS) {
+            const int r = i / QC, q = QC * kc + (i % QC);
             if (row0 + r < p.m) cp16(sX + r * PM_PITCH + 4 * q, p.obs + (row0 + r) * p.obs_stride + 4 * q);
             else *reinterpret_cast<float4*>(sX + r * PM_PITCH + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        for (int i = tid; i < PM_H * 8; i += PM_THREADS) {
-            const int r = i >> 3, q = 8 * kc + (i & 7);
+        for (int i = tid; i < PM_H * QC; i += PM_THREADS) {
+            const int r = i / QC, q = QC * kc + (i % QC);
             cp16(sW + r * PM_PITCH + 4 * q, p.w_enc + r * PM_K + 4 * q);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -90,14 +91,14 @@ __global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams 
     for (int nt = 0; nt < 16; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
     const float* xa = sX + (16 * warp + g) * PM_PITCH + t;
 #pragma unroll
-    for (int kc = 0; kc < 4; ++kc) {
-        if (kc == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
-        else if (kc == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (kc == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    for (int kc = 0; kc < NCH; ++kc) {
+        if (NCH - 1 - kc == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (NCH - 1 - kc == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (NCH - 1 - kc == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-#pragma unroll 2
-        for (int ks = 4 * kc; ks < 4 * kc + 4; ++ks) {
+#pragma unroll 4
+        for (int ks = (16 / NCH) * kc; ks < (16 / NCH) * (kc + 1); ++ks) {
             uint32_t a[4];
             a[0] = to_tf32(xa[8 * ks]);                       // (row g,   k = 8ks + t)
             a[1] = to_tf32(xa[8 * PM_PITCH + 8 * ks]);        // (row g+8, k = 8ks + t)
@@ -209,16 +210,18 @@ extern "C" int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const 
     PB_REQUIRE(!ticket_dev || counter_dev, PB_ERR_INVALID, "pb_policy_mlp_sample: ticket_dev needs counter_dev");
     PolicyParams p{obs, obs_stride, w_enc, b_enc, w_heads, b_heads, m, n_act, seed, counter_dev, ticket_dev,
                    actions, logprobs, values, entropies};
-    static const int rows_cfg = [] { const char* e = getenv("PB_POLICY_ROWS"); return e ? atoi(e) : 64; }();
-    if (rows_cfg == 128) {
-        const size_t smem = (size_t)(128 + PM_H) * PM_PITCH * sizeof(float);
-        PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_policy_mlp_sample<128><<<(unsigned)pb_ceil_div(m, 128), 256, smem, (cudaStream_t)stream>>>(p);
-    } else {
-        const size_t smem = (size_t)(64 + PM_H) * PM_PITCH * sizeof(float);
-        PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_policy_mlp_sample<64><<<(unsigned)pb_ceil_div(m, 64), 128, smem, (cudaStream_t)stream>>>(p);
-    }
+    static const int chunks_cfg = [] { const char* e = getenv("PB_POLICY_CHUNKS"); return e ? atoi(e) : 4; }();
+    const size_t smem = (size_t)(64 + PM_H) * PM_PITCH * sizeof(float);
+    const unsigned grid = (unsigned)pb_ceil_div(m, 64);
+#define PB_POLICY_LAUNCH(NCH)                                                                                          \
+    do {                                                                                                               \
+        PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample<64, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_policy_mlp_sample<64, NCH><<<grid, 128, smem, (cudaStream_t)stream>>>(p);                                    \
+    } while (0)
+    if (chunks_cfg == 1) PB_POLICY_LAUNCH(1);
+    else if (chunks_cfg == 2) PB_POLICY_LAUNCH(2);
+    else PB_POLICY_LAUNCH(4);
+#undef PB_POLICY_LAUNCH
     PB_LAUNCH_CHECK();
     return PB_OK;
 }
