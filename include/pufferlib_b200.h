@@ -210,7 +210,8 @@ int pb_ppo_loss(const float* logits, int64_t logits_stride, const float* value, 
  * both heads, sample_logits (frameworks/cleanrl.py:25-47) and the value / logprob / action row stores of
  * Experience.store (clean_pufferl.py:443-446) in ONE launch per env step; the hidden layer never leaves the SM
  * (mma.sync TF32 tensor-core tiles, fp32 accumulate).  w_heads / b_heads: the 8-row padded head matrix
- * (n_act logits | value | zeros).  Sampling: counter-based inverse CDF on (seed, *counter_dev, row).  With a non-null
+ * (n_act logits | value | zeros).  w_enc is consumed as TF32: the tensor core ignores the low 13 mantissa bits, so pass
+ * it pre-rounded (cvt.rna) for round-to-nearest products.  Sampling: counter-based inverse CDF on (seed, *counter_dev, row).  With a non-null
  * ticket_dev (one zero-initialised uint32 owned by the caller) the last CTA to finish advances *counter_dev by 1, so a
  * captured rollout graph needs no separate counter update per env step. */
 int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const float* w_enc, const float* b_enc,

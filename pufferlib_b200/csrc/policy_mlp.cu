@@ -4,8 +4,9 @@
 //   encoder Linear + ReLU -> action head + value head (pufferlib/models.py:12-62) -> sample_logits
 //   (pufferlib/frameworks/cleanrl.py:25-47) -> Experience.store of value / logprob / action (clean_pufferl.py:443-446)
 // which the library path runs as 2 GEMM launches + sampler + counter update.  At rollout time M = num_envs rows (16384),
-// so the GEMMs are tiny (0.5 GFLOP) and launch/latency bound; here a CTA owns 128 rows:
-//   * the 128x128 fp32 observation tile and the 128x128 encoder weights land in shared memory with 16-byte cp.async;
+// so the GEMMs are tiny (0.5 GFLOP) and launch/latency bound; here a CTA owns 64 rows:
+//   * the 64x128 fp32 observation tile and the 128x128 encoder weights land in shared memory as 512-byte bulk copies
+//     (cp.async.bulk, one per row, two mbarriers);
 //   * hidden = relu(X W^T + b) on the tensor cores (mma.sync m16n8k8 TF32, fp32 accumulate; a warp owns 16 rows x 128
 //     columns, accumulators stay in registers -- `hidden` is never written to memory);
 //   * the two heads (n_act logits + value, padded to 8 columns) are a second mma whose A operand is the accumulator
@@ -14,15 +15,14 @@
 //     entropy and writes action, logprob, value straight into the rollout rows.
 // Tensor-core path note: this is a 128x128x128 tile per CTA, far below the size where tcgen05/TMEM pays; the large
 // training GEMMs stay on cuBLAS (tcgen05 inside the library).
-#include <stdlib.h>
-
 #include "pb_common.cuh"
+#include "tma.cuh"
 
 namespace {
 
 constexpr int PM_K = 128;           // obs features
 constexpr int PM_H = 128;           // hidden units
-constexpr int PM_PITCH = PM_K + 4;  // shared row pitch in floats: banks 4*row + col -> conflict-free fragment loads
+constexpr int PM_PITCH = PM_K + 8;  // shared row pitch in floats (544 B): conflict-free 64-bit fragment loads
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
@@ -48,66 +48,66 @@ struct PolicyParams {
     int64_t* actions; float* logprobs; float* values; float* entropies;   // [M] each (entropies may be null)
 };
 
-// PM_ROWS rows per CTA, one warp per 16 rows (PM_ROWS = 64: 128 threads, 101 KB shared -> 2 CTAs per SM)
-template <int PM_ROWS, int NCH>
-__global__ void __launch_bounds__(PM_ROWS * 2) k_policy_mlp_sample(PolicyParams p) {
-    constexpr int PM_THREADS = PM_ROWS * 2;
-    extern __shared__ __align__(16) float smem[];
-    float* sX = smem;                              // [128][132]
-    float* sW = smem + PM_ROWS * PM_PITCH;         // [128][132]  (row = hidden unit, col = input feature)
+// 64 rows per CTA, one warp per 16 rows: 128 threads, 104 KB shared -> 2 CTAs per SM, 256 CTAs at 16384 rows
+constexpr int PM_ROWS = 64;
+constexpr int PM_THREADS = 2 * PM_ROWS;
+
+__global__ void __launch_bounds__(PM_THREADS) k_policy_mlp_sample(PolicyParams p) {
+    extern __shared__ __align__(128) float smem[];
+    float* sX = smem;                              // [64][136]
+    float* sW = smem + PM_ROWS * PM_PITCH;         // [128][136]  (row = hidden unit, col = input feature)
     __shared__ float sWh[8][PM_H];
     __shared__ float sBe[PM_H];
     __shared__ float sBh[8];
+    __shared__ __align__(8) uint64_t bars[2];      // [0]: obs tile + W rows 0..63, [1]: W rows 64..127
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int64_t row0 = (int64_t)blockIdx.x * PM_ROWS;
-
+    const int valid = (int)((p.m - row0) < PM_ROWS ? (p.m - row0) : PM_ROWS);
     const uint64_t offset = p.counter ? *p.counter : 0ull;   // every CTA reads it before taking its exit ticket
 
-    // ---- stage the observation tile and the weights: 16-byte async copies in 4 commit groups of 32 k-columns each,
-    //      so the first k-steps of the product start while the later columns are still in flight
-    //      (rows past M are zero-filled)
-#pragma unroll
-    constexpr int QC = 32 / NCH;   // float4 columns per commit group
-    for (int kc = 0; kc < NCH; ++kc) {
-        for (int i = tid; i < PM_ROWS * QC; i += PM_THREADS) {
-            const int r = i / QC, q = QC * kc + (i % QC);
-            if (row0 + r < p.m) cp16(sX + r * PM_PITCH + 4 * q, p.obs + (row0 + r) * p.obs_stride + 4 * q);
-            else *reinterpret_cast<float4*>(sX + r * PM_PITCH + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int i = tid; i < PM_H * QC; i += PM_THREADS) {
-            const int r = i / QC, q = QC * kc + (i % QC);
-            cp16(sW + r * PM_PITCH + 4 * q, p.w_enc + r * PM_K + 4 * q);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    // ---- stage the observation tile and the weights: one 512-byte bulk copy (TMA engine) per row, completion counted
+    //      on two mbarriers so the first 8 n-tiles start while the second half of W is still in flight
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bars[0], (uint32_t)(valid + 64) * PM_K * 4u);
+        mbar_expect_tx(&bars[1], 64u * PM_K * 4u);
+    }
+    if (tid >= valid && tid < PM_ROWS) {           // rows past M: zeros
+#pragma unroll 8
+        for (int q = 0; q < PM_K / 4; ++q) *reinterpret_cast<float4*>(sX + tid * PM_PITCH + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int i = tid; i < 8 * PM_H; i += PM_THREADS) sWh[i >> 7][i & 127] = p.w_heads[i];
     if (tid < PM_H) sBe[tid] = p.b_enc[tid];
     if (tid < 8) sBh[tid] = p.b_heads[tid];
+    __syncthreads();
+    if (tid < valid) tma_load_1d(sX + tid * PM_PITCH, p.obs + (row0 + tid) * p.obs_stride, PM_K * 4u, &bars[0]);
+    tma_load_1d(sW + tid * PM_PITCH, p.w_enc + (int64_t)tid * PM_K, PM_K * 4u, &bars[tid >> 6]);
 
-    // ---- hidden tile: warp w owns rows 16w..16w+15, all 128 columns (16 n-tiles), K = 128 (16 k-steps)
+    // ---- hidden tile: warp w owns rows 16w..16w+15, all 128 columns (16 n-tiles), K = 128 (16 k-steps).
+    //      The sum over k is order-free, so k slots (t, t+4) of a k-step are mapped to the ADJACENT columns
+    //      (8ks + 2t, 8ks + 2t + 1) for both operands: every fragment is one 64-bit shared load (pitch 136: conflict-free).
+    //      A is rounded to TF32 here; W arrives pre-rounded (or is truncated by the tensor core, see the header).
     float acc[16][4];
 #pragma unroll
     for (int nt = 0; nt < 16; ++nt) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
-    const float* xa = sX + (16 * warp + g) * PM_PITCH + t;
+    const float* xa = sX + (16 * warp + g) * PM_PITCH + 2 * t;
+    const float* wbase = sW + g * PM_PITCH + 2 * t;
 #pragma unroll
-    for (int kc = 0; kc < NCH; ++kc) {
-        if (NCH - 1 - kc == 3) asm volatile("cp.async.wait_group 3;" ::: "memory");
-        else if (NCH - 1 - kc == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (NCH - 1 - kc == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
+    for (int half = 0; half < 2; ++half) {
+        mbar_wait(&bars[half], 0);
 #pragma unroll 4
-        for (int ks = (16 / NCH) * kc; ks < (16 / NCH) * (kc + 1); ++ks) {
-            uint32_t a[4];
-            a[0] = to_tf32(xa[8 * ks]);                       // (row g,   k = 8ks + t)
-            a[1] = to_tf32(xa[8 * PM_PITCH + 8 * ks]);        // (row g+8, k = 8ks + t)
-            a[2] = to_tf32(xa[8 * ks + 4]);                   // (row g,   k = 8ks + t + 4)
-            a[3] = to_tf32(xa[8 * PM_PITCH + 8 * ks + 4]);    // (row g+8, k = 8ks + t + 4)
+        for (int ks = 0; ks < 16; ++ks) {
+            const float2 x0 = *reinterpret_cast<const float2*>(xa + 8 * ks);
+            const float2 x1 = *reinterpret_cast<const float2*>(xa + 8 * PM_PITCH + 8 * ks);
+            const uint32_t a[4] = {to_tf32(x0.x), to_tf32(x1.x), to_tf32(x0.y), to_tf32(x1.y)};
 #pragma unroll
-            for (int nt = 0; nt < 16; ++nt) {
-                const float* wb = sW + (8 * nt + g) * PM_PITCH + 8 * ks + t;   // B[k][n] = W[n][k]
-                mma_tf32(acc[nt], a, to_tf32(wb[0]), to_tf32(wb[4]));
+            for (int n8 = 0; n8 < 8; ++n8) {
+                const int nt = 8 * half + n8;
+                const float2 w = *reinterpret_cast<const float2*>(wbase + 8 * nt * PM_PITCH + 8 * ks);   // B[k][n] = W[n][k]
+                mma_tf32(acc[nt], a, __float_as_uint(w.x), __float_as_uint(w.y));
             }
         }
     }
@@ -210,18 +210,9 @@ extern "C" int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const 
     PB_REQUIRE(!ticket_dev || counter_dev, PB_ERR_INVALID, "pb_policy_mlp_sample: ticket_dev needs counter_dev");
     PolicyParams p{obs, obs_stride, w_enc, b_enc, w_heads, b_heads, m, n_act, seed, counter_dev, ticket_dev,
                    actions, logprobs, values, entropies};
-    static const int chunks_cfg = [] { const char* e = getenv("PB_POLICY_CHUNKS"); return e ? atoi(e) : 4; }();
-    const size_t smem = (size_t)(64 + PM_H) * PM_PITCH * sizeof(float);
-    const unsigned grid = (unsigned)pb_ceil_div(m, 64);
-#define PB_POLICY_LAUNCH(NCH)                                                                                          \
-    do {                                                                                                               \
-        PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample<64, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_policy_mlp_sample<64, NCH><<<grid, 128, smem, (cudaStream_t)stream>>>(p);                                    \
-    } while (0)
-    if (chunks_cfg == 1) PB_POLICY_LAUNCH(1);
-    else if (chunks_cfg == 2) PB_POLICY_LAUNCH(2);
-    else PB_POLICY_LAUNCH(4);
-#undef PB_POLICY_LAUNCH
+    const size_t smem = (size_t)(PM_ROWS + PM_H) * PM_PITCH * sizeof(float);
+    PB_CUDA(cudaFuncSetAttribute(k_policy_mlp_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_policy_mlp_sample<<<(unsigned)pb_ceil_div(m, PM_ROWS), PM_THREADS, smem, (cudaStream_t)stream>>>(p);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

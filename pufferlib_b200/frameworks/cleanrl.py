@@ -87,8 +87,9 @@ class Policy(torch.nn.Module):
         if self._ticket is None:
             self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         w_cat, b_cat = model.head_matrix()
+        w_enc = model.encoder_weight_tf32()
         _native.check(_native.lib().pb_policy_mlp_sample(
-            _native.ptr(x2), x2.stride(0), _native.ptr(model.encoder.weight), _native.ptr(model.encoder.bias),
+            _native.ptr(x2), x2.stride(0), _native.ptr(w_enc), _native.ptr(model.encoder.bias),
             _native.ptr(w_cat), _native.ptr(b_cat), n, 128, hid, n_act, C.c_uint64(self._seed),
             _native.ptr(self._counter), _native.ptr(self._ticket), _native.ptr(actions), _native.ptr(logprob),
             _native.ptr(value), _native.ptr(ent), _native.stream_ptr()))   # the kernel's last CTA advances the counter

@@ -114,6 +114,20 @@ class Default(nn.Module):
             cache['key'], cache['w'], cache['b'] = key, w_cat, b_cat
         return w_cat, b_cat
 
+    def encoder_weight_tf32(self):
+        """The encoder weight rounded to TF32 (round-to-nearest, ties away: cvt.rna) for pb_policy_mlp_sample, which
+        feeds the bits straight to the tensor cores; cached with the head matrix (same invalidation)."""
+        cache = self._head_cache
+        key = (self.encoder.weight.data_ptr(), torch.cuda.is_current_stream_capturing())
+        if not torch.is_grad_enabled() and cache.get('ekey') == key:
+            return cache['wenc']
+        with torch.no_grad():
+            bits = self.encoder.weight.detach().contiguous().view(torch.int32)
+            w = ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+        if not torch.is_grad_enabled():
+            cache['ekey'], cache['wenc'] = key, w
+        return w
+
     def _fast_ok(self, x):
         n_act, hid = self.decoder.weight.shape
         return self.fast_path and x.is_cuda and hid == 128 and n_act + 1 <= 8 and not x.requires_grad
