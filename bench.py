@@ -228,8 +228,10 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                                               exp.num_minibatches, _native.stream_ptr()))
     gather(0)
     t_g = time_launches(gather, 5)
-    out['obs_gather'] = dict(kernel='k_minibatch_gather<uint4,4>', bytes_per_launch=2 * n * h * o, seconds=t_g,
-                             launches_per_step=1)
+    # with zero-copy slab minibatches (the default for the non-LSTM path) the gather is not on the step path at all
+    on_path = 0 if getattr(exp, '_slabs', None) is not None else 1
+    out['obs_gather'] = dict(kernel='k_minibatch_gather<uint4,8>', bytes_per_launch=2 * n * h * o, seconds=t_g,
+                             launches_per_step=on_path)
     # fused rollout-time policy step (encoder + ReLU + heads + sampling), launched on the rollout rows
     pol = data.policy
     if hasattr(pol, '_policy_step_fused') and args.env == 'breakout':
@@ -241,7 +243,7 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                 pol._policy_step_fused(obs_rows[i % h], outs3)
         pstep(0)
         t_pol = time_launches(pstep, h)
-        out['policy_step'] = dict(kernel='k_policy_mlp_sample + counter add', seconds=t_pol,
+        out['policy_step'] = dict(kernel='k_policy_mlp_sample', seconds=t_pol,
                                   bytes_per_launch=n * (o + 16) + 128 * 128 * 4, launches_per_step=h)
     # train-side kernels at the minibatch size of the workload (rotating buffers > L2 where the working set is small)
     if args.env != 'pong' and args.hidden == 128:
@@ -378,7 +380,7 @@ def run_b200(args):
                        'bptt_horizon': 16, 'parallelism': f'dp{world} (env shards + 1 NCCL grad all-reduce/step)',
                        'l2': 'inputs larger than L2 (1 GiB rollout rotates; no flush needed)',
                        'cuda_graph_rollout': not args.no_graph,
-                       'cuda_graph_train': 'whole' if data.train_graph_state == 2 else ('segments' if data.train_segments else False), 'note': data.msg},
+                       'cuda_graph_train': 'whole' if data.train_graph_state == 2 else ('segments' if data.train_segments else False), 'zero_copy_minibatches': getattr(data.experience, '_slabs', None) is not None, 'note': data.msg},
             'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'roofline_kernels': roof_all,
             'cpu_baseline': cpu, 'clocks': clk, 'profile_s': prof, 'env_stats': stats,
         }

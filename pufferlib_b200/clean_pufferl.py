@@ -219,7 +219,8 @@ class Experience:
         self.returns_sorted = torch.zeros(batch_size, **z)
         self.returns = torch.zeros(batch_size, **z)           # returns_np of clean_pufferl.py:476
         shape3 = (nm, self.minibatch_rows, bptt_horizon)
-        self.b_obs = torch.zeros(nm, self.minibatch_rows, bptt_horizon, *obs_shape, dtype=obs_dtype, **z)
+        self._b_obs = None        # [nm, minibatch_rows, bptt, *obs]: allocated by the first flatten_batch() that gathers
+        self._slabs = None        # zero-copy minibatch form (flatten_batch_slabs)
         self.b_actions = torch.zeros(shape3, dtype=torch.int64, **z)
         self.b_logprobs = torch.zeros(shape3, **z)
         self.b_dones = torch.zeros(shape3, **z)
@@ -230,6 +231,13 @@ class Experience:
         lib = _native.lib()
         self._advnorm_ws = torch.zeros(max(16, lib.pb_adv_norm_workspace_bytes(nm, mb)), dtype=torch.uint8, **z)
         self._gae_ws = None
+
+    @property
+    def b_obs(self):
+        if self._b_obs is None:
+            self._b_obs = torch.zeros(self.num_minibatches, self.minibatch_rows, self.bptt_horizon, *self.obs_shape,
+                                      dtype=self.obs.dtype, device=self.device)
+        return self._b_obs
 
     @property
     def full(self):
@@ -339,12 +347,49 @@ class Experience:
             _native.ptr(self.obs), _native.ptr(self.b_obs), self.obs_row_bytes, n, h, self.num_minibatches,
             self.minibatch_rows, self.bptt_horizon, 0, self.num_minibatches, s))
 
-    def normalize_advantages(self):
+    def flatten_batch_slabs(self, advantages=None):
+        """flatten_batch without the observation gather, for policies whose loss does not depend on the row order
+        inside a minibatch (no LSTM).  Minibatch mb of clean_pufferl.py:466-482 holds the bptt segments s = r*nm + mb;
+        when the segments per env S = H/bptt are a multiple of nm these are, for EVERY env, the time windows
+        k = mb, mb+nm, ... -- in the time-major rollout buffer that is G = S/nm contiguous slabs of bptt*N rows.  So
+        the minibatch observations are a strided view [G, bptt*N, *obs] of self.obs (slab_obs) and only the small
+        per-row tensors are re-ordered (slab-major: s_x[mb][g][j*N + e] = x[((g*nm + mb)*bptt + j)*N + e]).  Same
+        row SETS as the reference, so the minibatch means, the advantage normalisation and the gradients agree up to
+        summation order.  Returns False (nothing done) when the shape condition does not hold."""
+        adv = self.advantages if advantages is None else advantages
+        n, h, nm, bptt = self.num_envs, self.horizon, self.num_minibatches, self.bptt_horizon
+        if h % bptt != 0 or (h // bptt) % nm != 0:
+            return False
+        g_, r_ = (h // bptt) // nm, bptt * n
+        if self._slabs is None:
+            z = dict(device=self.device)
+            mb = self.minibatch_size
+            self._slabs = pufferlib_b200.namespace(
+                actions=torch.zeros(nm, mb, dtype=torch.int64, **z), logprobs=torch.zeros(nm, mb, **z),
+                values=torch.zeros(nm, mb, **z), advantages=torch.zeros(nm, mb, **z), returns=torch.zeros(nm, mb, **z),
+                advantages_normalized=torch.zeros(nm, mb, **z))
+        sl = self._slabs
+        for dst, src in ((sl.actions, self.actions), (sl.logprobs, self.logprobs), (sl.values, self.values)):
+            dst.view(nm, g_, r_).copy_(src.view(g_, nm, r_).transpose(0, 1))
+        sl.advantages.view(nm, g_, bptt, n).copy_(adv.view(n, g_, nm, bptt).permute(2, 1, 3, 0))   # sorted -> slab-major
+        torch.add(sl.advantages, sl.values, out=sl.returns)
+        torch.add(adv, self.values, out=self.returns)            # returns_np of clean_pufferl.py:476 (sorted + arrival)
+        sl.shape = (g_, r_)
+        return True
+
+    def slab_obs(self, mb):
+        """Observations of minibatch mb as a zero-copy view [G, bptt*N, *obs] of the rollout buffer."""
+        g_, r_ = self._slabs.shape
+        return self.obs.view(g_, self.num_minibatches, r_, *self.obs_shape)[:, mb]
+
+    def normalize_advantages(self, slabs=False):
         """clean_pufferl.py:211-213 for every minibatch at once -> self.b_advantages_normalized."""
+        src, dst = (self._slabs.advantages, self._slabs.advantages_normalized) if slabs else \
+            (self.b_advantages, self.b_advantages_normalized)
         _native.check(_native.lib().pb_adv_norm(
-            _native.ptr(self.b_advantages), _native.ptr(self.b_advantages_normalized), self.num_minibatches,
+            _native.ptr(src), _native.ptr(dst), self.num_minibatches,
             self.minibatch_size, _native.ptr(self._advnorm_ws), self._advnorm_ws.numel(), _native.stream_ptr()))
-        return self.b_advantages_normalized
+        return dst
 
 
 class _LazyIdxs:
@@ -566,12 +611,18 @@ def _train_device_part(data, seg=None):
     config, profile, experience = data.config, data.profile, data.experience
     device = experience.device
 
+    # zero-copy minibatches (Experience.flatten_batch_slabs): order-free loss only, i.e. the fused non-LSTM path
+    model = getattr(data.policy, 'policy', None)
+    want_slabs = data.fused_loss and experience.lstm_h is None and hasattr(model, 'forward_packed_slabs') and \
+        bool(getattr(config, 'zero_copy_minibatches', True))
     with profile.train_misc:
         experience.sort_training_data()
         experience.compute_gae(config.gamma, config.gae_lambda)
-        experience.flatten_batch()
+        slabs = want_slabs and experience.flatten_batch_slabs()
+        if not slabs:
+            experience.flatten_batch()
         if config.norm_adv:
-            experience.normalize_advantages()
+            experience.normalize_advantages(slabs=slabs)
 
     n_mb = experience.num_minibatches
     if seg is not None:                        # persistent accumulator: the segment graphs update it in place
@@ -586,18 +637,26 @@ def _train_device_part(data, seg=None):
     carry = {'lstm_state': None, 'approx_kl': None}
 
     def forward_backward(mb):
-        obs = experience.b_obs[mb]
-        atn = experience.b_actions[mb]
-        log_probs = experience.b_logprobs[mb]
-        val = experience.b_values[mb]
-        adv = experience.b_advantages_normalized[mb] if config.norm_adv else experience.b_advantages[mb]
-        ret = experience.b_returns[mb]
+        if slabs:
+            sl = experience._slabs
+            obs = experience.slab_obs(mb)
+            atn, log_probs, val, ret = sl.actions[mb], sl.logprobs[mb], sl.values[mb], sl.returns[mb]
+            adv = sl.advantages_normalized[mb] if config.norm_adv else sl.advantages[mb]
+        else:
+            obs = experience.b_obs[mb]
+            atn = experience.b_actions[mb]
+            log_probs = experience.b_logprobs[mb]
+            val = experience.b_values[mb]
+            adv = experience.b_advantages_normalized[mb] if config.norm_adv else experience.b_advantages[mb]
+            ret = experience.b_returns[mb]
 
         with profile.train_forward:
             packed = None
             if fused:          # logits / value straight from the model; loss + its gradient in one kernel
                 model = data.policy.policy
-                if hasattr(model, 'forward_packed'):
+                if slabs:
+                    packed = model.forward_packed_slabs(obs)
+                elif hasattr(model, 'forward_packed'):
                     packed = model.forward_packed(obs.reshape(-1, *obs_shape))
                 if packed is None:
                     logits, newvalue = model(obs.reshape(-1, *obs_shape))

@@ -23,10 +23,19 @@ class _DefaultMLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_enc, b_enc, w_dec, b_dec, w_val, b_val, cache):
         n_act, hid = w_dec.shape
-        try:
-            hidden = torch._addmm_activation(b_enc, x, w_enc.t(), use_gelu=False)
-        except (AttributeError, RuntimeError):
-            hidden = torch.relu(torch.addmm(b_enc, x, w_enc.t()))
+        if x.dim() == 3:
+            # slab form [G, R, F]: G equally spaced row slabs of the rollout buffer (a strided VIEW, see
+            # Experience.flatten_batch_slabs) -- one GEMM per slab writes its part of the contiguous hidden layer,
+            # the observations are never gathered into a minibatch copy
+            g_, r_, _ = x.shape
+            hidden = x.new_empty(g_ * r_, hid)
+            for g in range(g_):
+                torch._addmm_activation(b_enc, x[g], w_enc.t(), use_gelu=False, out=hidden[g * r_:(g + 1) * r_])
+        else:
+            try:
+                hidden = torch._addmm_activation(b_enc, x, w_enc.t(), use_gelu=False)
+            except (AttributeError, RuntimeError):
+                hidden = torch.relu(torch.addmm(b_enc, x, w_enc.t()))
         # the 8-row head matrix: rebuilt on every forward that records gradients (the parameters change every optimizer
         # step, and fused optimizers do NOT bump tensor._version, so it cannot be cached across steps); under no_grad
         # (the rollout: 128 forwards with frozen parameters) it is built once and reused until invalidate_cache()
@@ -68,7 +77,17 @@ class _DefaultMLPFunction(torch.autograd.Function):
         # dW_enc = dPre^T @ x is one 128x128 output tile with K = M: as a batched GEMM over 64 K-slices (+ a 64-way sum)
         # the library GEMM runs at the HBM roofline (91 us vs 193 us at M = 524288; profiles/tools/gemm_variants.py)
         split = 64
-        if m % split == 0 and m // split >= 256:
+        if x.dim() == 3:            # slab form: the K-slices tile each slab, partial products into one buffer
+            g_, r_, f_ = x.shape
+            sp = max(1, split // g_)
+            while r_ % sp:
+                sp //= 2
+            part = x.new_empty(g_ * sp, hid, f_)
+            for g in range(g_):
+                torch.bmm(dpre[g * r_:(g + 1) * r_].view(sp, r_ // sp, hid).transpose(1, 2),
+                          x[g].view(sp, r_ // sp, f_), out=part[g * sp:(g + 1) * sp])
+            dw_enc = part.sum(0)
+        elif m % split == 0 and m // split >= 256:
             dw_enc = torch.bmm(dpre.view(split, m // split, hid).transpose(1, 2), x.view(split, m // split, -1)).sum(0)
         else:
             dw_enc = dpre.t() @ x
@@ -139,6 +158,18 @@ class Default(nn.Module):
         if not self._fast_ok(x):
             return None
         out = _DefaultMLPFunction.apply(x.float().contiguous(), self.encoder.weight, self.encoder.bias,
+                                        self.decoder.weight, self.decoder.bias, self.value_head.weight,
+                                        self.value_head.bias, self._head_cache)
+        return out, self.decoder.weight.shape[0]
+
+    def forward_packed_slabs(self, slabs):
+        """forward_packed for a minibatch given as [G, R, features] row slabs (a strided view of the rollout
+        observations; Experience.slab_obs): rows of the result are slab-major.  None when the fast path does not apply."""
+        if slabs.dim() > 3:
+            slabs = slabs.flatten(2)          # [G, R, *obs] -> [G, R, features] (a view: obs dims are contiguous)
+        if slabs.dim() != 3 or not self._fast_ok(slabs) or slabs.stride(2) != 1 or slabs.stride(1) != slabs.shape[2]:
+            return None
+        out = _DefaultMLPFunction.apply(slabs.float(), self.encoder.weight, self.encoder.bias,
                                         self.decoder.weight, self.decoder.bias, self.value_head.weight,
                                         self.value_head.bias, self._head_cache)
         return out, self.decoder.weight.shape[0]

@@ -104,6 +104,27 @@ def test_flatten_and_gather_vs_numpy_oracle(n, h, mb, bptt, obs_shape, dtype):
         t_ref = torch.as_tensor(ora.b_advantages[m])
         t_ref = ((t_ref - t_ref.mean()) / (t_ref.std() + 1e-8)).numpy()      # clean_pufferl.py:213 on CPU fp32
         assert np.allclose(norm[m], t_ref, rtol=1e-5, atol=2e-5)
+    # zero-copy minibatch form: same row sets as the reference minibatches, slab-major order inside a minibatch
+    nm, s_per_env = exp.num_minibatches, h // bptt
+    ok = exp.flatten_batch_slabs()
+    assert ok == (h % bptt == 0 and s_per_env % nm == 0)
+    if ok:
+        g_ = s_per_env // nm
+        sl = exp._slabs
+        for name in ('actions', 'logprobs', 'values', 'advantages', 'returns'):
+            s_x, b_x = cpu(getattr(sl, name)), cpu(getattr(exp, 'b_' + name))
+            for m in range(nm):
+                assert np.array_equal(s_x[m].reshape(g_, bptt, n).transpose(2, 0, 1), b_x[m].reshape(n, g_, bptt)), name
+        for m in range(nm):
+            so = exp.slab_obs(m)
+            assert so.data_ptr() == exp.obs.data_ptr() + m * bptt * n * exp.obs_row_bytes     # a view, not a copy
+            assert np.array_equal(cpu(so).reshape(g_, bptt, n, -1).transpose(2, 0, 1, 3),
+                                  cpu(exp.b_obs[m]).reshape(n, g_, bptt, -1))
+        assert np.array_equal(cpu(exp.returns), ora.returns_np)
+        norm_s = cpu(exp.normalize_advantages(slabs=True))
+        for m in range(nm):
+            assert np.allclose(norm_s[m].reshape(g_, bptt, n).transpose(2, 0, 1).reshape(-1), norm[m].reshape(-1),
+                               rtol=1e-6, atol=1e-6)
 
 
 @pytest.mark.parametrize('n_mb,mb_size', [(1, 2), (1, 2048), (4, 65536), (2, 1048576), (3, 1000), (128, 16384)])
@@ -242,3 +263,29 @@ def test_graphed_training_matches_eager_training():
     diffs = [max(float((a - b).abs().max()) for a, b in zip(pa, pb)) for pa, pb in zip(params['eager'], params['graph'])]
     assert agree[0] == 1.0 and agree[1] > 0.9995 and agree[2] > 0.98, (agree, diffs)
     assert diffs[0] <= 2e-6 and diffs[1] <= 2e-5, (agree, diffs)
+
+
+def test_zero_copy_minibatches_match_gathered_minibatches():
+    """train() on zero-copy slab minibatches (Experience.flatten_batch_slabs; observations never gathered) is the same
+    update as train() on the gathered, sorted minibatches of the reference layout: same rollout, parameters after the
+    first update agree to 2e-5 (row order inside a minibatch only changes the summation order)."""
+    from pufferlib_b200 import models
+    from pufferlib_b200.frameworks import cleanrl
+    n, h = 64, 32
+    params, acts, used = {}, {}, {}
+    for zc in (True, False):
+        vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200)
+        torch.manual_seed(0)
+        pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=7).cuda()
+        data = clean_pufferl.create(make_config(n, h, env='breakout', zero_copy_minibatches=zc), vec, pol)
+        clean_pufferl.evaluate(data)
+        acts[zc] = cpu(data.experience.actions).copy()
+        clean_pufferl.train(data)
+        params[zc] = [p.detach().cpu().clone() for p in pol.parameters()]
+        used[zc] = data.experience._slabs is not None
+        assert np.isfinite(data.losses.policy_loss) and np.isfinite(data.losses.explained_variance)
+        clean_pufferl.close(data)
+    assert used[True] and not used[False]
+    assert np.array_equal(acts[True], acts[False])
+    diff = max(float((a - b).abs().max()) for a, b in zip(params[True], params[False]))
+    assert diff <= 2e-5, diff
