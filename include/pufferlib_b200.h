@@ -231,6 +231,32 @@ int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_
                          int32_t hidden_size, float* dpre, float* grads_out, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* -- optimizer step for small policies -------------------------------------------------------------------------------
+ * clip_grad_norm_ + Adam of clean_pufferl.py:240-244 (torch.nn.utils.clip_grad_norm_(params, max_grad_norm);
+ * optimizer.step() with torch.optim.Adam(eps=1e-5)) in ONE single-CTA launch for up to 1 Mi parameters in up to 8
+ * tensors.  Gradients are first multiplied by grad_scale (1/world_size after a sum all-reduce), the global L2 norm
+ * gives coef = min(max_grad_norm / (norm + 1e-6), 1) (max_grad_norm <= 0: no clipping), then per element
+ *   m += (1-b1)(g-m);  v = b2 v + (1-b2) g^2;  step += 1;  p -= lr/(1-b1^step) * m / (sqrt(v)/sqrt(1-b2^step) + eps)
+ * on the optimizer's own state tensors (`step` is torch's per-parameter fp32 device scalar).  lr_dev (nullable)
+ * overrides lr with a device scalar (CUDA-graph replays read the annealed value).  total_norm_out: nullable. */
+typedef struct pb_adam_tensor {
+    float* param;
+    float* exp_avg;
+    float* exp_avg_sq;
+    float* step;
+    const float* grad;
+    int64_t numel;
+} pb_adam_tensor;
+int pb_clip_adam(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
+                 const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out, void* stream);
+
+/* The 8-row head matrix of models.Default (pufferlib/models.py:33-38: decoder rows | value_head row | zero padding),
+ * its bias, and (optionally) the encoder weight rounded to TF32, in one launch: the operands pb_policy_mlp_sample,
+ * pb_mlp_tail_backward and the 8-column head GEMM consume. */
+int pb_pack_heads(const float* w_dec, const float* b_dec, const float* w_val, const float* b_val, int32_t n_act,
+                  int32_t hidden_size, float* w_cat, float* b_cat, const float* w_enc, float* w_enc_tf32,
+                  int64_t enc_numel, void* stream);
+
 /* -- structured observation pack / unpack --------------------------------------------------------
  * Replaces, for N samples at once, `emulate` / `nativize` (pufferlib/extensions.pyx:19-30, 32-49): leaf tensors
  * [N][nbytes[k]] <-> C-aligned records [N][record_bytes] whose layout is `np.dtype(..., align=True)` of the space

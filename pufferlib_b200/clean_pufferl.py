@@ -165,6 +165,150 @@ def fused_ppo_loss_packed(out, n_act, actions, old_logprobs, adv, returns, old_v
     return _FusedPPOLoss.apply(out, None, actions, old_logprobs, adv, returns, old_values, cfg, int(n_act))
 
 
+class _DefaultMLPUpdate:
+    """The minibatch update of clean_pufferl.py:186-244 for models.Default + the fused PPO loss, written out by hand
+    instead of through autograd: with 17k parameters and 524k-row minibatches the update is a fixed chain of seven
+    large kernels, and everything autograd, clip_grad_norm_ and the optimizer add around it (gradient scaling by the
+    upstream 1.0, AccumulateGrad copies, ~12 norm/clip/Adam launches, 6 launches to re-pack the heads, 8 to fold the
+    statistics) is ~120 us of 3-us launches per minibatch.  Chain per minibatch:
+        encoder GEMM (+bias+ReLU epilogue, one per slab) -> 8-column head GEMM -> pb_ppo_loss (loss statistics +
+        analytic dLoss/dOut) -> pb_mlp_tail_backward (dPre, dW_heads, db_heads, db_enc) -> split-K dW_enc GEMM + sum
+        [-> gradient all-reduce over ONE flat buffer when world_size > 1] -> pb_clip_adam -> pb_pack_heads.
+    Same math as the autograd path (tests/test_gpu_experience.py::test_manual_update_matches_autograd_update); the
+    optimizer's own state tensors are updated in place, so state_dict() and optimizer.step() keep working."""
+
+    @staticmethod
+    def eligible(data):
+        config, model, opt = data.config, getattr(data.policy, 'policy', None), data.optimizer
+        if not (data.fused_loss and data.experience.lstm_h is None and bool(getattr(config, 'manual_update', True))):
+            return False
+        if not (hasattr(model, 'forward_packed_slabs') and getattr(model, 'fast_path', False)):
+            return False
+        if config.target_kl is not None or not getattr(data, 'own_optimizer', False):
+            return False
+        n_act, hid = model.decoder.weight.shape
+        if hid != 128 or n_act > 7 or model.encoder.weight.dtype != torch.float32 or not model.encoder.weight.is_cuda:
+            return False
+        g = opt.param_groups[0]
+        if len(opt.param_groups) != 1 or g.get('amsgrad') or g.get('weight_decay') or g.get('maximize'):
+            return False
+        params = [model.encoder.weight, model.encoder.bias, model.decoder.weight, model.decoder.bias,
+                  model.value_head.weight, model.value_head.bias]
+        mine = {id(p) for p in params}
+        return {id(p) for p in g['params']} == mine and sum(p.numel() for p in params) <= (1 << 20)
+
+    def __init__(self, data):
+        model, opt = data.policy.policy, data.optimizer
+        self.model, self.opt = model, opt
+        dev = model.encoder.weight.device
+        self.n_act, self.hid = model.decoder.weight.shape
+        self.features = model.encoder.weight.shape[1]
+        hid, f_, n_act = self.hid, self.features, self.n_act
+        z = dict(dtype=torch.float32, device=dev)
+        # ONE flat gradient buffer: dW_enc | dW_heads (8 x hid) | db_enc | db_heads (8)  (also the all-reduce bucket)
+        self.gflat = torch.zeros(hid * f_ + 8 * hid + hid + 8, **z)
+        self.dw_enc = self.gflat[:hid * f_].view(hid, f_)
+        self.tail = self.gflat[hid * f_:]
+        dw_cat = self.tail[:8 * hid].view(8, hid)
+        db_enc, db_cat = self.tail[8 * hid:9 * hid], self.tail[9 * hid:]
+        self.w_cat, self.b_cat = torch.zeros(8, hid, **z), torch.zeros(8, **z)
+        params = [model.encoder.weight, model.encoder.bias, model.decoder.weight, model.decoder.bias,
+                  model.value_head.weight, model.value_head.bias]
+        grads = [self.dw_enc, db_enc, dw_cat[:n_act], db_cat[:n_act], dw_cat[n_act:n_act + 1], db_cat[n_act:n_act + 1]]
+        self.tensors = (_native.AdamTensor * len(params))()
+        for k, (p, g) in enumerate(zip(params, grads)):
+            st = opt.state[p]
+            if len(st) == 0:          # what torch.optim.Adam._init_group creates for fused / capturable parameters
+                st['step'] = torch.zeros((), **z)
+                st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            assert st['step'].is_cuda and st['step'].dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
+            self.tensors[k] = _native.AdamTensor(p.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
+                                                 st['step'].data_ptr(), g.data_ptr(), p.numel())
+        self._keep = (params, grads)
+        self.rows = 0
+        self.stats = None
+        self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
+                                                            torch.distributed.is_initialized()) else 1
+
+    def _buffers(self, m, n_stats):
+        if self.rows != m:
+            z = dict(dtype=torch.float32, device=self.gflat.device)
+            self.hidden, self.dpre = torch.empty(m, self.hid, **z), torch.empty(m, self.hid, **z)
+            self.out, self.dout = torch.empty(m, 8, **z), torch.empty(m, 8, **z)
+            self.ws = torch.empty(_native.lib().pb_mlp_tail_workspace_bytes(m, self.hid), dtype=torch.uint8,
+                                  device=self.gflat.device)
+            self.part = None
+            self.rows = m
+        if self.stats is None or self.stats.shape[0] != n_stats:
+            self.stats = torch.zeros(n_stats, 8, dtype=torch.float64, device=self.gflat.device)
+
+    def pack_heads(self):
+        m = self.model
+        _native.check(_native.lib().pb_pack_heads(
+            _native.ptr(m.decoder.weight), _native.ptr(m.decoder.bias), _native.ptr(m.value_head.weight),
+            _native.ptr(m.value_head.bias), self.n_act, self.hid, _native.ptr(self.w_cat), _native.ptr(self.b_cat),
+            None, None, 0, _native.stream_ptr()))
+
+    @torch.no_grad()
+    def forward_backward(self, k, n_stats, obs, slab_form, atn, log_probs, adv, ret, val, config):
+        """obs: slab view [G, R, *obs] (slab_form) or [M, *obs]; the rest [M].  Statistics of this minibatch go to
+        row k of self.stats."""
+        x = obs if slab_form else obs.reshape(1, atn.numel(), -1)
+        x = x.flatten(2).float()
+        g_, r_, f_ = x.shape
+        m, hid = g_ * r_, self.hid
+        self._buffers(m, n_stats)
+        model, lib, s = self.model, _native.lib(), _native.stream_ptr()
+        w_enc, b_enc = model.encoder.weight, model.encoder.bias
+        for g in range(g_):
+            torch._addmm_activation(b_enc, x[g], w_enc.t(), use_gelu=False, out=self.hidden[g * r_:(g + 1) * r_])
+        torch.addmm(self.b_cat, self.hidden, self.w_cat.t(), out=self.out)
+        cp = C.c_void_p
+        o_ptr, d_ptr, n_act = self.out.data_ptr(), self.dout.data_ptr(), self.n_act
+        _native.check(lib.pb_ppo_loss(
+            cp(o_ptr), 8, cp(o_ptr + 4 * n_act), 8, _native.ptr(atn.reshape(-1)), _native.ptr(log_probs.reshape(-1)),
+            _native.ptr(adv.reshape(-1)), _native.ptr(ret.reshape(-1)), _native.ptr(val.reshape(-1)), m, n_act,
+            C.c_float(config.clip_coef), int(bool(config.clip_vloss)), C.c_float(config.vf_clip_coef),
+            C.c_float(config.vf_coef), C.c_float(config.ent_coef), cp(d_ptr), 8, cp(d_ptr + 4 * n_act), 8,
+            cp(self.stats.data_ptr() + 64 * k), s))
+        _native.check(lib.pb_mlp_tail_backward(_native.ptr(self.dout), 8, _native.ptr(self.w_cat),
+                                               _native.ptr(self.hidden), m, hid, _native.ptr(self.dpre),
+                                               _native.ptr(self.tail), _native.ptr(self.ws), self.ws.numel(), s))
+        sp = max(1, 64 // g_)
+        while r_ % sp:
+            sp //= 2
+        if self.part is None or self.part.shape != (g_ * sp, hid, f_):
+            self.part = torch.empty(g_ * sp, hid, f_, dtype=torch.float32, device=x.device)
+        for g in range(g_):
+            torch.bmm(self.dpre[g * r_:(g + 1) * r_].view(sp, r_ // sp, hid).transpose(1, 2),
+                      x[g].view(sp, r_ // sp, f_), out=self.part[g * sp:(g + 1) * sp])
+        torch.sum(self.part, 0, out=self.dw_enc)
+
+    def all_reduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.gflat)
+
+    @torch.no_grad()
+    def optimizer_step(self, config):
+        g = self.opt.param_groups[0]
+        lr = g['lr']
+        lr_dev = _native.ptr(lr) if isinstance(lr, torch.Tensor) else None
+        b1, b2 = g['betas']
+        _native.check(_native.lib().pb_clip_adam(
+            self.tensors, len(self.tensors), C.c_float(float(config.max_grad_norm)), C.c_float(1.0 / self.world),
+            C.c_float(0.0 if lr_dev is not None else float(lr)), lr_dev, C.c_float(b1), C.c_float(b2),
+            C.c_float(g['eps']), None, _native.stream_ptr()))
+        self.pack_heads()
+
+    def loss_means(self, n_mb):
+        """[policy, value, entropy, old_kl, kl, clipfrac]: per-minibatch means / n_mb, summed over all minibatches
+        (the accumulation of clean_pufferl.py:249-254)."""
+        tot = self.stats.sum(0)[:6] / (self.rows * n_mb)
+        tot[1] *= 0.5
+        return tot.float()
+
+
 class Experience:
     """Flat tensor storage in arrival order, on the device (reference: clean_pufferl.py:380-482)."""
 
@@ -440,6 +584,7 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
     if getattr(config, 'compile', False):
         raise NotImplementedError('torch.compile is not used on the B200 path (no Triton); set compile=False')
 
+    own_optimizer = optimizer is None
     if optimizer is None:
         # same update rule as the reference's Adam (clean_pufferl.py:54-55); fused=True applies it in one kernel
         graphed = bool(getattr(config, 'cuda_graph', False))
@@ -461,7 +606,7 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         experience=experience, profile=profile, losses=losses, wandb=wandb, global_step=0, epoch=0, stats={},
         msg=msg, last_log_time=0, utilization=None, grad_bucket=grad_bucket,
         io=pufferlib_b200.namespace(h2d=0, d2h=0), graph_state=0, rollout_graph=None, graph_steps=0,
-        graph_launches=0, graph_replays=0, train_graph_state=0, train_graph=None, train_result=None, train_graph_launches=0, train_graph_replays=0, train_segments=None, train_acc=None,
+        graph_launches=0, graph_replays=0, train_graph_state=0, train_graph=None, train_result=None, train_graph_launches=0, train_graph_replays=0, train_segments=None, train_acc=None, own_optimizer=own_optimizer, manual_update=None,
         fused_rows=bool(getattr(policy, 'fused_sample', False)) and hasattr(vecenv, 'bind_rollout')
         and not getattr(vecenv, 'host_buffers', False),
         # one-kernel PPO loss (pb_ppo_loss): needs a wrapper exposing .policy(obs) -> (logits, value), one Discrete head
@@ -635,8 +780,15 @@ def _train_device_part(data, seg=None):
     obs_shape = data.vecenv.single_observation_space.shape
     fused = data.fused_loss and experience.lstm_h is None
     carry = {'lstm_state': None, 'approx_kl': None}
+    manual = None
+    if _DefaultMLPUpdate.eligible(data):
+        if getattr(data, 'manual_update', None) is None:
+            data.manual_update = _DefaultMLPUpdate(data)
+        manual = data.manual_update
+        manual.pack_heads()                      # the parameters may have changed since the last train() (checkpoints)
+    n_stats = config.update_epochs * n_mb
 
-    def forward_backward(mb):
+    def forward_backward(mb, k=0):              # k = epoch * n_mb + mb: the manual path's statistics row
         if slabs:
             sl = experience._slabs
             obs = experience.slab_obs(mb)
@@ -649,6 +801,11 @@ def _train_device_part(data, seg=None):
             val = experience.b_values[mb]
             adv = experience.b_advantages_normalized[mb] if config.norm_adv else experience.b_advantages[mb]
             ret = experience.b_returns[mb]
+
+        if manual is not None:
+            with profile.train_forward:
+                manual.forward_backward(k, n_stats, obs, bool(slabs), atn, log_probs, adv, ret, val, config)
+            return
 
         with profile.train_forward:
             packed = None
@@ -712,17 +869,24 @@ def _train_device_part(data, seg=None):
 
     def optimizer_step():
         with profile.learn:
+            if manual is not None:
+                manual.optimizer_step(config)
+                return
             torch.nn.utils.clip_grad_norm_(data.policy.parameters(), config.max_grad_norm)
             data.optimizer.step()
 
     for epoch in range(config.update_epochs):
         carry['lstm_state'] = None
         for mb in range(n_mb):
-            if seg is not None:
-                seg.run(('fb', mb), lambda: forward_backward(mb))
+            if seg is not None:       # the manual path writes its statistics to a per-(epoch, minibatch) row
+                seg.run(('fb', mb) if manual is None else ('fb', epoch, mb),
+                        lambda: forward_backward(mb, epoch * n_mb + mb))
             else:
-                forward_backward(mb)
-            if data.grad_bucket is not None:
+                forward_backward(mb, epoch * n_mb + mb)
+            if manual is not None:
+                with profile.learn:
+                    manual.all_reduce()                         # ONE NCCL all-reduce (sum; 1/world folded into the step)
+            elif data.grad_bucket is not None:
                 with profile.learn:
                     data.grad_bucket.all_reduce_mean()          # ONE NCCL all-reduce per optimizer step
             if seg is not None:
@@ -739,6 +903,8 @@ def _train_device_part(data, seg=None):
         y_pred, y_true = experience.values, experience.returns
         var_y = y_true.var(unbiased=False)
         ev = 1 - (y_true - y_pred).var(unbiased=False) / var_y
+        if manual is not None:
+            acc = manual.loss_means(n_mb)
         return torch.cat([acc, torch.stack([ev, var_y])])
 
 

@@ -1,0 +1,161 @@
+// optim.cu -- the optimizer step of clean_pufferl.train for small policies, ONE launch (sm_100a).
+//
+// Replaces /root/reference/clean_pufferl.py:240-244
+//     torch.nn.utils.clip_grad_norm_(policy.parameters(), max_grad_norm);  optimizer.step()      (Adam, eps 1e-5)
+// which for the 17k-parameter models.Default is ~12 launches of 3-17 us each per minibatch (multi-tensor L2 norms,
+// cleanup, reciprocal / clamp / multiply, fused Adam): latency, not work.  Here a single 1024-thread CTA makes two
+// passes over the gradients (<= 1 M elements): global L2 norm -> clip coefficient, then the Adam update with the
+// bias corrections of torch.optim.Adam(capturable=True): step counters, moments and parameters are the optimizer's
+// own state tensors, updated in place, so state_dict() and a later fall-back to optimizer.step() stay valid.
+//
+// pb_pack_heads builds the 8-row head matrix (n_act logit rows | value row | zero pad) that the fused forward, the
+// rollout-time policy kernel and pb_mlp_tail_backward consume, plus the TF32-rounded encoder weight, in one launch
+// (the ATen formulation is 2 fills + 4 strided copies + 3 elementwise kernels per optimizer step).
+#include "pb_common.cuh"
+
+namespace {
+
+constexpr int CA_THREADS = 1024;
+constexpr int CA_MAX_TENSORS = 8;
+
+struct AdamArgs {
+    pb_adam_tensor t[CA_MAX_TENSORS];
+    int n;
+    float max_norm, grad_scale, lr;
+    const float* lr_dev;
+    float beta1, beta2, eps;
+    float* total_norm_out;
+};
+
+__global__ void __launch_bounds__(CA_THREADS) k_clip_adam(AdamArgs a) {
+    __shared__ double s_red[CA_THREADS / 32];
+    __shared__ float s_coef;
+    __shared__ float s_step_size[CA_MAX_TENSORS], s_bc2_sqrt[CA_MAX_TENSORS];
+    const int tid = threadIdx.x;
+
+    // ---- pass 1: global L2 norm of the (scaled) gradients
+    float ss = 0.f;
+    for (int k = 0; k < a.n; ++k) {
+        const float* g = a.t[k].grad;
+        for (int64_t i = tid; i < a.t[k].numel; i += CA_THREADS) {
+            const float x = g[i] * a.grad_scale;
+            ss += x * x;
+        }
+    }
+    double d = (double)ss;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if ((tid & 31) == 0) s_red[tid >> 5] = d;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < CA_THREADS / 32; ++w) tot += s_red[w];
+        const float norm = (float)sqrt(tot);
+        // clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to 1 (max_norm <= 0: no clipping)
+        float coef = 1.f;
+        if (a.max_norm > 0.f) coef = fminf(a.max_norm / (norm + 1e-6f), 1.f);
+        s_coef = coef * a.grad_scale;
+        if (a.total_norm_out) *a.total_norm_out = norm;
+    }
+    // ---- step counters and bias corrections (torch.optim.Adam: step += 1 first; double math like ATen's fused kernel)
+    if (tid < a.n) {
+        const float step = *a.t[tid].step + 1.f;
+        const double lr = a.lr_dev ? (double)*a.lr_dev : (double)a.lr;
+        const double bc1 = 1.0 - pow((double)a.beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)a.beta2, (double)step);
+        s_step_size[tid] = (float)(lr / bc1);
+        s_bc2_sqrt[tid] = (float)sqrt(bc2);
+        *a.t[tid].step = step;
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+
+    // ---- pass 2: Adam
+    for (int k = 0; k < a.n; ++k) {
+        const float* g = a.t[k].grad;
+        float* p = a.t[k].param;
+        float* m = a.t[k].exp_avg;
+        float* v = a.t[k].exp_avg_sq;
+        const float step_size = s_step_size[k], bc2_sqrt = s_bc2_sqrt[k];
+        for (int64_t i = tid; i < a.t[k].numel; i += CA_THREADS) {
+            const float x = g[i] * coef;
+            const float mi = m[i] + w1 * (x - m[i]);                  // lerp(exp_avg, grad, 1 - beta1)
+            const float vi = a.beta2 * v[i] + w2 * x * x;
+            const float denom = sqrtf(vi) / bc2_sqrt + a.eps;
+            m[i] = mi;
+            v[i] = vi;
+            p[i] -= step_size * mi / denom;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack_heads(const float* __restrict__ w_dec, const float* __restrict__ b_dec,
+                                                    const float* __restrict__ w_val, const float* __restrict__ b_val,
+                                                    int n_act, int hid, float* __restrict__ w_cat,
+                                                    float* __restrict__ b_cat, const float* __restrict__ w_enc,
+                                                    float* __restrict__ w_enc_tf32, int64_t enc_numel) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = i; j < 8 * (int64_t)hid; j += stride) {
+        const int r = (int)(j / hid), c = (int)(j % hid);
+        w_cat[j] = r < n_act ? w_dec[(int64_t)r * hid + c] : (r == n_act ? w_val[c] : 0.f);
+    }
+    if (i < 8) b_cat[i] = i < n_act ? b_dec[i] : (i == n_act ? b_val[0] : 0.f);
+    if (w_enc_tf32)
+        for (int64_t j = i; j < enc_numel; j += stride) {   // cvt.rna.tf32.f32: round to nearest, ties away from zero
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w_enc[j]));
+            w_enc_tf32[j] = __uint_as_float(r);
+        }
+}
+
+}  // namespace
+
+extern "C" int pb_clip_adam(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale,
+                            float lr, const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
+                            void* stream) {
+    PB_REQUIRE(tensors && n_tensors >= 1 && n_tensors <= CA_MAX_TENSORS, PB_ERR_INVALID,
+               "pb_clip_adam: 1..%d tensors", CA_MAX_TENSORS);
+    AdamArgs a{};
+    int64_t total = 0;
+    for (int k = 0; k < n_tensors; ++k) {
+        const pb_adam_tensor& t = tensors[k];
+        PB_REQUIRE(t.param && t.exp_avg && t.exp_avg_sq && t.step && t.grad && t.numel >= 1, PB_ERR_INVALID,
+                   "pb_clip_adam: tensor %d has a null pointer or no elements", k);
+        a.t[k] = t;
+        total += t.numel;
+    }
+    PB_REQUIRE(total <= (1 << 20), PB_ERR_UNSUPPORTED,
+               "pb_clip_adam: single-CTA kernel for small policies (%lld parameters > 1 Mi)", (long long)total);
+    PB_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && grad_scale > 0.f,
+               PB_ERR_INVALID, "pb_clip_adam: bad hyper-parameters");
+    a.n = n_tensors;
+    a.max_norm = max_grad_norm;
+    a.grad_scale = grad_scale;
+    a.lr = lr;
+    a.lr_dev = lr_dev;
+    a.beta1 = beta1;
+    a.beta2 = beta2;
+    a.eps = eps;
+    a.total_norm_out = total_norm_out;
+    k_clip_adam<<<1, CA_THREADS, 0, (cudaStream_t)stream>>>(a);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+}
+
+extern "C" int pb_pack_heads(const float* w_dec, const float* b_dec, const float* w_val, const float* b_val,
+                             int32_t n_act, int32_t hidden_size, float* w_cat, float* b_cat, const float* w_enc,
+                             float* w_enc_tf32, int64_t enc_numel, void* stream) {
+    PB_REQUIRE(w_dec && b_dec && w_val && b_val && w_cat && b_cat, PB_ERR_INVALID, "pb_pack_heads: null pointer");
+    PB_REQUIRE(n_act >= 1 && n_act <= 7 && hidden_size >= 1, PB_ERR_INVALID, "pb_pack_heads: n_act in [1,7], hidden >= 1");
+    PB_REQUIRE(!w_enc_tf32 || (w_enc && enc_numel >= 1), PB_ERR_INVALID, "pb_pack_heads: w_enc_tf32 needs w_enc");
+    const int64_t work = w_enc_tf32 ? (enc_numel > 8 * (int64_t)hidden_size ? enc_numel : 8 * (int64_t)hidden_size)
+                                    : 8 * (int64_t)hidden_size;
+    int64_t blocks = pb_ceil_div(work, 256);
+    if (blocks > 4 * PB_NUM_SMS) blocks = 4 * PB_NUM_SMS;
+    k_pack_heads<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(w_dec, b_dec, w_val, b_val, n_act, hidden_size, w_cat,
+                                                                     b_cat, w_enc, w_enc_tf32, enc_numel);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+}

@@ -34,11 +34,6 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void cp16(float* dst_smem, const float* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
-                 : "memory");
-}
-
 struct PolicyParams {
     const float* obs; int64_t obs_stride;      // [M][128] fp32
     const float* w_enc; const float* b_enc;    // [128][128], [128]
