@@ -186,6 +186,10 @@ class _DefaultMLPUpdate:
             return False
         if config.target_kl is not None or not getattr(data, 'own_optimizer', False):
             return False
+        world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
+                                                        torch.distributed.is_initialized()) else 1
+        if world > 1 and not bool(getattr(config, 'manual_update_multi_gpu', False)):
+            return False          # round 1: measured on one GPU only; ranks > 1 keep the autograd + GradBucket path
         n_act, hid = model.decoder.weight.shape
         if hid != 128 or n_act > 7 or model.encoder.weight.dtype != torch.float32 or not model.encoder.weight.is_cuda:
             return False
