@@ -165,6 +165,28 @@ def fused_ppo_loss_packed(out, n_act, actions, old_logprobs, adv, returns, old_v
     return _FusedPPOLoss.apply(out, None, actions, old_logprobs, adv, returns, old_values, cfg, int(n_act))
 
 
+def slab_layout(num_envs, horizon, num_minibatches, bptt_horizon):
+    """(G, R) of the zero-copy minibatch form, or None when the reference minibatches are not unions of whole time
+    windows.  Minibatch mb of clean_pufferl.py:452-482 holds the bptt segments s = r*n_mb + mb of the (env, step)
+    sorted batch; segment s = e*S + k (S = horizon / bptt segments per env) lies in minibatch (e*S + k) % n_mb, which is
+    k % n_mb for every env iff S % n_mb == 0.  Then minibatch mb = time windows k = mb, mb + n_mb, ... of ALL envs =
+    G = S / n_mb slabs of R = bptt * num_envs consecutive rows of the time-major rollout buffer."""
+    if horizon % bptt_horizon != 0:
+        return None
+    s_per_env = horizon // bptt_horizon
+    if s_per_env % num_minibatches != 0:
+        return None
+    return s_per_env // num_minibatches, bptt_horizon * num_envs
+
+
+def slab_row_index(num_envs, horizon, num_minibatches, bptt_horizon):
+    """[n_mb, G*R] arrival-order row of every slab-major minibatch position (numpy; for tests and documentation --
+    the device path never materialises it): position (g, j, e) of minibatch mb is row ((g*n_mb + mb)*bptt + j)*N + e."""
+    g_, r_ = slab_layout(num_envs, horizon, num_minibatches, bptt_horizon)
+    rows = np.arange(num_envs * horizon, dtype=np.int64).reshape(g_, num_minibatches, r_)
+    return rows.transpose(1, 0, 2).reshape(num_minibatches, g_ * r_)
+
+
 class _DefaultMLPUpdate:
     """The minibatch update of clean_pufferl.py:186-244 for models.Default + the fused PPO loss, written out by hand
     instead of through autograd: with 17k parameters and 524k-row minibatches the update is a fixed chain of seven
@@ -506,9 +528,10 @@ class Experience:
         summation order.  Returns False (nothing done) when the shape condition does not hold."""
         adv = self.advantages if advantages is None else advantages
         n, h, nm, bptt = self.num_envs, self.horizon, self.num_minibatches, self.bptt_horizon
-        if h % bptt != 0 or (h // bptt) % nm != 0:
+        layout = slab_layout(n, h, nm, bptt)
+        if layout is None:
             return False
-        g_, r_ = (h // bptt) // nm, bptt * n
+        g_, r_ = layout
         if self._slabs is None:
             z = dict(device=self.device)
             mb = self.minibatch_size
