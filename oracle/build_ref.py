@@ -7,7 +7,6 @@ the snapshot).  Nothing is copied into the repo history.  ``load()`` imports the
 import glob
 import importlib.util
 import os
-import shutil
 import subprocess
 import sys
 import sysconfig

@@ -18,7 +18,6 @@ The policy stays a torch ``nn.Module`` with the reference's call convention
 (``policy(obs) -> actions, logprob, entropy, value``; ``policy(obs, action=a)`` in train).
 """
 import ctypes as C
-import os
 import random
 import time
 from collections import defaultdict

@@ -17,7 +17,6 @@ import numpy as np
 import torch
 
 from pufferlib_b200 import _native, spaces
-from pufferlib_b200.namespace import namespace
 
 numpy_to_torch_dtype_dict = {
     np.dtype('float64'): torch.float64, np.dtype('float32'): torch.float32, np.dtype('float16'): torch.float16,

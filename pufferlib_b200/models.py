@@ -59,7 +59,6 @@ class _DefaultMLPFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        import ctypes as C
         from pufferlib_b200 import _native
         x, hidden, w_cat = ctx.saved_tensors
         n_act, (m, hid) = ctx.n_act, hidden.shape

@@ -1,7 +1,5 @@
 """Experience (store -> GAE -> flatten_batch -> adv-norm) on the device vs the reference's own outputs
 (tests/golden/experience_*.npz) and the numpy oracle; plus the standalone train-prep kernels at larger sizes."""
-import ctypes as C
-
 import numpy as np
 import pytest
 import torch
