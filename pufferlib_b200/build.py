@@ -58,5 +58,23 @@ def build(force=False, verbose=False):
     return SO
 
 
+EXP_SO = os.path.join(HERE, 'libpuffer_b200_exp.so')
+
+
+def build_experimental(force=False, verbose=False):
+    """csrc/experimental/*.cu -> libpuffer_b200_exp.so: round-2 groundwork (tcgen05 kernels not yet validated on
+    hardware).  Nothing in the product path loads it; tests/experimental/ holds the hardware checks."""
+    srcs = sorted(glob.glob(os.path.join(CSRC, 'experimental', '*.cu')))
+    deps = srcs + glob.glob(os.path.join(CSRC, '*.cuh'))
+    if not force and os.path.exists(EXP_SO) and all(os.path.getmtime(EXP_SO) >= os.path.getmtime(d) for d in deps):
+        return EXP_SO
+    cmd = [NVCC] + ARCH_FLAGS + COMMON + (['-Xptxas', '-v'] if verbose else []) + ['-shared', '-o', EXP_SO] + srcs + \
+        ['-lcudart']
+    subprocess.check_call(cmd)
+    return EXP_SO
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    if '--experimental' in sys.argv:
+        print(build_experimental(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
