@@ -653,7 +653,9 @@ def _rollout_loop(data, infos):
             o, r, d, t, info, env_id, mask = vecenv.recv()
 
         with profile.eval_misc:
-            data.global_step += len(env_id) if on_device else int(sum(mask))
+            # sum(mask) of clean_pufferl.py:90; count_nonzero instead of the Python-level sum over a numpy array, which
+            # costs 1 ms per env step at N = 16384
+            data.global_step += len(env_id) if on_device else int(np.count_nonzero(mask))
             if on_device:
                 o_device = o
             else:   # host buffers: the reference's H2D of the observation batch (clean_pufferl.py:92-95)
