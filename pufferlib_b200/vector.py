@@ -289,8 +289,6 @@ class B200:
                 obs, rewards = x.obs[lo:hi], x.rewards[lo:hi]
             else:
                 obs, rewards = b.observations, b.rewards
-            infos = self._collect_infos() if self.exact_infos else []
-            self.infos = infos
             if self.host_buffers:
                 h = self._host
                 h.observations.copy_(obs, non_blocking=True)
@@ -301,7 +299,12 @@ class B200:
                 self.d2h_bytes += (h.observations.numel() * h.observations.element_size()
                                    + 4 * self.num_agents + 2 * self.num_agents)
                 hn = self._host_np
+                # the terminal flags are on the host already: no second D2H for the info dicts
+                infos = self._collect_infos(hn.terminals) if self.exact_infos else []
+                self.infos = infos
                 return (hn.observations, hn.rewards, hn.terminals, hn.truncations, infos, self.agent_ids, hn.masks)
+            infos = self._collect_infos() if self.exact_infos else []
+            self.infos = infos
         return (obs, rewards, b.terminals, b.truncations, infos, self.agent_ids, b.masks)
 
     def pinned(self, array):
@@ -312,11 +315,13 @@ class B200:
                 return self._host[k]
         return torch.as_tensor(array)
 
-    def _collect_infos(self):
+    def _collect_infos(self, term=None):
         """Per-env info dicts for rows that just ended an episode (EpisodeStats, postprocess.py:36-52), in env
-        order like Serial.send (vector.py:153-154).  Costs one D2H of the terminal flags per recv."""
-        term = self.buf.terminals.cpu().numpy()
-        self.d2h_bytes += term.nbytes
+        order like Serial.send (vector.py:153-154).  Costs one D2H of the terminal flags per recv unless the caller
+        already has them on the host (``term``)."""
+        if term is None:
+            term = self.buf.terminals.cpu().numpy()
+            self.d2h_bytes += term.nbytes
         idx = np.nonzero(term)[0]
         if len(idx) == 0:
             return []
@@ -324,9 +329,14 @@ class B200:
         p_ret, p_len, p_score = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _native.check(lib.pb_env_episode_rows(self._handle, C.byref(p_ret), C.byref(p_len), C.byref(p_score)))
         n = self.num_agents
-        ret = _from_device(p_ret.value, n, np.float64)
-        length = _from_device(p_len.value, n, np.int32)
-        score = _from_device(p_score.value, n, np.float32)
+        # the three per-env arrays through ONE staging tensor and ONE device->host copy (one sync instead of three)
+        stage = torch.empty(16 * n, dtype=torch.uint8, device=self.buf.terminals.device)
+        base, s_ = stage.data_ptr(), _native.stream_ptr()
+        for src, off, nbytes in ((p_ret.value, 0, 8 * n), (p_len.value, 8 * n, 4 * n), (p_score.value, 12 * n, 4 * n)):
+            _native.check(lib.pb_copy_rows(C.c_void_p(src), nbytes, C.c_void_p(base + off), nbytes, nbytes, 1, s_))
+        host = stage.cpu().numpy()
+        ret, length, score = host[:8 * n].view(np.float64), host[8 * n:12 * n].view(np.int32), \
+            host[12 * n:].view(np.float32)
         self.d2h_bytes += n * 16
         return [{'episode_return': float(ret[i]), 'episode_length': int(length[i]), 'score': float(score[i])}
                 for i in idx]
@@ -470,15 +480,6 @@ class B200Pool:
     def close(self):
         for v in self.groups:
             v.close()
-
-
-def _from_device(addr, n, dtype):
-    """Copy n elements of a raw device array to a numpy array (cudaMemcpy through a torch byte tensor)."""
-    nbytes = n * np.dtype(dtype).itemsize
-    out = torch.empty(nbytes, dtype=torch.uint8, device='cuda')
-    _native.check(_native.lib().pb_copy_rows(C.c_void_p(addr), nbytes, _native.ptr(out), nbytes, nbytes, 1,
-                                             _native.stream_ptr()))
-    return out.cpu().numpy().view(dtype)
 
 
 def make(env_creator_or_creators, env_args=None, env_kwargs=None, backend=B200, num_envs=1, **kwargs):
