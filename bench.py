@@ -352,8 +352,11 @@ def run_b200(args):
     # ---- e2e: same step through the public API with host buffers
     e2e = None
     if not args.no_e2e:
-        hdata, _ = make_b200(args, rank, world, host_buffers=True, cuda_graph=False)
-        cp.evaluate(hdata); cp.train(hdata)
+        # host buffers: the rollout loop talks to the host every env step (no rollout graph); the update has no host
+        # interaction, so it is still captured (first train() eager, second captures: two warm-up steps)
+        hdata, _ = make_b200(args, rank, world, host_buffers=True, cuda_graph=not args.no_graph)
+        for _ in range(2):
+            cp.evaluate(hdata); cp.train(hdata)
         hv = hdata.vecenv
         io0 = (hdata.io.h2d + hv.h2d_bytes, hdata.io.d2h + hv.d2h_bytes)
         k_e2e = max(2, min(args.steps, 5))
