@@ -251,10 +251,23 @@ class _DefaultMLPUpdate:
             self.tensors[k] = _native.AdamTensor(p.data_ptr(), st['exp_avg'].data_ptr(), st['exp_avg_sq'].data_ptr(),
                                                  st['step'].data_ptr(), g.data_ptr(), p.numel())
         self._keep = (params, grads)
+        self._state_ptrs = self._current_state_ptrs()
         self.rows = 0
         self.stats = None
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
                                                             torch.distributed.is_initialized()) else 1
+
+    def _current_state_ptrs(self):
+        out = []
+        for p in self._keep[0]:
+            st = self.opt.state.get(p, {})
+            out.append(tuple(st[k].data_ptr() if k in st else 0 for k in ('exp_avg', 'exp_avg_sq', 'step')) + (p.data_ptr(),))
+        return out
+
+    def stale(self):
+        """True when the optimizer's state tensors are no longer the ones whose addresses pb_clip_adam was given
+        (optimizer.load_state_dict() replaces them): the caller rebuilds the update object."""
+        return self._current_state_ptrs() != self._state_ptrs
 
     def _buffers(self, m, n_stats):
         if self.rows != m:
@@ -443,6 +456,13 @@ class Experience:
         n = value.shape[0]
         if self.num_envs is None:            # total agents (create() sets it; pool mode stores batch_size-row chunks)
             self.num_envs = n
+        # the arithmetic sort needs arange-ordered, fully valid blocks (what the B200 backends produce); anything else
+        # would be trained on in the wrong order, so refuse it (the reference filters by mask and sorts by (env_id, step))
+        if env_id is not None and (len(env_id) != n or int(env_id[0]) != self.ptr % self.num_envs
+                                   or int(env_id[-1]) - int(env_id[0]) != n - 1):
+            raise APIUsageError('store(): env_id must be the contiguous block of agents expected at this rollout position')
+        if isinstance(mask, np.ndarray) and not mask.all():
+            raise APIUsageError('store(): padded agents (mask False) are not supported on the device path')
         if self.batch_size % n != 0 or self.num_envs % n != 0:
             raise APIUsageError('batch_size / num_envs must be multiples of the agents per store()')
         ptr, end = self.ptr, self.ptr + n
@@ -613,7 +633,7 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
     own_optimizer = optimizer is None
     if optimizer is None:
         # same update rule as the reference's Adam (clean_pufferl.py:54-55); fused=True applies it in one kernel
-        graphed = bool(getattr(config, 'cuda_graph', False))
+        graphed = any(bool(getattr(config, k, False)) for k in ('cuda_graph', 'cuda_graph_train', 'cuda_graph_rollout'))
         lr = torch.tensor(float(config.learning_rate), device=config.device) if graphed else config.learning_rate
         optimizer = torch.optim.Adam(policy.parameters(), lr=lr, eps=1e-5, fused=True, capturable=graphed)
 
@@ -666,10 +686,16 @@ def _rollout_loop(data, infos):
 
         with profile.eval_forward, torch.no_grad():
             if experience.lstm_h is not None:
-                # clean_pufferl.py:100-105 with env_id == every env: the state tensors are updated in place
-                actions, logprob, _, value, (h, c) = policy(o_device, (experience.lstm_h, experience.lstm_c))
-                experience.lstm_h.copy_(h)
-                experience.lstm_c.copy_(c)
+                # clean_pufferl.py:100-105: h = lstm_h[:, env_id] -> policy -> lstm_h[:, env_id] = h.  env_id is a
+                # contiguous range here (every env, or one pool group): slices instead of index gathers
+                lo, hi = int(env_id[0]), int(env_id[0]) + len(env_id)
+                if lo == 0 and hi == experience.lstm_h.shape[1]:
+                    h_in, c_in = experience.lstm_h, experience.lstm_c
+                else:
+                    h_in, c_in = experience.lstm_h[:, lo:hi].contiguous(), experience.lstm_c[:, lo:hi].contiguous()
+                actions, logprob, _, value, (h, c) = policy(o_device, (h_in, c_in))
+                experience.lstm_h[:, lo:hi].copy_(h)
+                experience.lstm_c[:, lo:hi].copy_(c)
             elif data.fused_rows and experience.num_envs is not None:
                 actions, logprob, _, value = policy(o_device, out=experience.rows())
             else:
@@ -783,6 +809,7 @@ def _train_device_part(data, seg=None):
     the gradient all-reduce (multi-GPU)."""
     config, profile, experience = data.config, data.profile, data.experience
     device = experience.device
+    _invalidate_policy_cache(data)     # nothing cached by the rollout (eager or captured) may leak into an update graph
 
     # zero-copy minibatches (Experience.flatten_batch_slabs): order-free loss only, i.e. the fused non-LSTM path
     model = getattr(data.policy, 'policy', None)
@@ -810,7 +837,7 @@ def _train_device_part(data, seg=None):
     carry = {'lstm_state': None, 'approx_kl': None}
     manual = None
     if _DefaultMLPUpdate.eligible(data):
-        if getattr(data, 'manual_update', None) is None:
+        if getattr(data, 'manual_update', None) is None or data.manual_update.stale():
             data.manual_update = _DefaultMLPUpdate(data)
         manual = data.manual_update
         manual.pack_heads()                      # the parameters may have changed since the last train() (checkpoints)
@@ -943,6 +970,12 @@ def train(data):
     config, profile, experience = data.config, data.profile, data.experience
     data.losses = make_losses()
     losses = data.losses
+    if getattr(data, 'manual_update', None) is not None and data.manual_update.stale():
+        # optimizer.load_state_dict() (try_load_checkpoint) replaced the Adam state tensors: the hand-written update
+        # and any captured graph hold the old addresses -- rebuild both (eager call now, re-capture on the next one)
+        data.manual_update = None
+        if data.train_graph_state > 0:
+            data.train_graph, data.train_segments, data.train_graph_state = None, None, 0
     # multi-GPU: capturing the NCCL all-reduce inside one big graph hung on this stack (torch 2.11 / NCCL 2.28); ranks > 1
     # use per-segment graphs around an ordinary all-reduce call instead (see `segmented`)
     want_graph = bool(getattr(config, 'cuda_graph_train', getattr(config, 'cuda_graph', False)))
@@ -996,6 +1029,49 @@ def train(data):
         losses.explained_variance = float('nan') if host[7] == 0 else float(host[6])
         data.epoch += 1
         profile.update(data)
+        interval = getattr(config, 'checkpoint_interval', None)        # clean_pufferl.py:288-290
+        if interval and hasattr(config, 'data_dir') and \
+                (data.epoch % interval == 0 or data.global_step >= config.total_timesteps):
+            save_checkpoint(data)
+            data.msg = f'Checkpoint saved at update {data.epoch}'
+
+
+def save_checkpoint(data):
+    """clean_pufferl.py:509-530: model_<epoch>.pt (the whole module) + trainer_state.pt (optimizer state, counters)."""
+    import os
+    config = data.config
+    path = os.path.join(config.data_dir, config.exp_id)
+    os.makedirs(path, exist_ok=True)
+    model_name = f'model_{data.epoch:06d}.pt'
+    model_path = os.path.join(path, model_name)
+    torch.save(data.uncompiled_policy, model_path)
+    state = {'optimizer_state_dict': data.optimizer.state_dict(), 'global_step': data.global_step,
+             'agent_step': data.global_step, 'update': data.epoch, 'model_name': model_name, 'exp_id': config.exp_id}
+    state_path = os.path.join(path, 'trainer_state.pt')
+    torch.save(state, state_path + '.tmp')
+    os.rename(state_path + '.tmp', state_path)
+    return model_path
+
+
+def try_load_checkpoint(data):
+    """clean_pufferl.py:532-546.  The parameters are loaded IN PLACE (their addresses are captured in CUDA graphs);
+    the optimizer state tensors are replaced by load_state_dict, which train() detects (_DefaultMLPUpdate.stale)."""
+    import os
+    config = data.config
+    path = os.path.join(config.data_dir, config.exp_id)
+    if not os.path.exists(path):
+        print('No checkpoints found. Assuming new experiment')
+        return
+    resume_state = torch.load(os.path.join(path, 'trainer_state.pt'), weights_only=False)
+    data.global_step = resume_state['global_step']
+    data.epoch = resume_state['update']
+    model_path = os.path.join(path, resume_state['model_name'])
+    data.uncompiled_policy.load_state_dict(torch.load(model_path, weights_only=False).state_dict())
+    data.optimizer.load_state_dict(resume_state['optimizer_state_dict'])
+    _invalidate_policy_cache(data)
+    if data.train_graph_state > 0:      # captured updates hold the old optimizer-state addresses: capture again
+        data.train_graph, data.train_segments, data.train_graph_state = None, None, 0
+    print(f'Loaded checkpoint {resume_state["model_name"]}')
 
 
 def close(data):

@@ -39,7 +39,8 @@ class _DefaultMLPFunction(torch.autograd.Function):
         # the 8-row head matrix: rebuilt on every forward that records gradients (the parameters change every optimizer
         # step, and fused optimizers do NOT bump tensor._version, so it cannot be cached across steps); under no_grad
         # (the rollout: 128 forwards with frozen parameters) it is built once and reused until invalidate_cache()
-        use_cache = not torch.is_grad_enabled()
+        # (torch.is_grad_enabled() is always False inside Function.forward: decide from the inputs that need gradients)
+        use_cache = not any(ctx.needs_input_grad[1:7])
         key = (w_dec.data_ptr(), torch.cuda.is_current_stream_capturing())
         if use_cache and cache.get('key') == key:
             w_cat, b_cat = cache['w'], cache['b']

@@ -78,6 +78,14 @@ class Dict:
     """Ordered mapping of sub-spaces (gymnasium.spaces.Dict surface used by emulation.dtype_from_space)."""
 
     def __init__(self, spaces=None, **kw):
+        # gymnasium.spaces.Dict sorts the keys of a plain dict and keeps the order of an OrderedDict; the structured
+        # dtype layout (emulation.dtype_from_space) follows this order
+        from collections import OrderedDict
+        if isinstance(spaces, dict) and not isinstance(spaces, OrderedDict):
+            try:
+                spaces = dict(sorted(spaces.items()))
+            except TypeError:
+                pass
         self.spaces = dict(spaces or {}, **kw)
 
     def items(self):
