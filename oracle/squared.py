@@ -34,8 +34,9 @@ def reward_table(distance_to_target):
 
 
 class SquaredSerial:
-    def __init__(self, num_envs, distance_to_target=3, num_targets=1):
+    def __init__(self, num_envs, distance_to_target=3, num_targets=1, index_offset=0):
         assert num_targets == 1, 'oracle restates the num_targets=1 path only'
+        self.index_offset = index_offset      # global index of env 0 (a Multiprocessing worker's slice of the seeds)
         self.n = num_envs
         self.d = distance_to_target
         self.g = 2 * distance_to_target + 1
@@ -79,7 +80,7 @@ class SquaredSerial:
     def async_reset(self, seed=42):
         self.infos = []
         for i in range(self.n):
-            self._reset_env(i, seed + i)                          # vector.py:639-641
+            self._reset_env(i, seed + self.index_offset + i)      # vector.py:639-641 (424-428: a worker gets its slice)
 
     def _step_env(self, i, action):
         d = self.d
@@ -127,3 +128,32 @@ class SquaredSerial:
     def recv(self):
         return (self.observations, self.rewards, self.terminals, self.truncations,
                 self.infos, self.agent_ids, self.masks)
+
+
+class SquaredMultiprocessing:
+    """``vector.Multiprocessing`` (synchronous mode, batch_size == num_envs) over ``Squared``: every worker process is a
+    ``Serial`` over its own envs with its OWN process-global MT19937 (vector.py:168-190, seeds sliced per worker at
+    :424-428), so auto-resets draw from the stream left by the worker's last seeded env, in env order inside the worker.
+    recv() returns the workers' rows in worker order (vector.py:360-369); infos likewise (:397-401)."""
+
+    def __init__(self, num_envs, num_workers, distance_to_target=3):
+        assert num_envs % num_workers == 0
+        e = num_envs // num_workers
+        self.workers = [SquaredSerial(e, distance_to_target, index_offset=w * e) for w in range(num_workers)]
+        self.n, self.e = num_envs, e
+        self.agent_ids = np.arange(num_envs)
+
+    def async_reset(self, seed=42):
+        for w in self.workers:
+            w.async_reset(seed)
+
+    def send(self, actions):
+        actions = np.asarray(actions)
+        for k, w in enumerate(self.workers):
+            w.send(actions[k * self.e:(k + 1) * self.e])
+
+    def recv(self):
+        cat = lambda name: np.concatenate([getattr(w, name) for w in self.workers])   # noqa: E731
+        infos = [i for w in self.workers for i in w.infos]
+        return (cat('observations'), cat('rewards'), cat('terminals'), cat('truncations'), infos, self.agent_ids,
+                cat('masks'))

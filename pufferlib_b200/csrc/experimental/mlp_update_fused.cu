@@ -1,0 +1,669 @@
+// mlp_update_fused.cu -- the whole minibatch forward + PPO loss + backward of models.Default in ONE persistent
+// tcgen05 kernel: the observations are read from HBM once, `hidden` / `dPre` never leave the SM.
+//
+// Replaces, per minibatch of clean_pufferl.train (/root/reference/clean_pufferl.py:186-244; policy =
+// /root/reference/pufferlib/models.py:12-62 with 128 input features, 128 hidden units, <= 7 actions), the chain
+//     hidden = relu(x W_enc^T + b_enc)            (cuBLAS GEMM, writes 268 MB at M = 524288)
+//     out    = hidden W_heads^T + b_heads         (cuBLAS GEMM, reads hidden)
+//     pb_ppo_loss(out) -> dOut, statistics        (csrc/ppo_loss.cu)
+//     pb_mlp_tail_backward(dOut, hidden) -> dPre, dW_heads, db_enc, db_heads      (csrc/mlp_tail.cu, reads hidden, writes dPre)
+//     dW_enc = dPre^T x                           (split-K cuBLAS GEMM, reads dPre and x)
+// which streams `hidden` / `dPre` through HBM five times (1.9 GB, ~350 us per minibatch).  Here the algorithmic traffic is
+// x once (268 MB) + 24 B of per-row scalars.
+//
+// CTA = 192 threads, one per SM, persistent over 128-row tiles:
+//   warp 0      TMA producer: W_enc once, then x tiles (4 boxes of [128 rows][32 floats], SWIZZLE_128B) into a 2-stage ring
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue:
+//                 forward   h[128 rows][128 hid]  = x . W_enc^T       16 x (M128 N128 K8) kind::tf32, both operands K-major
+//                 backward  dW^T[128 feat][32 hid chunk] += x^T . dPre_chunk   16 x (M128 N32 K8), both operands MN-major:
+//                           A = the SAME x tile bytes the forward used (a K-major SW128 tile read as MN-major:
+//                           M = feature, K = row), B = the dPre chunk the epilogue warps wrote to shared memory
+//   warps 2..5  epilogue, thread = row (TMEM lane): tcgen05.ld h -> bias + ReLU -> heads (W_heads as constant-bank FFMA
+//               operands) -> the pb_ppo_loss row math -> dOut -> per 32-column chunk: dPre = (dOut . W_heads) * (h > 0)
+//               -> swizzled MN-major chunk in shared memory (generic stores + fence.proxy.async) for the dW UMMA;
+//               dW_heads by mma.sync on the warp's own rows (relu(h) chunk staged through the same buffer), db_enc by
+//               column sums of the staged dPre chunk, db_heads / statistics in registers.
+// TMEM: columns [0,256) two forward accumulators, [256,384) dW^T accumulator (lives across all tiles of the CTA).
+// Per-CTA partial results go to a workspace; k_update_reduce sums them deterministically into the flat gradient
+// buffer [dW_enc (hid x feat) | dW_heads (8 x hid) | db_enc | db_heads] of clean_pufferl._DefaultMLPUpdate.
+//
+// Descriptor encodings were validated on hardware with csrc/experimental/umma_probe.cu (tests/experimental/
+// check_umma_probe.py).  Every mbarrier wait is bounded (tma.cuh: __trap instead of a hang).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../tma.cuh"
+
+namespace {
+
+char g_err3[512] = "";
+void set_err3(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err3, sizeof(g_err3), fmt, ap);
+    va_end(ap);
+}
+
+constexpr int TILE_M = 128, HID = 128, FEAT = 128, NO = 8;
+constexpr int KBLK = 32;                               // floats per 128-byte swizzle row
+constexpr int KBLK_BYTES = TILE_M * KBLK * 4;          // 16 KiB: one [128 rows][32 floats] box
+constexpr int TILE_BYTES = 4 * KBLK_BYTES;             // 64 KiB
+constexpr int NCHUNK = 4, CHUNK_COLS = 32;
+constexpr int CHUNK_BYTES = TILE_M * CHUNK_COLS * 4;   // 16 KiB: [128 rows][32 hid] MN-major (N contiguous)
+constexpr int NBUF = 2;                                // dPre chunk buffers
+constexpr int SMEM_W = 0, SMEM_X = TILE_BYTES, SMEM_CH = 3 * TILE_BYTES;
+constexpr int SMEM_BAR = SMEM_CH + NBUF * CHUNK_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_DW = 256;                           // first column of the dW^T accumulator
+constexpr int TAIL = NO * HID + HID + NO;              // dW_heads | db_enc | db_heads
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+
+// W_heads [8][128], b_enc [128], b_heads [8]: uniform per warp at every use -> constant-bank operands of the FFMAs
+__constant__ float c_wh[NO * HID];
+__constant__ float c_benc[HID];
+__constant__ float c_bh[NO];
+
+struct FusedParams {
+    const int64_t* actions;
+    const float* old_logprobs;
+    const float* adv;
+    const float* returns;
+    const float* old_values;
+    int64_t m;                 // rows of the minibatch (all slabs): the 1/M of the loss means
+    int64_t slab_rows;         // R
+    int64_t slab_stride_rows;  // distance between slab starts, in rows of the x tensor map
+    int tiles_per_slab, n_tiles;
+    int n_act;
+    float clip, vclip, vf_coef, ent_coef;
+    int clip_vloss;
+    float* part_dw;            // [grid][FEAT][HID]
+    float* part_tail;          // [grid][TAIL]
+    double* stats;             // [8]
+    float* dbg_hidden;         // nullable [m][128]
+    float* dbg_dpre;           // nullable [m][128]
+    float* dbg_dout;           // nullable [m][8]
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// SWIZZLE_128B descriptors (PTX ISA tcgen05 shared-memory descriptor; cute/arch/mma_sm100_desc.hpp): start>>4 | LBO>>4 <<16
+// | SBO>>4 <<32 | version 1 <<46 | layout 2 <<61.  K-major: LBO unused (1), SBO = 1024 B between 8-row groups.
+// MN-major: LBO = distance between 32-element MN groups, SBO = 1024 B between 8-k groups.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fmt F32 (1<<4) | A TF32 (2<<7) | B TF32 (2<<10) | A major bit 15 | B major bit 16 | N>>3 <<17 | M>>4 <<24
+constexpr uint32_t IDESC_FWD = (1u << 4) | (2u << 7) | (2u << 10) | ((HID >> 3) << 17) | ((TILE_M >> 4) << 24);
+constexpr uint32_t IDESC_DW = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((CHUNK_COLS >> 3) << 17) |
+                              ((FEAT >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+    uint32_t u[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+          "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+          "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float& c0, float& c1, float& z0, float& z1, const uint32_t (&a)[2], uint32_t b0,
+                                         uint32_t b1) {
+    // m16n8k8: rows 8..15 of A are zero (a1 = a3 = 0), their accumulators (z0, z1) are shared dummies
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c0), "+f"(c1), "+f"(z0), "+f"(z1)
+                 : "r"(a[0]), "r"(0u), "r"(a[1]), "r"(0u), "r"(b0), "r"(b1));
+}
+
+// The row math of k_ppo_loss<PACKED> (csrc/ppo_loss.cu; clean_pufferl.py:202-238 + frameworks/cleanrl.py:25-47):
+// z[0..n_act) logits, z[n_act] value -> dOut[8] (already scaled by 1/M) and the six per-row statistics.
+struct RowStats { float pg, v, ent, okl, kl, clipped; };
+__device__ __forceinline__ RowStats ppo_row(const float (&zin)[8], const FusedParams& p, int act, float old_lp, float adv,
+                                            float ret, float old_v, float (&gro)[8]) {
+    float z[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        z[k] = zin[k];
+        if (k < p.n_act) mx = fmaxf(mx, z[k]);
+    }
+    float v_new = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k == p.n_act) v_new = z[k];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < p.n_act) sum += expf(z[k] - mx);
+    const float lse = mx + logf(sum);
+    const int a = act < 0 ? 0 : (act >= p.n_act ? p.n_act - 1 : act);
+    float ent = 0.f, nl_a = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < p.n_act) {
+            const float nl = z[k] - lse, pk = expf(nl);
+            ent -= pk * nl;
+            if (k == a) nl_a = nl;
+            z[k] = nl;
+        }
+    const float logratio = nl_a - old_lp;
+    const float ratio = expf(logratio);
+    const float pg1 = -adv * ratio;
+    const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
+    const float pg2 = -adv * rc;
+    const float pg = fmaxf(pg1, pg2);
+    const float in_range = (ratio >= 1.f - p.clip && ratio <= 1.f + p.clip) ? 1.f : 0.f;
+    float g_ratio;
+    if (pg1 > pg2) g_ratio = -adv;
+    else if (pg1 < pg2) g_ratio = -adv * in_range;
+    else g_ratio = 0.5f * (-adv) + 0.5f * (-adv * in_range);
+    const float inv_m = 1.0f / (float)p.m;
+    const float g_nlp = g_ratio * ratio * inv_m;
+    const float dv = v_new - ret;
+    float vl, g_v;
+    if (p.clip_vloss) {
+        const float d = v_new - old_v;
+        const float dc = fminf(fmaxf(d, -p.vclip), p.vclip);
+        const float vc = old_v + dc;
+        const float vu = dv * dv, vcl = (vc - ret) * (vc - ret);
+        vl = fmaxf(vu, vcl);
+        const float v_in = (d >= -p.vclip && d <= p.vclip) ? 1.f : 0.f;
+        const float gu = 2.f * dv, gc = 2.f * (vc - ret) * v_in;
+        g_v = vu > vcl ? gu : (vu < vcl ? gc : 0.5f * (gu + gc));
+    } else {
+        vl = dv * dv;
+        g_v = 2.f * dv;
+    }
+    const float gv_out = 0.5f * p.vf_coef * g_v * inv_m;
+    const float g_ent = p.ent_coef * inv_m;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        gro[k] = 0.f;
+        if (k < p.n_act) {
+            const float pk = expf(z[k]);
+            gro[k] = g_nlp * ((k == a ? 1.f : 0.f) - pk) + g_ent * pk * (z[k] + ent);
+        }
+        if (k == p.n_act) gro[k] = gv_out;
+    }
+    RowStats s;
+    s.pg = pg; s.v = vl; s.ent = ent; s.okl = -logratio; s.kl = (ratio - 1.f) - logratio;
+    s.clipped = fabsf(ratio - 1.f) > p.clip ? 1.f : 0.f;
+    return s;
+}
+
+// byte offset of element (row r, column j) of a [128 rows][32 floats] SWIZZLE_128B chunk
+__device__ __forceinline__ uint32_t chunk_off(int r, int j) {
+    return (uint32_t)(r * 128 + ((((j >> 2) ^ (r & 7))) << 4) + ((j & 3) << 2));
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+    uint64_t* w_full = bars;              // [1]
+    uint64_t* x_full = bars + 1;          // [2]
+    uint64_t* x_empty = bars + 3;         // [2]
+    uint64_t* h_full = bars + 5;          // [2]
+    uint64_t* h_empty = bars + 7;         // [2]  count 4 (epilogue warps)
+    uint64_t* dp_full = bars + 9;         // [NBUF] count 4
+    uint64_t* dp_empty = bars + 9 + NBUF; // [NBUF]
+    uint64_t* dw_done = bars + 9 + 2 * NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * NBUF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&x_full[i], 1);
+            mbar_init(&x_empty[i], 1);
+            mbar_init(&h_full[i], 1);
+            mbar_init(&h_empty[i], 4);
+        }
+        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(&dp_full[i], 4);
+            mbar_init(&dp_empty[i], 1);
+        }
+        mbar_init(dw_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA (>= 1)
+
+    // per-thread results of the epilogue warps, reduced after the role loops
+    float acc_wh[NCHUNK][4][2];          // dW_heads[a = lane>>2][j = 32c + 8nb + 2(lane&3) + {0,1}]  (this warp's rows)
+    float acc_benc[NCHUNK];              // db_enc[32c + lane]
+    float acc_bh[NO];                    // db_heads (this thread's rows)
+    double st[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        acc_benc[c] = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) acc_wh[c][nb][0] = acc_wh[c][nb][1] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NO; ++k) acc_bh[k] = 0.f;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(w_full, TILE_BYTES);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + SMEM_W + kb * KBLK_BYTES, &map_w, kb * KBLK, 0, w_full);
+            for (int it = 0; it < n_my; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int s = it & 1, ph = (it >> 1) & 1;
+                const int64_t row0 = (int64_t)(tile / p.tiles_per_slab) * p.slab_stride_rows +
+                                     (int64_t)(tile % p.tiles_per_slab) * TILE_M;
+                mbar_wait(&x_empty[s], ph ^ 1);
+                mbar_expect_tx(&x_full[s], TILE_BYTES);
+                uint8_t* dst = smem + SMEM_X + s * TILE_BYTES;
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(dst + kb * KBLK_BYTES, &map_x, kb * KBLK, (int)row0, &x_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            const uint32_t w_addr = smem_u32(smem + SMEM_W);
+            auto forward = [&](int it) {
+                const int s = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(&h_empty[s], ph ^ 1);     // epilogue drained accumulator stage s (tile it - 2)
+                mbar_wait(&x_full[s], ph);          // x tile landed
+                tc_fence_after();
+                const uint32_t x_addr = smem_u32(smem + SMEM_X + s * TILE_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * HID);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32(d_tmem, desc_kmajor(x_addr + kb * KBLK_BYTES + k * 32),
+                                  desc_kmajor(w_addr + kb * KBLK_BYTES + k * 32), IDESC_FWD, (kb | k) ? 1u : 0u);
+                umma_commit(&h_full[s]);
+            };
+            mbar_wait(w_full, 0);
+            forward(0);
+            for (int it = 0; it < n_my; ++it) {
+                if (it + 1 < n_my) forward(it + 1);            // overlaps the epilogue of tile `it`
+                const uint32_t x_addr = smem_u32(smem + SMEM_X + (it & 1) * TILE_BYTES);
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const int n = it * NCHUNK + c, b = n % NBUF;
+                    mbar_wait(&dp_full[b], (uint32_t)((n / NBUF) & 1));
+                    tc_fence_after();
+                    const uint32_t ch_addr = smem_u32(smem + SMEM_CH + b * CHUNK_BYTES);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(TMEM_DW + c * CHUNK_COLS);
+#pragma unroll
+                    for (int k = 0; k < TILE_M / 8; ++k)      // K = 8 rows per MMA: one 1 KiB swizzle atom per step
+                        umma_tf32(d_tmem, desc_mnmajor(x_addr + k * 1024, KBLK_BYTES), desc_mnmajor(ch_addr + k * 1024, KBLK_BYTES),
+                                  IDESC_DW, (it | k) ? 1u : 0u);
+                    umma_commit(&dp_empty[b]);
+                }
+                umma_commit(&x_empty[it & 1]);                 // x stage reusable once the dW MMAs have read it
+            }
+            umma_commit(dw_done);
+        }
+    } else {
+        // ================= epilogue warps: thread = tile row = TMEM lane 32q + lane =================
+        const int q = warp & 3;
+        const int g = lane >> 2, t = lane & 3;
+        const int rloc = 32 * q + lane;                        // row inside the tile
+        float z0 = 0.f, z1 = 0.f;                              // dummy accumulators of the zero A rows
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int s = it & 1, ph = (it >> 1) & 1;
+            const int slab = tile / p.tiles_per_slab;
+            const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
+            const bool valid = lrow < p.slab_rows;
+            const int64_t i = (int64_t)slab * p.slab_rows + lrow;
+            int act = 0;
+            float old_lp = 0.f, adv = 0.f, ret = 0.f, old_v = 0.f;
+            if (valid) {
+                act = (int)p.actions[i];
+                old_lp = p.old_logprobs[i];
+                adv = p.adv[i];
+                ret = p.returns[i];
+                old_v = p.clip_vloss ? p.old_values[i] : 0.f;
+            }
+            mbar_wait(&h_full[s], ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * HID);
+
+            // ---- pass 1: heads
+            float out[NO];
+#pragma unroll
+            for (int a = 0; a < NO; ++a) out[a] = c_bh[a];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {     // fully unrolled: every c_wh / c_benc operand is a constant-bank immediate
+                float v[32];
+                tmem_ld32(taddr + 32 * c, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float rh = fmaxf(v[k] + c_benc[32 * c + k], 0.f);
+#pragma unroll
+                    for (int a = 0; a < NO; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * c + k], out[a]);
+                }
+            }
+            // ---- loss row math -> dOut
+            float dO[NO];
+#pragma unroll
+            for (int a = 0; a < NO; ++a) dO[a] = 0.f;
+            if (valid) {
+                const RowStats rs = ppo_row(out, p, act, old_lp, adv, ret, old_v, dO);
+                st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
+                if (p.dbg_dout) {
+                    *reinterpret_cast<float4*>(p.dbg_dout + i * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+                    *reinterpret_cast<float4*>(p.dbg_dout + i * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < NO; ++a) acc_bh[a] += dO[a];
+
+            // ---- A fragments of the dW_heads mma (A[m = head a][k = row]): staged through this warp's rows of the chunk
+            //      buffer the first chunk will use (32 B per row; private to the warp until the dPre chunk is published)
+            uint32_t afr[4][2];
+            {
+                const int n0 = it * NCHUNK, b0 = n0 % NBUF;
+                mbar_wait(&dp_empty[b0], (uint32_t)(((n0 / NBUF) & 1) ^ 1));
+                uint8_t* buf = smem + SMEM_CH + b0 * CHUNK_BYTES;
+                *reinterpret_cast<float4*>(buf + rloc * 128) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+                *reinterpret_cast<float4*>(buf + rloc * 128 + 16) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                __syncwarp();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    afr[ks][0] = to_tf32(*reinterpret_cast<const float*>(buf + (32 * q + 8 * ks + t) * 128 + g * 4));
+                    afr[ks][1] = to_tf32(*reinterpret_cast<const float*>(buf + (32 * q + 8 * ks + t + 4) * 128 + g * 4));
+                }
+                __syncwarp();
+            }
+
+            // ---- pass 2: per 32-column chunk  dPre -> shared memory (UMMA operand), dW_heads, db_enc
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int n = it * NCHUNK + c, b = n % NBUF;
+                uint8_t* buf = smem + SMEM_CH + b * CHUNK_BYTES;
+                float v[32];
+                tmem_ld32(taddr + 32 * c, v);
+                float dp[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float pre = v[k] + c_benc[32 * c + k];
+                    float gk = 0.f;
+#pragma unroll
+                    for (int a = 0; a < NO; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * c + k], gk);
+                    dp[k] = pre > 0.f ? gk : 0.f;
+                    v[k] = fmaxf(pre, 0.f);                    // relu(h)
+                }
+                if (valid && p.dbg_hidden) {
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        *reinterpret_cast<float4*>(p.dbg_hidden + i * HID + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                        *reinterpret_cast<float4*>(p.dbg_dpre + i * HID + 32 * c + k) = make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]);
+                    }
+                }
+                mbar_wait(&dp_empty[b], (uint32_t)(((n / NBUF) & 1) ^ 1));     // the dW MMAs of the buffer's last use retired
+                // relu(h) chunk of this warp's 32 rows (TF32-rounded) -> B fragments of the dW_heads mma
+#pragma unroll
+                for (int jc = 0; jc < 8; ++jc)
+                    *reinterpret_cast<uint4*>(buf + rloc * 128 + ((jc ^ (rloc & 7)) << 4)) =
+                        make_uint4(to_tf32(v[4 * jc]), to_tf32(v[4 * jc + 1]), to_tf32(v[4 * jc + 2]), to_tf32(v[4 * jc + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int r0 = 32 * q + 8 * ks + t;
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(buf + chunk_off(r0, 8 * nb + g));
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(buf + chunk_off(r0 + 4, 8 * nb + g));
+                        mma_tf32(acc_wh[c][nb][0], acc_wh[c][nb][1], z0, z1, afr[ks], b0, b1);
+                    }
+                }
+                __syncwarp();
+                // dPre chunk -> the same rows (MN-major SW128 operand of the dW UMMA)
+#pragma unroll
+                for (int jc = 0; jc < 8; ++jc)
+                    *reinterpret_cast<float4*>(buf + rloc * 128 + ((jc ^ (rloc & 7)) << 4)) =
+                        make_float4(dp[4 * jc], dp[4 * jc + 1], dp[4 * jc + 2], dp[4 * jc + 3]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&dp_full[b]);
+                // db_enc: column sums over this warp's rows (reads race with nothing: the UMMA only reads)
+                float cs = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) cs += *reinterpret_cast<const float*>(buf + chunk_off(32 * q + r, lane));
+                acc_benc[c] += cs;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_empty[s]);
+        }
+        // ---- the dW^T accumulator of this CTA: TMEM lane = feature, column = hidden unit
+        mbar_wait(dw_done, 0);
+        tc_fence_after();
+        float* pd = p.part_dw + ((int64_t)blockIdx.x * FEAT + rloc) * HID;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(TMEM_DW + 32 * c), v);
+#pragma unroll
+            for (int k = 0; k < 32; k += 4)
+                *reinterpret_cast<float4*>(pd + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        }
+        // loss statistics: warp reduce, one fp64 atomic per warp and statistic
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            double x = st[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            if (lane == 0) atomicAdd(p.stats + k, x);
+        }
+    }
+
+    // ================= CTA reduction of the small gradients (4 epilogue warps -> one partial row) =================
+    tc_fence_before();
+    __syncthreads();                       // every role is done: all MMAs retired (dw_done), all TMA loads consumed
+    float* red = reinterpret_cast<float*>(smem + SMEM_X);          // [4][TAIL] scratch in the (now idle) x stages
+    if (warp >= 2) {
+        const int q = warp & 3, g = lane >> 2, t = lane & 3;
+        float* mine = red + q * TAIL;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                mine[g * HID + 32 * c + 8 * nb + 2 * t] = acc_wh[c][nb][0];
+                mine[g * HID + 32 * c + 8 * nb + 2 * t + 1] = acc_wh[c][nb][1];
+            }
+            mine[NO * HID + 32 * c + lane] = acc_benc[c];
+        }
+#pragma unroll
+        for (int k = 0; k < NO; ++k) {
+            float x = acc_bh[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            if (lane == 0) mine[NO * HID + HID + k] = x;
+        }
+    }
+    __syncthreads();
+    float* pt = p.part_tail + (int64_t)blockIdx.x * TAIL;
+    for (int j = threadIdx.x; j < TAIL; j += THREADS) pt[j] = red[j] + red[TAIL + j] + red[2 * TAIL + j] + red[3 * TAIL + j];
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+}
+
+// Deterministic sum of the per-CTA partials into the flat gradient buffer:
+//   gflat = [ dW_enc[hid][feat] (transposed from the partials' [feat][hid]) | dW_heads 8 x hid | db_enc | db_heads ]
+// Block = 64 outputs x 4 partial groups; consecutive threads read consecutive partial elements (coalesced).
+__global__ void __launch_bounds__(256) k_update_reduce(const float* __restrict__ part_dw, const float* __restrict__ part_tail,
+                                                       int n_parts, float* __restrict__ gflat) {
+    __shared__ float sh[4][64];
+    const int e = blockIdx.x * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
+    constexpr int NDW = FEAT * HID;
+    float s = 0.f;
+    if (e < NDW + TAIL) {
+        const float* src = e < NDW ? part_dw + e : part_tail + (e - NDW);
+        const int64_t stride = e < NDW ? NDW : TAIL;
+#pragma unroll 4
+        for (int pidx = grp; pidx < n_parts; pidx += 4) s += src[(int64_t)pidx * stride];
+    }
+    sh[grp][threadIdx.x & 63] = s;
+    __syncthreads();
+    if (grp == 0 && e < NDW + TAIL) {
+        const float tot = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
+        if (e < NDW) gflat[(e % HID) * FEAT + e / HID] = tot;      // partial element (f, j) -> dW_enc[j][f]
+        else gflat[e] = tot;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t rows, int64_t row_stride_floats) {
+    const cuuint64_t dims[2] = {(cuuint64_t)FEAT, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)row_stride_floats * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)TILE_M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_err3("cuTensorMapEncodeTiled failed: %d", (int)r);
+        return -1;
+    }
+    return 0;
+}
+
+int g_sms = 0;
+int num_sms() {
+    if (!g_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return g_sms;
+}
+
+}  // namespace
+
+extern "C" const char* pbx_muf_last_error(void) { return g_err3; }
+
+// workspace: per-CTA partials ([grid][128][128] + [grid][1160] floats), grid = min(tiles, SMs)
+extern "C" size_t pbx_mlp_update_fused_workspace_bytes(void) {
+    return (size_t)num_sms() * (FEAT * HID + TAIL) * sizeof(float);
+}
+
+// One minibatch of the models.Default update up to (and including) the gradients:
+//   x            n_slabs slabs of slab_rows rows x 128 fp32 features, row stride ldx floats, slab s starts at row
+//                s * slab_stride_rows (the zero-copy minibatch view of the time-major rollout; n_slabs = 1 for a plain matrix)
+//   w_enc [128][128], b_enc [128], w_heads [8][128] (n_act logit rows | value row | zeros), b_heads [8]
+//   per-row tensors in slab-major order [n_slabs * slab_rows]: actions, old_logprobs, advantages, returns, old_values
+//   gflat [128*128 + 8*128 + 128 + 8]: dW_enc | dW_heads | db_enc | db_heads;  stats8: the sums pb_ppo_loss produces
+//   dbg_*: nullable dumps of relu(h), dPre, dOut for validation.
+extern "C" int pbx_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
+                                    const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
+                                    const int64_t* actions, const float* old_logprobs, const float* advantages,
+                                    const float* returns, const float* old_values, int32_t n_act, float clip_coef,
+                                    int32_t clip_vloss, float vf_clip_coef, float vf_coef, float ent_coef, float* gflat,
+                                    double* stats8, void* workspace, size_t workspace_bytes, float* dbg_hidden,
+                                    float* dbg_dpre, float* dbg_dout, void* stream) {
+    if (!x || !w_enc || !b_enc || !w_heads || !b_heads || !actions || !old_logprobs || !advantages || !returns || !gflat ||
+        !stats8 || !workspace || slab_rows < 1 || n_slabs < 1 || n_act < 1 || n_act > 7 || (clip_vloss && !old_values) ||
+        ldx < FEAT || ldx % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)w_enc & 15) ||
+        (n_slabs > 1 && slab_stride_rows < slab_rows) || workspace_bytes < pbx_mlp_update_fused_workspace_bytes() ||
+        (dbg_hidden && !dbg_dpre)) {
+        set_err3("pbx_mlp_update_fused: bad arguments");
+        return -1;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
+        qr != cudaDriverEntryPointSuccess) {
+        set_err3("cuTensorMapEncodeTiled entry point not available");
+        return -2;
+    }
+    const int64_t tiles_per_slab = (slab_rows + TILE_M - 1) / TILE_M;
+    const int64_t n_tiles = tiles_per_slab * n_slabs;
+    const int64_t map_rows = (int64_t)(n_slabs - 1) * slab_stride_rows + slab_rows;
+    if (n_tiles > 0x7FFFFFFF || map_rows > 0x7FFFFFFF) {
+        set_err3("pbx_mlp_update_fused: too many rows");
+        return -1;
+    }
+    alignas(64) CUtensorMap map_x, map_w;
+    if (make_map2((EncodeTiledFn)fn, &map_x, x, map_rows, ldx) || make_map2((EncodeTiledFn)fn, &map_w, w_enc, HID, FEAT)) return -3;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = n_tiles < num_sms() ? (int)n_tiles : num_sms();
+    FusedParams p;
+    p.actions = actions; p.old_logprobs = old_logprobs; p.adv = advantages; p.returns = returns; p.old_values = old_values;
+    p.m = slab_rows * n_slabs; p.slab_rows = slab_rows; p.slab_stride_rows = n_slabs > 1 ? slab_stride_rows : slab_rows;
+    p.tiles_per_slab = (int)tiles_per_slab; p.n_tiles = (int)n_tiles; p.n_act = n_act;
+    p.clip = clip_coef; p.vclip = vf_clip_coef; p.vf_coef = vf_coef; p.ent_coef = ent_coef; p.clip_vloss = clip_vloss;
+    p.part_dw = (float*)workspace; p.part_tail = (float*)workspace + (size_t)num_sms() * FEAT * HID;
+    p.stats = stats8; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
+    cudaError_t e = cudaMemsetAsync(stats8, 0, 8 * sizeof(double), s);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_benc, b_enc, sizeof(float) * HID, 0, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_bh, b_heads, sizeof(float) * NO, 0, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_mlp_update_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+    if (e == cudaSuccess) {
+        k_mlp_update_fused<<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
+        k_update_reduce<<<(FEAT * HID + TAIL + 63) / 64, 256, 0, s>>>(p.part_dw, p.part_tail, grid, gflat);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {
+        set_err3("pbx_mlp_update_fused: %s", cudaGetErrorString(e));
+        return -4;
+    }
+    return 0;
+}

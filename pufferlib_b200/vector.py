@@ -152,12 +152,26 @@ class B200:
         self.host_buffers = bool(host_buffers)
         self.exact_infos = self.host_buffers if exact_infos is None else bool(exact_infos)
         lib = _native.lib()
-        cfg = _native.EnvConfig(kind=_native.ENV_KINDS[kind], num_envs=num_envs, device=self.device_index,
-                                reserved=0, env_index_offset=int(env_index_offset),
-                                iparam=(C.c_int32 * 8)(*iparam))
-        handle = C.c_void_p()
-        _native.check(lib.pb_env_create(C.byref(cfg), C.byref(handle)))
-        self._handle = handle
+        # num_workers (the reference's Multiprocessing argument): every worker PROCESS there runs a Serial over its envs
+        # with its own process-global `random` stream (vector.py:168-190, seeds sliced per worker at :424-428).  Only envs
+        # that draw from that global stream depend on it (ocean.Squared); for them the envs are split into one pb_env
+        # shard per worker, each with its own MT19937 stream, writing into the same contiguous buffers.  The other
+        # kinds key their counter-based RNG by global env index, so the worker split cannot change their results.
+        workers = kwargs.get('num_workers') or 1
+        if kind != 'squared' or workers <= 1:
+            workers = 1
+        if num_envs % workers != 0:
+            raise APIUsageError('num_envs must be divisible by num_workers')
+        per = num_envs // workers
+        self._shards = []          # (handle, first env, envs)
+        for w in range(workers):
+            cfg = _native.EnvConfig(kind=_native.ENV_KINDS[kind], num_envs=per, device=self.device_index,
+                                    reserved=0, env_index_offset=int(env_index_offset) + w * per,
+                                    iparam=(C.c_int32 * 8)(*iparam))
+            handle = C.c_void_p()
+            _native.check(lib.pb_env_create(C.byref(cfg), C.byref(handle)))
+            self._shards.append((handle, w * per, per))
+        self._handle = self._shards[0][0]
         info = _native.EnvInfo()
         _native.check(lib.pb_env_get_info(self._handle, C.byref(info)))
         self.obs_bytes = int(info.obs_bytes)
@@ -215,29 +229,38 @@ class B200:
         self._cursor = 0
         self._pending_own = True
 
-    def _env_out(self, row):
-        """pb_env_out for rollout row `row`, or for the vecenv's own buffers when row is None."""
+    def _env_out(self, row, lo=0):
+        """pb_env_out for rollout row `row`, or for the vecenv's own buffers when row is None; `lo` = first env of the
+        shard the outputs belong to."""
         b = self.buf
         if row is None:
-            return _native.EnvOut(obs=b.observations.data_ptr(), obs_stride=self.obs_bytes,
-                                  rewards=b.rewards.data_ptr(), terminals=b.terminals.data_ptr(),
-                                  truncations=b.truncations.data_ptr(), masks=b.masks.data_ptr(),
-                                  dones_f32=b.dones_f32.data_ptr())
+            return _native.EnvOut(obs=b.observations.data_ptr() + lo * self.obs_bytes, obs_stride=self.obs_bytes,
+                                  rewards=b.rewards.data_ptr() + lo * 4, terminals=b.terminals.data_ptr() + lo,
+                                  truncations=b.truncations.data_ptr() + lo, masks=b.masks.data_ptr() + lo,
+                                  dones_f32=b.dones_f32.data_ptr() + lo * 4)
         x, n = self._rollout, self.num_agents
-        return _native.EnvOut(obs=x.obs.data_ptr() + row * n * self.obs_bytes, obs_stride=self.obs_bytes,
-                              rewards=x.rewards.data_ptr() + row * n * 4, terminals=b.terminals.data_ptr(),
-                              truncations=b.truncations.data_ptr(), masks=b.masks.data_ptr(),
-                              dones_f32=x.dones.data_ptr() + row * n * 4)
+        return _native.EnvOut(obs=x.obs.data_ptr() + (row * n + lo) * self.obs_bytes, obs_stride=self.obs_bytes,
+                              rewards=x.rewards.data_ptr() + (row * n + lo) * 4, terminals=b.terminals.data_ptr() + lo,
+                              truncations=b.truncations.data_ptr() + lo, masks=b.masks.data_ptr() + lo,
+                              dones_f32=x.dones.data_ptr() + (row * n + lo) * 4)
 
     # -- vector.Serial surface ---------------------------------------------------------------------------------
     def async_reset(self, seed=42):
         if not isinstance(seed, int):
-            raise APIUsageError(f'seed {seed} must be an integer (per-env seed lists are not supported on the device)')
+            # list form of make_seeds (vector.py:639-650) -- what Multiprocessing hands each worker is the slice
+            # [seed + lo, ..., seed + hi - 1] (:424-428).  Env i is seeded with seed + i on the device, so a list is
+            # accepted when it is such a run of consecutive integers; arbitrary per-env seeds have no device form.
+            seeds = make_seeds(seed, self.num_agents)
+            if not all(isinstance(x, (int, np.integer)) for x in seeds) or \
+                    any(int(seeds[i]) != int(seeds[0]) + i for i in range(len(seeds))):
+                raise APIUsageError(f'seed {seed} must be an integer or a list of consecutive integers')
+            seed = int(seeds[0])
         self.flag = RECV
-        out = self._env_out(None)
         with torch.cuda.device(self.device):
-            _native.check(_native.lib().pb_env_reset(self._handle, C.c_uint64(seed % (1 << 64)), C.byref(out),
-                                                     _native.stream_ptr()))
+            for handle, lo, _ in self._shards:
+                out = self._env_out(None, lo)
+                _native.check(_native.lib().pb_env_reset(handle, C.c_uint64(seed % (1 << 64)), C.byref(out),
+                                                         _native.stream_ptr()))
         self._pending_own = True
         self._cursor = 0
         self.infos = []
@@ -260,9 +283,10 @@ class B200:
             row = None
             if self._rollout is not None and not self._pending_own and self._cursor + 1 < self._horizon:
                 row = self._cursor + 1
-            out = self._env_out(row)
-            _native.check(_native.lib().pb_env_step(self._handle, C.c_void_p(a.data_ptr()), C.byref(out),
-                                                    _native.stream_ptr()))
+            for handle, lo, _ in self._shards:
+                out = self._env_out(row, lo)
+                _native.check(_native.lib().pb_env_step(handle, C.c_void_p(a.data_ptr() + 8 * lo), C.byref(out),
+                                                        _native.stream_ptr()))
             if self._rollout is not None:
                 if row is None:
                     self._pending_own = True
@@ -326,14 +350,16 @@ class B200:
         if len(idx) == 0:
             return []
         lib = _native.lib()
-        p_ret, p_len, p_score = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        _native.check(lib.pb_env_episode_rows(self._handle, C.byref(p_ret), C.byref(p_len), C.byref(p_score)))
         n = self.num_agents
         # the three per-env arrays through ONE staging tensor and ONE device->host copy (one sync instead of three)
         stage = torch.empty(16 * n, dtype=torch.uint8, device=self.buf.terminals.device)
         base, s_ = stage.data_ptr(), _native.stream_ptr()
-        for src, off, nbytes in ((p_ret.value, 0, 8 * n), (p_len.value, 8 * n, 4 * n), (p_score.value, 12 * n, 4 * n)):
-            _native.check(lib.pb_copy_rows(C.c_void_p(src), nbytes, C.c_void_p(base + off), nbytes, nbytes, 1, s_))
+        for handle, lo, cnt in self._shards:
+            p_ret, p_len, p_score = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _native.check(lib.pb_env_episode_rows(handle, C.byref(p_ret), C.byref(p_len), C.byref(p_score)))
+            for src, off, nbytes in ((p_ret.value, 8 * lo, 8 * cnt), (p_len.value, 8 * n + 4 * lo, 4 * cnt),
+                                     (p_score.value, 12 * n + 4 * lo, 4 * cnt)):
+                _native.check(lib.pb_copy_rows(C.c_void_p(src), nbytes, C.c_void_p(base + off), nbytes, nbytes, 1, s_))
         host = stage.cpu().numpy()
         ret, length, score = host[:8 * n].view(np.float64), host[8 * n:12 * n].view(np.int32), \
             host[12 * n:].view(np.float32)
@@ -344,19 +370,22 @@ class B200:
     def episode_stats(self, clear=True):
         """Device-side EpisodeStats reduction: {episode_return, episode_length, score} means over the episodes
         finished since the last call, plus their count (one 32-byte D2H)."""
-        out = (C.c_double * 4)()
+        out = [0.0] * 4
         with torch.cuda.device(self.device):
-            _native.check(_native.lib().pb_env_stats_read(self._handle, out, int(clear), _native.stream_ptr()))
-        self.d2h_bytes += 256 * 32
+            for handle, _, _ in self._shards:
+                part = (C.c_double * 4)()
+                _native.check(_native.lib().pb_env_stats_read(handle, part, int(clear), _native.stream_ptr()))
+                out = [a + b for a, b in zip(out, part)]
+                self.d2h_bytes += 256 * 32
         cnt = out[0]
         if cnt <= 0:
             return {}, 0
         return {'episode_return': out[1] / cnt, 'episode_length': out[2] / cnt, 'score': out[3] / cnt}, int(cnt)
 
     def close(self):
-        if getattr(self, '_handle', None):
-            _native.lib().pb_env_destroy(self._handle)
-            self._handle = None
+        for handle, _, _ in getattr(self, '_shards', []):
+            _native.lib().pb_env_destroy(handle)
+        self._shards, self._handle = [], None
 
     def __del__(self):
         try:
@@ -388,9 +417,18 @@ class B200Pool:
         if b < 1 or num_envs % b != 0:
             raise APIUsageError('num_envs must be divisible by batch_size')
         g = num_envs // b
+        # num_workers given: a batch is workers_per_batch = batch_size / envs_per_worker whole workers (vector.py:244-246),
+        # each with its own RNG stream; not given: one stream per group
+        nw = kwargs.get('num_workers')
+        wpb = {}
+        if nw:
+            epw = num_envs // nw
+            if epw < 1 or b % epw != 0:
+                raise APIUsageError('batch_size must be divisible by (num_envs / num_workers)')
+            wpb = {'num_workers': b // epw}
         self.groups = [B200(env_creators[i * b:(i + 1) * b], env_args[i * b:(i + 1) * b], env_kwargs[i * b:(i + 1) * b], b,
                             host_buffers=host_buffers, exact_infos=exact_infos, device=device,
-                            env_index_offset=env_index_offset + i * b) for i in range(g)]
+                            env_index_offset=env_index_offset + i * b, **wpb) for i in range(g)]
         first = self.groups[0]
         self.device = first.device
         self.host_buffers, self.exact_infos = first.host_buffers, first.exact_infos

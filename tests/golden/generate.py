@@ -153,7 +153,45 @@ def gen_experience(compute_gae):
         print(name, 'B', batch, 'b_obs', tuple(exp.b_obs.shape))
 
 
+
+
+def run_squared_multiprocessing(num_envs, num_workers, seed, horizon):
+    """The reference's Multiprocessing backend in its synchronous mode (batch_size == num_envs: every recv() returns
+    all workers' rows in worker order, vector.py:360-369), so the golden is deterministic.  Each worker process runs a
+    Serial over its envs with its OWN process-global `random` stream (vector.py:168-190): the outputs differ from the
+    Serial golden of the same seed from the first auto-reset on."""
+    vec = pufferlib.vector.make(ocean.env_creator('squared'), num_envs=num_envs, num_workers=num_workers,
+                                batch_size=num_envs, backend=pufferlib.vector.Multiprocessing)
+    tape = action_tape(horizon, num_envs)
+    obs, rew, term, info_rows = [], [], [], []
+    vec.async_reset(seed)
+    for t in range(horizon + 1):
+        o, r, d, tr, infos, env_id, m = vec.recv()
+        assert np.array_equal(env_id, np.arange(num_envs)) and m.all() and not tr.any()
+        obs.append(o.copy()); rew.append(r.copy()); term.append(d.copy())
+        for k, i in enumerate(infos):
+            info_rows.append((t, k, i['episode_return'], i['episode_length'], i['score']))
+        if t < horizon:
+            vec.send(tape[t])
+    vec.close()
+    obs = np.stack(obs)
+    return dict(num_envs=num_envs, num_workers=num_workers, seed=seed, horizon=horizon, actions=tape,
+                obs_i8=obs.astype(np.int8), rewards=np.stack(rew), terminals=np.stack(term),
+                infos=np.asarray(info_rows, dtype=np.float64).reshape(-1, 5))
+
+
+def gen_squared_multiprocessing():
+    for name, kw in {'squared_mp_n8_w2': dict(num_envs=8, num_workers=2, seed=11, horizon=40),
+                     'squared_mp_n12_w4': dict(num_envs=12, num_workers=4, seed=5, horizon=33)}.items():
+        out = run_squared_multiprocessing(**kw)
+        serial = run_squared(kw['num_envs'], kw['seed'], kw['horizon'])
+        out['differs_from_serial'] = np.asarray(not np.array_equal(serial['obs_i8'], out['obs_i8']))
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+        print(name, out['obs_i8'].shape, 'differs from Serial:', bool(out['differs_from_serial']))
+
+
 if __name__ == '__main__':
     gen_squared()
+    gen_squared_multiprocessing()
     cg = gen_gae()
     gen_experience(cg)

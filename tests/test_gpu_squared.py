@@ -116,3 +116,88 @@ def test_api_order_errors():
     with pytest.raises(APIUsageError):
         pvec.make(ocean.env_creator('squared'), num_envs=4, backend=pvec.B200, bogus=1)
     vec.close(); vec2.close()
+
+
+@pytest.mark.parametrize('case', ['squared_mp_n8_w2', 'squared_mp_n12_w4'])
+@pytest.mark.parametrize('bound', [False, True])
+def test_squared_multiprocessing_golden_sync(golden, case, bound):
+    """backend=B200 with num_workers=W against the reference's own Multiprocessing backend run with W real worker
+    processes (tests/golden/generate.py::run_squared_multiprocessing): every worker has its own process-global MT19937
+    stream (vector.py:168-190, 424-428), which changes the targets of every auto-reset relative to Serial."""
+    g = golden(case)
+    n, w, seed, h = int(g['num_envs']), int(g['num_workers']), int(g['seed']), int(g['horizon'])
+    vec = pvec.make(ocean.env_creator('squared'), num_envs=n, num_workers=w, batch_size=n,
+                    backend=pvec.B200.options(exact_infos=True))
+    assert isinstance(vec, pvec.B200) and len(vec._shards) == w
+    if bound:
+        from pufferlib_b200 import clean_pufferl
+        exp = clean_pufferl.Experience(n * 8, 4, n * 8, (7, 7), np.float32, ())
+        vec.bind_rollout(exp)
+    vec.async_reset(seed)
+    infos_all = []
+    for t in range(h + 1):
+        o, r, d, tr, infos, ids, m = vec.recv()
+        assert np.array_equal(to_np(o), g['obs_i8'][t].astype(np.float32)), f'obs step {t}'
+        assert np.array_equal(to_np(r).view(np.uint32), g['rewards'][t].view(np.uint32)), f'reward bits step {t}'
+        assert np.array_equal(to_np(d), g['terminals'][t])
+        for k, i in enumerate(infos):
+            infos_all.append((t, k, i['episode_return'], i['episode_length'], i['score']))
+        if t < h:
+            a = torch.as_tensor(g['actions'][t], device='cuda')
+            if bound:
+                z = torch.zeros(n, device='cuda')
+                exp.store(o, z, a, z, r, d, ids, m)
+                if exp.full:
+                    exp.sort_training_data()
+            vec.send(a)
+    ref = g['infos']
+    got = np.asarray(infos_all, dtype=np.float64).reshape(-1, 5)
+    assert got.shape == ref.shape and np.array_equal(got[:, [0, 1, 3, 4]], ref[:, [0, 1, 3, 4]])
+    assert np.allclose(got[:, 2], ref[:, 2], rtol=1e-12, atol=0)
+    vec.close()
+
+
+def test_squared_multiprocessing_golden_pool():
+    """Pool mode (batch_size = one worker's envs): groups come back round-robin instead of first-ready, but every env's
+    trajectory under its own action sequence is the reference Multiprocessing trajectory (per-worker streams)."""
+    from conftest import load_golden
+    g = load_golden('squared_mp_n12_w4')
+    n, w, seed, h = int(g['num_envs']), int(g['num_workers']), int(g['seed']), int(g['horizon'])
+    b = n // w
+    vec = pvec.make(ocean.env_creator('squared'), num_envs=n, num_workers=w, batch_size=b, backend=pvec.B200)
+    assert isinstance(vec, pvec.B200Pool) and len(vec.groups) == w
+    vec.async_reset(seed)
+    for t in range(h + 1):
+        for k in range(w):
+            o, r, d, tr, infos, ids, m = vec.recv()
+            lo, hi = k * b, (k + 1) * b
+            assert np.array_equal(ids, np.arange(lo, hi))
+            assert np.array_equal(to_np(o), g['obs_i8'][t, lo:hi].astype(np.float32)), (t, k)
+            assert np.array_equal(to_np(d), g['terminals'][t, lo:hi])
+            vec.send(torch.as_tensor(g['actions'][min(t, h - 1), lo:hi], device='cuda'))
+    # two workers per batch: each group holds two RNG shards
+    vec2 = pvec.make(ocean.env_creator('squared'), num_envs=n, num_workers=w, batch_size=2 * b, backend=pvec.B200)
+    assert len(vec2.groups) == 2 and all(len(v._shards) == 2 for v in vec2.groups)
+    vec2.async_reset(seed)
+    for t in range(h + 1):
+        for k in range(2):
+            o, r, d, tr, infos, ids, m = vec2.recv()
+            lo, hi = k * 2 * b, (k + 1) * 2 * b
+            assert np.array_equal(to_np(o), g['obs_i8'][t, lo:hi].astype(np.float32)), (t, k)
+            vec2.send(torch.as_tensor(g['actions'][min(t, h - 1), lo:hi], device='cuda'))
+    vec.close(); vec2.close()
+
+
+def test_seed_lists(golden):
+    """make_seeds list form (vector.py:639-650): a run of consecutive integers is what Multiprocessing hands a worker."""
+    g = golden('squared_n5_seed42')
+    vec = pvec.make(ocean.env_creator('squared'), num_envs=5, backend=pvec.B200)
+    vec.async_reset([42, 43, 44, 45, 46])
+    assert np.array_equal(to_np(vec.recv()[0]), g['obs_i8'][0].astype(np.float32))
+    with pytest.raises(APIUsageError):
+        vec.async_reset([1, 2, 3])               # wrong length
+    with pytest.raises(APIUsageError):
+        vec.async_reset([5, 4, 3, 2, 1])         # not representable on the device
+    with pytest.raises(APIUsageError):
+        vec.async_reset('seed')
+    vec.close()

@@ -135,3 +135,26 @@ def test_gae_oracle_vs_reference_compiled_c_gae(n, p_done, gamma, lam):
     ref = np.asarray(ref_mod.compute_gae(d, v, r, gamma, lam))
     got = ogae.compute_gae(d, v, r, gamma, lam)
     assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+
+
+@pytest.mark.parametrize('case', ['squared_mp_n8_w2', 'squared_mp_n12_w4'])
+def test_squared_multiprocessing_oracle_bit_exact(golden, case):
+    """vector.Multiprocessing (reference run with real worker processes, tests/golden/generate.py): per-worker
+    process-global MT19937 streams (vector.py:168-190) -- the oracle restates it as one SquaredSerial per worker."""
+    from oracle.squared import SquaredMultiprocessing
+    g = golden(case)
+    assert bool(g['differs_from_serial'])       # the golden really exercises the per-worker stream consequence
+    n, w, seed, h = int(g['num_envs']), int(g['num_workers']), int(g['seed']), int(g['horizon'])
+    vec = SquaredMultiprocessing(n, w)
+    vec.async_reset(seed)
+    infos = []
+    for t in range(h + 1):
+        o, r, d, tr, info, ids, m = vec.recv()
+        assert np.array_equal(o, g['obs_i8'][t].astype(np.float32)), f'obs step {t}'
+        assert np.array_equal(r.view(np.uint32), g['rewards'][t].view(np.uint32)), f'reward bits step {t}'
+        assert np.array_equal(d, g['terminals'][t]) and not tr.any() and m.all()
+        for k, i in enumerate(info):
+            infos.append((t, k, i['episode_return'], i['episode_length'], i['score']))
+        if t < h:
+            vec.send(g['actions'][t])
+    assert np.array_equal(np.asarray(infos, dtype=np.float64).reshape(-1, 5), g['infos'])
