@@ -190,8 +190,52 @@ def gen_squared_multiprocessing():
         print(name, out['obs_i8'].shape, 'differs from Serial:', bool(out['differs_from_serial']))
 
 
+def gen_lstm():
+    """The reference's recurrent path end to end on CPU: create -> evaluate (lstm_h[:, env_id] state carry,
+    clean_pufferl.py:100-105) -> train (bptt segments [rows, bptt, *obs], state carried ACROSS minibatches inside an
+    epoch and reset per epoch, :176-191) with models.LSTMWrapper (models.py:64-111) around models.Default."""
+    import clean_pufferl
+    import pufferlib.models
+    import pufferlib.frameworks.cleanrl
+    n, h, bptt, mbs, hid = 8, 16, 4, 64, 32
+    vec = pufferlib.vector.make(ocean.env_creator('squared'), num_envs=n, backend=pufferlib.vector.Serial)
+    torch.manual_seed(3)
+    base = pufferlib.models.Default(vec.driver_env, hidden_size=hid)
+    wrapper = pufferlib.models.LSTMWrapper(vec.driver_env, base, input_size=hid, hidden_size=hid)
+    policy = pufferlib.frameworks.cleanrl.RecurrentPolicy(wrapper)
+    init = {k: v.detach().clone().numpy() for k, v in policy.state_dict().items()}
+    cfg = dict(seed=1, torch_deterministic=True, env='squared', batch_size=n * h, bptt_horizon=bptt, minibatch_size=mbs,
+               cpu_offload=False, device='cpu', compile=False, compile_mode='default', learning_rate=2.5e-3, gamma=0.99,
+               gae_lambda=0.95, update_epochs=2, norm_adv=True, clip_coef=0.1, clip_vloss=True, vf_clip_coef=0.1,
+               vf_coef=0.5, ent_coef=0.01, max_grad_norm=0.5, target_kl=None, anneal_lr=False,
+               total_timesteps=10 ** 9, checkpoint_interval=10 ** 9, data_dir='/tmp/golden_lstm', exp_id='lstm')
+    data = clean_pufferl.create(pufferlib.namespace(**cfg), vec, policy)
+    clean_pufferl.evaluate(data)
+    exp = data.experience
+    out = dict(num_envs=n, horizon=h, bptt=bptt, minibatch_size=mbs, hidden=hid, seed=1,
+               learning_rate=cfg['learning_rate'], update_epochs=cfg['update_epochs'],
+               obs_i8=exp.obs.numpy().astype(np.int8), actions=exp.actions_np.copy(), logprobs=exp.logprobs_np.copy(),
+               values=exp.values_np.copy(), rewards=exp.rewards_np.copy(), dones=exp.dones_np.copy(),
+               lstm_h=exp.lstm_h.numpy().copy(), lstm_c=exp.lstm_c.numpy().copy())
+    clean_pufferl.train(data)
+    for k in ('policy_loss', 'value_loss', 'entropy', 'old_approx_kl', 'approx_kl', 'clipfrac', 'explained_variance'):
+        out['loss_' + k] = np.asarray(getattr(data.losses, k), dtype=np.float64)
+    out['b_obs_i8'] = exp.b_obs.numpy().astype(np.int8)
+    out['advantages'] = exp.b_advantages.numpy().copy()
+    for k, v in init.items():
+        out['init/' + k] = v
+    for k, v in policy.state_dict().items():
+        out['after/' + k] = v.detach().numpy().copy()
+    data.utilization.stop()
+    vec.close()
+    np.savez_compressed(os.path.join(HERE, 'lstm_squared.npz'), **out)
+    print('lstm_squared', {k: float(out['loss_' + k]) for k in ('policy_loss', 'value_loss', 'entropy')},
+          'params', sum(v.size for k, v in out.items() if k.startswith('init/')))
+
+
 if __name__ == '__main__':
     gen_squared()
     gen_squared_multiprocessing()
     cg = gen_gae()
     gen_experience(cg)
+    gen_lstm()

@@ -287,3 +287,77 @@ def test_zero_copy_minibatches_match_gathered_minibatches():
     assert np.array_equal(acts[True], acts[False])
     diff = max(float((a - b).abs().max()) for a, b in zip(params[True], params[False]))
     assert diff <= 2e-5, diff
+
+
+def test_lstm_parity_vs_reference(golden):
+    """The recurrent path against the REFERENCE's own run (tests/golden/lstm_squared.npz: unmodified
+    clean_pufferl.create/evaluate/train + models.LSTMWrapper + cleanrl.RecurrentPolicy on CPU, generate.py::gen_lstm).
+    Same initial weights, same seed, the reference's sampled actions replayed: evaluate must store the same
+    observations / values / logprobs and leave the same LSTM state (lstm_h[:, env_id] carry, clean_pufferl.py:100-105);
+    train must give the same losses and parameters (bptt segments [rows, bptt, *obs], state carried across the
+    minibatches of an epoch and reset per epoch, :176-191; models.py:64-111)."""
+    import pufferlib_b200
+    from pufferlib_b200 import models
+    from pufferlib_b200.frameworks import cleanrl
+    g = golden('lstm_squared')
+    n, h, bptt, mbs, hid = (int(g[k]) for k in ('num_envs', 'horizon', 'bptt', 'minibatch_size', 'hidden'))
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False     # the golden is CPU fp32
+    try:
+        vec = pvec.make(ocean.env_creator('squared'), num_envs=n, backend=pvec.B200)
+        net = models.LSTMWrapper(vec.driver_env, models.Default(vec.driver_env, hidden_size=hid), input_size=hid,
+                                 hidden_size=hid)
+        net.policy.fast_path = False
+
+        class TapePolicy(cleanrl.RecurrentPolicy):
+            """RecurrentPolicy that replays the reference's sampled actions in evaluate (sampling itself is
+            torch.multinomial on the CPU generator there; the given-action branch of sample_logits is the same code)."""
+            tape, t = torch.as_tensor(g['actions'].reshape(h, n), device='cuda'), 0
+
+            def forward(self, x, state=None, action=None):
+                if action is None:
+                    action = self.tape[self.t]
+                    self.t += 1
+                return super().forward(x, state, action)
+
+        pol = TapePolicy(net).cuda()
+        sd = {k[len('init/'):]: torch.as_tensor(g[k]) for k in g.files if k.startswith('init/')}
+        assert set(sd) == set(pol.state_dict()), 'module / parameter names follow the reference'
+        pol.load_state_dict(sd)
+        cfg = pufferlib_b200.namespace(
+            seed=int(g['seed']), torch_deterministic=True, env='squared', batch_size=n * h, bptt_horizon=bptt,
+            minibatch_size=mbs, cpu_offload=False, device='cuda', compile=False, learning_rate=float(g['learning_rate']),
+            gamma=0.99, gae_lambda=0.95, update_epochs=int(g['update_epochs']), norm_adv=True, clip_coef=0.1,
+            clip_vloss=True, vf_clip_coef=0.1, vf_coef=0.5, ent_coef=0.01, max_grad_norm=0.5, target_kl=None,
+            anneal_lr=False, total_timesteps=10 ** 9)
+        data = clean_pufferl.create(cfg, vec, pol)
+        clean_pufferl.evaluate(data)
+        exp = data.experience
+        assert np.array_equal(cpu(exp.obs), g['obs_i8'].astype(np.float32))
+        assert np.array_equal(cpu(exp.actions), g['actions'])
+        assert np.array_equal(cpu(exp.rewards), g['rewards']) and np.array_equal(cpu(exp.dones), g['dones'])
+        assert np.allclose(cpu(exp.values), g['values'], rtol=1e-4, atol=2e-6)
+        assert np.allclose(cpu(exp.logprobs), g['logprobs'], rtol=1e-4, atol=2e-6)
+        assert np.allclose(cpu(exp.lstm_h), g['lstm_h'], rtol=1e-4, atol=2e-6)
+        assert np.allclose(cpu(exp.lstm_c), g['lstm_c'], rtol=1e-4, atol=2e-6)
+        clean_pufferl.train(data)
+        assert np.array_equal(cpu(exp.b_obs), g['b_obs_i8'].astype(np.float32))
+        assert np.allclose(cpu(exp.b_advantages), g['advantages'], rtol=1e-4, atol=1e-5)
+        for k in ('policy_loss', 'value_loss', 'entropy', 'old_approx_kl', 'approx_kl', 'clipfrac'):
+            assert np.isclose(getattr(data.losses, k), float(g['loss_' + k]), rtol=2e-3, atol=2e-5), \
+                (k, getattr(data.losses, k), float(g['loss_' + k]))
+        assert np.isclose(data.losses.explained_variance, float(g['loss_explained_variance']), rtol=1e-3, atol=1e-4)
+        # parameters after update_epochs x num_minibatches Adam steps (lr 2.5e-3): Adam normalises the gradient, so fp32
+        # noise on near-zero gradients moves single elements by a fraction of lr -- the bulk must agree tightly
+        diffs = []
+        for k, v in pol.state_dict().items():
+            d = np.abs(cpu(v) - g['after/' + k])
+            assert d.max() < 1e-3, (k, d.max())
+            diffs.append(d.ravel())
+        diffs = np.concatenate(diffs)
+        assert np.mean(diffs) < 2e-5 and np.quantile(diffs, 0.99) < 2e-4
+        moved = np.concatenate([np.abs(g['after/' + k] - g['init/' + k]).ravel() for k in sd])
+        assert np.mean(moved) > 50 * np.mean(diffs), 'the update itself is much larger than the disagreement'
+        clean_pufferl.close(data)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
