@@ -250,6 +250,31 @@ typedef struct pb_adam_tensor {
 int pb_clip_adam(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
                  const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out, void* stream);
 
+/* -- gradient all-reduce over NVLink peer memory (multi-GPU, one node; SURVEY §8e: the reference has no distributed path) --
+ * Each rank allocates one buffer (pb_peer_alloc: cudaMalloc + IPC handle), exchanges the 64-byte handles through the
+ * host (torch.distributed), maps every peer's buffer (pb_peer_open) and fills a pb_peer_comm.  pb_peer_allreduce sums a
+ * flat fp32 buffer in place over all ranks inside ONE single-CTA kernel: copy to the own peer-visible slot, raise a flag
+ * in every peer's buffer, wait for all flags, add all ranks' slots in rank order with direct NVLink loads (identical
+ * bits on every rank).  No host involvement per call: it can be captured in a CUDA graph.  pb_clip_adam_peer is
+ * pb_clip_adam with that all-reduce of the flat gradient buffer fused in front (all `grad` pointers of the tensors must
+ * lie inside grad_flat[0..grad_flat_numel)); pass grad_scale = 1/world for the mean. */
+#define PB_PEER_MAX_RANKS 8
+typedef struct pb_peer_comm {
+    int32_t world, rank;
+    void* base[PB_PEER_MAX_RANKS]; /* rank r's buffer as mapped in THIS process (base[rank] = the own allocation) */
+    uint64_t* epoch;               /* one zero-initialised device uint64 owned by the caller (calls made so far) */
+    int64_t capacity;              /* floats per gradient slot */
+} pb_peer_comm;
+size_t pb_peer_buffer_bytes(int64_t capacity_floats);
+int pb_peer_alloc(size_t bytes, void** ptr_out, void* handle64_out);
+int pb_peer_open(const void* handle64, void** ptr_out);
+int pb_peer_close(void* ptr);
+int pb_peer_free(void* ptr);
+int pb_peer_allreduce(const pb_peer_comm* comm, float* flat, int64_t n, void* stream);
+int pb_clip_adam_peer(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
+                      const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
+                      const pb_peer_comm* comm, float* grad_flat, int64_t grad_flat_numel, void* stream);
+
 /* The 8-row head matrix of models.Default (pufferlib/models.py:33-38: decoder rows | value_head row | zero padding),
  * its bias, and (optionally) the encoder weight rounded to TF32, in one launch: the operands pb_policy_mlp_sample,
  * pb_mlp_tail_backward and the 8-column head GEMM consume. */

@@ -32,6 +32,11 @@ class AdamTensor(C.Structure):
                 ('grad', C.c_void_p), ('numel', C.c_int64)]
 
 
+class PeerComm(C.Structure):
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('base', C.c_void_p * 8), ('epoch', C.c_void_p),
+                ('capacity', C.c_int64)]
+
+
 class EnvOut(C.Structure):
     _fields_ = [('obs', C.c_void_p), ('obs_stride', C.c_int64), ('rewards', C.c_void_p), ('terminals', C.c_void_p),
                 ('truncations', C.c_void_p), ('masks', C.c_void_p), ('dones_f32', C.c_void_p)]
@@ -74,6 +79,15 @@ SIGNATURES = {
                              C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'pb_clip_adam': (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float,
                                C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    'pb_clip_adam_peer': (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float,
+                                    C.c_float, C.c_float, C.c_void_p, C.POINTER(PeerComm), C.c_void_p, C.c_int64,
+                                    C.c_void_p]),
+    'pb_peer_buffer_bytes': (C.c_size_t, [C.c_int64]),
+    'pb_peer_alloc': (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    'pb_peer_open': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    'pb_peer_close': (C.c_int, [C.c_void_p]),
+    'pb_peer_free': (C.c_int, [C.c_void_p]),
+    'pb_peer_allreduce': (C.c_int, [C.POINTER(PeerComm), C.c_void_p, C.c_int64, C.c_void_p]),
     'pb_pack_heads': (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]),
     'pb_struct_pack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     'pb_struct_unpack': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -207,10 +207,11 @@ class _DefaultMLPUpdate:
             return False
         if config.target_kl is not None or not getattr(data, 'own_optimizer', False):
             return False
-        world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
-                                                        torch.distributed.is_initialized()) else 1
-        if world > 1 and not bool(getattr(config, 'manual_update_multi_gpu', False)):
-            return False          # round 1: measured on one GPU only; ranks > 1 keep the autograd + GradBucket path
+        if not bool(getattr(config, 'manual_update_multi_gpu', True)):
+            world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
+                                                            torch.distributed.is_initialized()) else 1
+            if world > 1:
+                return False      # opt-out: ranks > 1 on the autograd + GradBucket (NCCL) path
         n_act, hid = model.decoder.weight.shape
         if hid != 128 or n_act > 7 or model.encoder.weight.dtype != torch.float32 or not model.encoder.weight.is_cuda:
             return False
@@ -256,6 +257,22 @@ class _DefaultMLPUpdate:
         self.stats = None
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
                                                             torch.distributed.is_initialized()) else 1
+        # multi-GPU: the gradient sum is fused into pb_clip_adam_peer over NVLink peer memory (distributed.PeerComm); the
+        # NCCL all-reduce is only the fallback when peer mapping is unavailable (config.peer_allreduce=False, or IPC failed)
+        self.peer = None
+        if self.world > 1 and bool(getattr(data.config, 'peer_allreduce', True)):
+            from pufferlib_b200.distributed import PeerComm
+            ok = torch.ones(1, device=dev)
+            try:
+                self.peer = PeerComm(self.gflat.numel())
+            except Exception as e:           # every rank must take the same path: agree on it below
+                data.msg = f'peer all-reduce unavailable ({type(e).__name__}: {e}); using NCCL'
+                ok.zero_()
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if float(ok.item()) == 0.0:
+                if self.peer is not None:
+                    self.peer.close()
+                self.peer = None
 
     def _current_state_ptrs(self):
         out = []
@@ -324,7 +341,7 @@ class _DefaultMLPUpdate:
         torch.sum(self.part, 0, out=self.dw_enc)
 
     def all_reduce(self):
-        if self.world > 1:
+        if self.world > 1 and self.peer is None:
             torch.distributed.all_reduce(self.gflat)
 
     @torch.no_grad()
@@ -333,10 +350,11 @@ class _DefaultMLPUpdate:
         lr = g['lr']
         lr_dev = _native.ptr(lr) if isinstance(lr, torch.Tensor) else None
         b1, b2 = g['betas']
-        _native.check(_native.lib().pb_clip_adam(
+        _native.check(_native.lib().pb_clip_adam_peer(
             self.tensors, len(self.tensors), C.c_float(float(config.max_grad_norm)), C.c_float(1.0 / self.world),
             C.c_float(0.0 if lr_dev is not None else float(lr)), lr_dev, C.c_float(b1), C.c_float(b2),
-            C.c_float(g['eps']), None, _native.stream_ptr()))
+            C.c_float(g['eps']), None, C.byref(self.peer.struct) if self.peer is not None else None,
+            _native.ptr(self.gflat), self.gflat.numel(), _native.stream_ptr()))
         self.pack_heads()
 
     def loss_means(self, n_mb):
@@ -979,9 +997,13 @@ def train(data):
     # multi-GPU: capturing the NCCL all-reduce inside one big graph hung on this stack (torch 2.11 / NCCL 2.28); ranks > 1
     # use per-segment graphs around an ordinary all-reduce call instead (see `segmented`)
     want_graph = bool(getattr(config, 'cuda_graph_train', getattr(config, 'cuda_graph', False)))
-    graphable = want_graph and data.grad_bucket is None and \
+    # an NCCL call inside the update loop (autograd path on several ranks, or the hand-written update without peer
+    # memory) keeps the update out of ONE graph; with the peer all-reduce fused into pb_clip_adam_peer there is none
+    mu = getattr(data, 'manual_update', None)
+    nccl_in_loop = data.grad_bucket is not None and not (mu is not None and (mu.world == 1 or mu.peer is not None))
+    graphable = want_graph and not nccl_in_loop and \
         config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
-    segmented = want_graph and data.grad_bucket is not None and \
+    segmented = want_graph and nccl_in_loop and \
         config.target_kl is None and experience.lstm_h is None and data.train_graph_state >= 0
     if segmented and data.train_graph_state >= 1:
         if data.train_segments is None:

@@ -12,6 +12,7 @@
 // rollout-time policy kernel and pb_mlp_tail_backward consume, plus the TF32-rounded encoder weight, in one launch
 // (the ATen formulation is 2 fills + 4 strided copies + 3 elementwise kernels per optimizer step).
 #include "pb_common.cuh"
+#include "peer.cuh"
 
 namespace {
 
@@ -25,6 +26,9 @@ struct AdamArgs {
     const float* lr_dev;
     float beta1, beta2, eps;
     float* total_norm_out;
+    pb_peer_comm peer;      // world <= 1: no exchange
+    float* flat;            // the flat gradient buffer all `grad` pointers lie in (peer exchange only)
+    int64_t flat_n;
 };
 
 __global__ void __launch_bounds__(CA_THREADS) k_clip_adam(AdamArgs a) {
@@ -32,6 +36,9 @@ __global__ void __launch_bounds__(CA_THREADS) k_clip_adam(AdamArgs a) {
     __shared__ float s_coef;
     __shared__ float s_step_size[CA_MAX_TENSORS], s_bc2_sqrt[CA_MAX_TENSORS];
     const int tid = threadIdx.x;
+
+    // ---- multi-GPU: sum the flat gradient buffer over all ranks through NVLink peer memory (peer.cuh)
+    if (a.peer.world > 1) pb_peer_allreduce_sum(a.peer, a.flat, a.flat_n);
 
     // ---- pass 1: global L2 norm of the (scaled) gradients
     float ss = 0.f;
@@ -115,6 +122,13 @@ __global__ void __launch_bounds__(256) k_pack_heads(const float* __restrict__ w_
 extern "C" int pb_clip_adam(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale,
                             float lr, const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
                             void* stream) {
+    return pb_clip_adam_peer(tensors, n_tensors, max_grad_norm, grad_scale, lr, lr_dev, beta1, beta2, eps, total_norm_out,
+                             nullptr, nullptr, 0, stream);
+}
+
+extern "C" int pb_clip_adam_peer(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale,
+                                 float lr, const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
+                                 const pb_peer_comm* comm, float* grad_flat, int64_t grad_flat_numel, void* stream) {
     PB_REQUIRE(tensors && n_tensors >= 1 && n_tensors <= CA_MAX_TENSORS, PB_ERR_INVALID,
                "pb_clip_adam: 1..%d tensors", CA_MAX_TENSORS);
     AdamArgs a{};
@@ -139,6 +153,18 @@ extern "C" int pb_clip_adam(const pb_adam_tensor* tensors, int32_t n_tensors, fl
     a.beta2 = beta2;
     a.eps = eps;
     a.total_norm_out = total_norm_out;
+    if (comm && comm->world > 1) {
+        PB_REQUIRE(comm->world <= PB_PEER_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world && comm->epoch &&
+                       grad_flat && grad_flat_numel >= 1 && grad_flat_numel <= comm->capacity,
+                   PB_ERR_INVALID, "pb_clip_adam_peer: bad communicator or flat gradient buffer");
+        for (int r = 0; r < comm->world; ++r) PB_REQUIRE(comm->base[r], PB_ERR_INVALID, "pb_clip_adam_peer: peer %d not mapped", r);
+        for (int k = 0; k < n_tensors; ++k)
+            PB_REQUIRE(tensors[k].grad >= grad_flat && tensors[k].grad + tensors[k].numel <= grad_flat + grad_flat_numel,
+                       PB_ERR_INVALID, "pb_clip_adam_peer: gradient %d lies outside the flat buffer", k);
+        a.peer = *comm;
+        a.flat = grad_flat;
+        a.flat_n = grad_flat_numel;
+    }
     k_clip_adam<<<1, CA_THREADS, 0, (cudaStream_t)stream>>>(a);
     PB_LAUNCH_CHECK();
     return PB_OK;

@@ -1,0 +1,57 @@
+// peer.cuh -- device side of the NVLink peer-memory all-reduce (see peer.cu); included by the optimizer kernel.
+#pragma once
+#include <string.h>
+
+#include "pb_common.cuh"
+
+constexpr int PB_PEER_HEADER_BYTES = 1024;   // 8 flag lines of 128 B
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pb_st_release_sys_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t pb_ld_acquire_sys_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float pb_ld_relaxed_sys_f32(const float* p) {   // peer data: never from a stale L1 line
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One CTA (any size that is a multiple of 32): flat[0..n) <- sum over ranks, in rank order (bit-identical everywhere).
+__device__ __forceinline__ void pb_peer_allreduce_sum(const pb_peer_comm& c, float* flat, int64_t n) {
+    if (c.world <= 1) return;
+    __shared__ uint64_t s_epoch;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) s_epoch = *c.epoch + 1;
+    __syncthreads();
+    const uint64_t e = s_epoch;
+    const int64_t slot_off = PB_PEER_HEADER_BYTES / 4 + (int64_t)(e & 1) * c.capacity;
+    float* mine = reinterpret_cast<float*>(c.base[c.rank]) + slot_off;
+    for (int64_t i = tid; i < n; i += nt) mine[i] = flat[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < c.world) {   // raise my flag in every rank's buffer (mine included)
+        uint64_t* flag = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(c.base[tid]) + 128 * c.rank);
+        pb_st_release_sys_u64(flag, e);
+        // ... and wait for rank `tid`'s flag in my buffer
+        const uint64_t* theirs = reinterpret_cast<const uint64_t*>(reinterpret_cast<const char*>(c.base[c.rank]) + 128 * tid);
+        const long long t0 = clock64();
+        while (pb_ld_acquire_sys_u64(theirs) < e) {
+            if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a peer died; do not hang the box
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    for (int64_t i = tid; i < n; i += nt) {
+        float s = 0.f;
+        for (int r = 0; r < c.world; ++r) s += pb_ld_relaxed_sys_f32(reinterpret_cast<const float*>(c.base[r]) + slot_off + i);
+        flat[i] = s;
+    }
+    __syncthreads();
+    if (tid == 0) *c.epoch = e;
+}
+#endif

@@ -5,7 +5,11 @@ The reference has no distributed code.  Envs are independent,
 minibatching are rank-local (identical to running the reference per shard); the policy is replicated and its
 gradients are averaged with a single NCCL all-reduce over one flat fp32 bucket (NVLink 5 / NVSwitch; the bucket
 is tens of KB for the MLP, 6.7 MB for NatureCNN -- latency-bound, so exactly one collective, no bucketing).
+
+For the hand-written update (clean_pufferl._DefaultMLPUpdate) the exchange is fused into the optimizer kernel over NVLink
+peer memory (``PeerComm`` / csrc/peer.cu): no NCCL call per step, so the update is ONE CUDA graph at any world size.
 """
+import ctypes as C
 import os
 
 import torch
@@ -83,3 +87,61 @@ def broadcast_parameters(module, src=0):
             dist.broadcast(p.data, src)
         for b in module.buffers():
             dist.broadcast(b.data, src)
+
+
+class PeerComm:
+    """NVLink peer-memory communicator for small flat fp32 buffers (csrc/peer.cu): every rank allocates one buffer with
+    the C ABI (cudaMalloc + cudaIpcGetMemHandle), the 64-byte handles travel through torch.distributed once, every rank
+    maps all peers.  ``struct`` is the pb_peer_comm the kernels take by value.  Single node only."""
+
+    def __init__(self, capacity_floats, group=None):
+        from pufferlib_b200 import _native
+        if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            raise RuntimeError('PeerComm needs an initialised process group with more than one rank')
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError('PeerComm: at most 8 ranks (one NVSwitch node)')
+        lib = _native.lib()
+        self.capacity = int(capacity_floats)
+        nbytes = lib.pb_peer_buffer_bytes(self.capacity)
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        _native.check(lib.pb_peer_alloc(nbytes, C.byref(own), handle))
+        self._own = own
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._opened = []
+        bases = (C.c_void_p * 8)()
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                bases[r] = own.value
+            else:
+                p = C.c_void_p()
+                _native.check(lib.pb_peer_open(C.create_string_buffer(h, 64), C.byref(p)))
+                self._opened.append(p)
+                bases[r] = p.value
+        self.epoch = torch.zeros(1, dtype=torch.int64, device='cuda')
+        self.struct = _native.PeerComm(world=self.world, rank=self.rank, base=bases, epoch=self.epoch.data_ptr(),
+                                       capacity=self.capacity)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)          # every buffer is zeroed and mapped before the first flag is raised
+
+    def all_reduce_(self, flat):
+        """In-place sum of a contiguous fp32 CUDA tensor over all ranks (one single-CTA kernel, graph-capturable)."""
+        from pufferlib_b200 import _native
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() <= self.capacity
+        _native.check(_native.lib().pb_peer_allreduce(C.byref(self.struct), _native.ptr(flat), flat.numel(),
+                                                      _native.stream_ptr()))
+        return flat
+
+    def close(self):
+        from pufferlib_b200 import _native
+        lib = _native.lib()
+        torch.cuda.synchronize()
+        for p in self._opened:
+            lib.pb_peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            if dist.is_initialized():
+                dist.barrier()             # nobody still has the buffer mapped / in use
+            lib.pb_peer_free(self._own)
+            self._own = None
