@@ -231,6 +231,27 @@ int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_
                          int32_t hidden_size, float* dpre, float* grads_out, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* -- fused minibatch update (forward + PPO loss + backward) -------------------------------------------------------------
+ * One minibatch of clean_pufferl.train (clean_pufferl.py:186-244) for models.Default (pufferlib/models.py:12-62) with
+ * 128 fp32 input features, 128 hidden units and <= 7 actions, up to and including the gradients, in ONE persistent
+ * tcgen05 kernel (+ a small deterministic partial-sum kernel): encoder GEMM and dW_enc = dPre^T x on the 5th-gen tensor
+ * cores (kind::tf32, fp32 accumulation in TMEM), heads / pb_ppo_loss row math / ReLU backward in the epilogue warps.
+ * The observations are read from HBM once; hidden and dPre never leave the SM.
+ *   x            n_slabs slabs of slab_rows rows x 128 features, row stride ldx floats; slab s starts slab_stride_rows rows
+ *                after slab s-1 (the zero-copy minibatch view of the time-major rollout; n_slabs = 1: a plain matrix)
+ *   w_heads/b_heads  the 8-row padded head matrix of pb_pack_heads (n_act logit rows | value row | zeros)
+ *   actions .. old_values   per-row tensors in slab-major order [n_slabs * slab_rows] (advantages already normalised)
+ *   grad_flat    [128*128 + 8*128 + 128 + 8]: dW_enc | dW_heads | db_enc | db_heads  (what pb_clip_adam consumes)
+ *   stats8       the six loss sums of pb_ppo_loss (zeroed here)
+ *   dbg_*        nullable dumps of relu(h) [M][128], dPre [M][128], dOut [M][8] for validation. */
+size_t pb_mlp_update_workspace_bytes(void);
+int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
+                        const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
+                        const int64_t* actions, const float* old_logprobs, const float* advantages, const float* returns,
+                        const float* old_values, int32_t n_act, float clip_coef, int32_t clip_vloss, float vf_clip_coef,
+                        float vf_coef, float ent_coef, float* grad_flat, double* stats8, void* workspace,
+                        size_t workspace_bytes, float* dbg_hidden, float* dbg_dpre, float* dbg_dout, void* stream);
+
 /* -- optimizer step for small policies -------------------------------------------------------------------------------
  * clip_grad_norm_ + Adam of clean_pufferl.py:240-244 (torch.nn.utils.clip_grad_norm_(params, max_grad_norm);
  * optimizer.step() with torch.optim.Adam(eps=1e-5)) in ONE single-CTA launch for up to 1 Mi parameters in up to 8

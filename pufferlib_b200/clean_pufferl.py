@@ -186,6 +186,11 @@ def slab_row_index(num_envs, horizon, num_minibatches, bptt_horizon):
     return rows.transpose(1, 0, 2).reshape(num_minibatches, g_ * r_)
 
 
+# the fused tcgen05 minibatch-update kernel (csrc/mlp_update.cu) is the default where it applies; config.fused_update
+# overrides
+FUSED_UPDATE_DEFAULT = True
+
+
 class _DefaultMLPUpdate:
     """The minibatch update of clean_pufferl.py:186-244 for models.Default + the fused PPO loss, written out by hand
     instead of through autograd: with 17k parameters and 524k-row minibatches the update is a fixed chain of seven
@@ -253,6 +258,7 @@ class _DefaultMLPUpdate:
                                                  st['step'].data_ptr(), g.data_ptr(), p.numel())
         self._keep = (params, grads)
         self._state_ptrs = self._current_state_ptrs()
+        self.fused_ws, self.used_fused = None, False
         self.rows = 0
         self.stats = None
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and
@@ -305,15 +311,44 @@ class _DefaultMLPUpdate:
             _native.ptr(m.value_head.bias), self.n_act, self.hid, _native.ptr(self.w_cat), _native.ptr(self.b_cat),
             None, None, 0, _native.stream_ptr()))
 
+    def _fused_ok(self, x, config):
+        """pb_mlp_update_fused (csrc/mlp_update.cu): fp32 observations with exactly 128 features in equally spaced row
+        slabs -- the C2 / C5 workload.  Everything else takes the kernel chain below."""
+        return (bool(getattr(config, 'fused_update', FUSED_UPDATE_DEFAULT)) and x.dtype == torch.float32 and x.shape[2] == 128
+                and self.hid == 128 and x.stride(2) == 1 and x.stride(1) % 4 == 0 and x.data_ptr() % 16 == 0
+                and (x.shape[0] == 1 or (x.stride(0) % x.stride(1) == 0 and x.stride(0) >= x.shape[1] * x.stride(1))))
+
     @torch.no_grad()
     def forward_backward(self, k, n_stats, obs, slab_form, atn, log_probs, adv, ret, val, config):
         """obs: slab view [G, R, *obs] (slab_form) or [M, *obs]; the rest [M].  Statistics of this minibatch go to
         row k of self.stats."""
         x = obs if slab_form else obs.reshape(1, atn.numel(), -1)
-        x = x.flatten(2).float()
+        x = x.flatten(2)
+        if self._fused_ok(x, config):
+            # ONE tcgen05 kernel: x read once, hidden / dPre stay on the SM, gradients land in self.gflat
+            g_, r_, _ = x.shape
+            lib = _native.lib()
+            if self.stats is None or self.stats.shape[0] != n_stats:
+                self.stats = torch.zeros(n_stats, 8, dtype=torch.float64, device=self.gflat.device)
+            if self.fused_ws is None:
+                self.fused_ws = torch.empty(lib.pb_mlp_update_workspace_bytes(), dtype=torch.uint8, device=self.gflat.device)
+            self.mb_rows = g_ * r_
+            m_ = self.model
+            _native.check(lib.pb_mlp_update_fused(
+                _native.ptr(x), x.stride(1), r_, (x.stride(0) // x.stride(1)) if g_ > 1 else r_, g_,
+                _native.ptr(m_.encoder.weight), _native.ptr(m_.encoder.bias), _native.ptr(self.w_cat), _native.ptr(self.b_cat),
+                _native.ptr(atn.reshape(-1)), _native.ptr(log_probs.reshape(-1)), _native.ptr(adv.reshape(-1)),
+                _native.ptr(ret.reshape(-1)), _native.ptr(val.reshape(-1)), self.n_act, C.c_float(config.clip_coef),
+                int(bool(config.clip_vloss)), C.c_float(config.vf_clip_coef), C.c_float(config.vf_coef),
+                C.c_float(config.ent_coef), _native.ptr(self.gflat), C.c_void_p(self.stats.data_ptr() + 64 * k),
+                _native.ptr(self.fused_ws), self.fused_ws.numel(), None, None, None, _native.stream_ptr()))
+            self.used_fused = True
+            return
+        x = x.float()
         g_, r_, f_ = x.shape
         m, hid = g_ * r_, self.hid
         self._buffers(m, n_stats)
+        self.mb_rows = m
         model, lib, s = self.model, _native.lib(), _native.stream_ptr()
         w_enc, b_enc = model.encoder.weight, model.encoder.bias
         for g in range(g_):
@@ -360,7 +395,7 @@ class _DefaultMLPUpdate:
     def loss_means(self, n_mb):
         """[policy, value, entropy, old_kl, kl, clipfrac]: per-minibatch means / n_mb, summed over all minibatches
         (the accumulation of clean_pufferl.py:249-254)."""
-        tot = self.stats.sum(0)[:6] / (self.rows * n_mb)
+        tot = self.stats.sum(0)[:6] / (self.mb_rows * n_mb)
         tot[1] *= 0.5
         return tot.float()
 

@@ -1,4 +1,4 @@
-// mlp_update_fused.cu -- the whole minibatch forward + PPO loss + backward of models.Default in ONE persistent
+// mlp_update.cu -- the whole minibatch forward + PPO loss + backward of models.Default in ONE persistent
 // tcgen05 kernel: the observations are read from HBM once, `hidden` / `dPre` never leave the SM.
 //
 // Replaces, per minibatch of clean_pufferl.train (/root/reference/clean_pufferl.py:186-244; policy =
@@ -30,22 +30,11 @@
 // Descriptor encodings were validated on hardware with csrc/experimental/umma_probe.cu (tests/experimental/
 // check_umma_probe.py).  Every mbarrier wait is bounded (tma.cuh: __trap instead of a hang).
 #include <cuda.h>
-#include <cuda_runtime.h>
-#include <stdarg.h>
-#include <stdint.h>
-#include <stdio.h>
 
-#include "../tma.cuh"
+#include "pb_common.cuh"
+#include "tma.cuh"
 
 namespace {
-
-char g_err3[512] = "";
-void set_err3(const char* fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(g_err3, sizeof(g_err3), fmt, ap);
-    va_end(ap);
-}
 
 constexpr int TILE_M = 128, HID = 128, FEAT = 128, NO = 8;
 constexpr int KBLK = 32;                               // floats per 128-byte swizzle row
@@ -577,11 +566,8 @@ int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t row
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_err3("cuTensorMapEncodeTiled failed: %d", (int)r);
-        return -1;
-    }
-    return 0;
+    PB_REQUIRE(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return PB_OK;
 }
 
 int g_sms = 0;
@@ -596,51 +582,40 @@ int num_sms() {
 
 }  // namespace
 
-extern "C" const char* pbx_muf_last_error(void) { return g_err3; }
-
-// workspace: per-CTA partials ([grid][128][128] + [grid][1160] floats), grid = min(tiles, SMs)
-extern "C" size_t pbx_mlp_update_fused_workspace_bytes(void) {
+extern "C" size_t pb_mlp_update_workspace_bytes(void) {
     return (size_t)num_sms() * (FEAT * HID + TAIL) * sizeof(float);
 }
 
-// One minibatch of the models.Default update up to (and including) the gradients:
-//   x            n_slabs slabs of slab_rows rows x 128 fp32 features, row stride ldx floats, slab s starts at row
-//                s * slab_stride_rows (the zero-copy minibatch view of the time-major rollout; n_slabs = 1 for a plain matrix)
-//   w_enc [128][128], b_enc [128], w_heads [8][128] (n_act logit rows | value row | zeros), b_heads [8]
-//   per-row tensors in slab-major order [n_slabs * slab_rows]: actions, old_logprobs, advantages, returns, old_values
-//   gflat [128*128 + 8*128 + 128 + 8]: dW_enc | dW_heads | db_enc | db_heads;  stats8: the sums pb_ppo_loss produces
-//   dbg_*: nullable dumps of relu(h), dPre, dOut for validation.
-extern "C" int pbx_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
-                                    const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
-                                    const int64_t* actions, const float* old_logprobs, const float* advantages,
-                                    const float* returns, const float* old_values, int32_t n_act, float clip_coef,
-                                    int32_t clip_vloss, float vf_clip_coef, float vf_coef, float ent_coef, float* gflat,
-                                    double* stats8, void* workspace, size_t workspace_bytes, float* dbg_hidden,
-                                    float* dbg_dpre, float* dbg_dout, void* stream) {
-    if (!x || !w_enc || !b_enc || !w_heads || !b_heads || !actions || !old_logprobs || !advantages || !returns || !gflat ||
-        !stats8 || !workspace || slab_rows < 1 || n_slabs < 1 || n_act < 1 || n_act > 7 || (clip_vloss && !old_values) ||
-        ldx < FEAT || ldx % 4 != 0 || ((uintptr_t)x & 15) || ((uintptr_t)w_enc & 15) ||
-        (n_slabs > 1 && slab_stride_rows < slab_rows) || workspace_bytes < pbx_mlp_update_fused_workspace_bytes() ||
-        (dbg_hidden && !dbg_dpre)) {
-        set_err3("pbx_mlp_update_fused: bad arguments");
-        return -1;
-    }
+extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
+                                   const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
+                                   const int64_t* actions, const float* old_logprobs, const float* advantages,
+                                   const float* returns, const float* old_values, int32_t n_act, float clip_coef,
+                                   int32_t clip_vloss, float vf_clip_coef, float vf_coef, float ent_coef, float* grad_flat,
+                                   double* stats8, void* workspace, size_t workspace_bytes, float* dbg_hidden,
+                                   float* dbg_dpre, float* dbg_dout, void* stream) {
+    PB_REQUIRE(x && w_enc && b_enc && w_heads && b_heads && actions && old_logprobs && advantages && returns && grad_flat &&
+                   stats8 && workspace,
+               PB_ERR_INVALID, "pb_mlp_update_fused: null pointer");
+    PB_REQUIRE(slab_rows >= 1 && n_slabs >= 1 && n_act >= 1 && n_act <= 7 && (!clip_vloss || old_values), PB_ERR_INVALID,
+               "pb_mlp_update_fused: bad sizes (slab_rows %lld, n_slabs %d, n_act %d)", (long long)slab_rows, n_slabs, n_act);
+    PB_REQUIRE(ldx >= FEAT && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w_enc & 15) == 0, PB_ERR_INVALID,
+               "pb_mlp_update_fused: x / w_enc must be 16-byte aligned, ldx a multiple of 4 floats");
+    PB_REQUIRE(n_slabs == 1 || slab_stride_rows >= slab_rows, PB_ERR_INVALID, "pb_mlp_update_fused: slabs overlap");
+    PB_REQUIRE(workspace_bytes >= pb_mlp_update_workspace_bytes(), PB_ERR_INVALID, "pb_mlp_update_fused: workspace too small");
+    PB_REQUIRE(!dbg_hidden || dbg_dpre, PB_ERR_INVALID, "pb_mlp_update_fused: dbg_hidden needs dbg_dpre");
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn ||
-        qr != cudaDriverEntryPointSuccess) {
-        set_err3("cuTensorMapEncodeTiled entry point not available");
-        return -2;
-    }
+    PB_REQUIRE(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+                   qr == cudaDriverEntryPointSuccess,
+               PB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     const int64_t tiles_per_slab = (slab_rows + TILE_M - 1) / TILE_M;
     const int64_t n_tiles = tiles_per_slab * n_slabs;
     const int64_t map_rows = (int64_t)(n_slabs - 1) * slab_stride_rows + slab_rows;
-    if (n_tiles > 0x7FFFFFFF || map_rows > 0x7FFFFFFF) {
-        set_err3("pbx_mlp_update_fused: too many rows");
-        return -1;
-    }
+    PB_REQUIRE(n_tiles <= 0x7FFFFFFF && map_rows <= 0x7FFFFFFF, PB_ERR_UNSUPPORTED, "pb_mlp_update_fused: too many rows");
     alignas(64) CUtensorMap map_x, map_w;
-    if (make_map2((EncodeTiledFn)fn, &map_x, x, map_rows, ldx) || make_map2((EncodeTiledFn)fn, &map_w, w_enc, HID, FEAT)) return -3;
+    int rc = make_map2((EncodeTiledFn)fn, &map_x, x, map_rows, ldx);
+    if (rc == PB_OK) rc = make_map2((EncodeTiledFn)fn, &map_w, w_enc, HID, FEAT);
+    if (rc != PB_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = n_tiles < num_sms() ? (int)n_tiles : num_sms();
     FusedParams p;
@@ -650,20 +625,18 @@ extern "C" int pbx_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_ro
     p.clip = clip_coef; p.vclip = vf_clip_coef; p.vf_coef = vf_coef; p.ent_coef = ent_coef; p.clip_vloss = clip_vloss;
     p.part_dw = (float*)workspace; p.part_tail = (float*)workspace + (size_t)num_sms() * FEAT * HID;
     p.stats = stats8; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
-    cudaError_t e = cudaMemsetAsync(stats8, 0, 8 * sizeof(double), s);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_benc, b_enc, sizeof(float) * HID, 0, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_bh, b_heads, sizeof(float) * NO, 0, cudaMemcpyDeviceToDevice, s);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_mlp_update_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-    if (e == cudaSuccess) {
-        k_mlp_update_fused<<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
-        k_update_reduce<<<(FEAT * HID + TAIL + 63) / 64, 256, 0, s>>>(p.part_dw, p.part_tail, grid, gflat);
-        e = cudaGetLastError();
+    PB_CUDA(cudaMemsetAsync(stats8, 0, 8 * sizeof(double), s));
+    PB_CUDA(cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s));
+    PB_CUDA(cudaMemcpyToSymbolAsync(c_benc, b_enc, sizeof(float) * HID, 0, cudaMemcpyDeviceToDevice, s));
+    PB_CUDA(cudaMemcpyToSymbolAsync(c_bh, b_heads, sizeof(float) * NO, 0, cudaMemcpyDeviceToDevice, s));
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        attr_set = true;
     }
-    if (e != cudaSuccess) {
-        set_err3("pbx_mlp_update_fused: %s", cudaGetErrorString(e));
-        return -4;
-    }
-    return 0;
+    k_mlp_update_fused<<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
+    PB_LAUNCH_CHECK();
+    k_update_reduce<<<(FEAT * HID + TAIL + 63) / 64, 256, 0, s>>>(p.part_dw, p.part_tail, grid, grad_flat);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
 }

@@ -1,4 +1,4 @@
-"""Hardware check of the fused tcgen05 minibatch-update kernel (csrc/experimental/mlp_update_fused.cu).
+"""Hardware check of the fused tcgen05 minibatch-update kernel (csrc/mlp_update.cu).
 
 Stage-wise: every stage's reference is computed from the kernel's OWN previous-stage dump (hidden -> dOut -> dPre ->
 gradients), so a mismatch names the stage that is wrong; then an end-to-end comparison against the validated chain
@@ -17,13 +17,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, REPO)
 from pufferlib_b200 import _native  # noqa: E402
 
-exp = C.CDLL(os.path.join(REPO, 'pufferlib_b200', 'libpuffer_b200_exp.so'))
-exp.pbx_mlp_update_fused.restype = C.c_int
-exp.pbx_mlp_update_fused.argtypes = ([C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32] + [C.c_void_p] * 9 +
-                                     [C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_float] +
-                                     [C.c_void_p] * 3 + [C.c_size_t] + [C.c_void_p] * 4)
-exp.pbx_mlp_update_fused_workspace_bytes.restype = C.c_size_t
-exp.pbx_muf_last_error.restype = C.c_char_p
+lib = _native.lib()
 CFG = (0.1, 1, 0.1, 0.5, 0.01)      # clip, clip_vloss, vclip, vf_coef, ent_coef
 
 
@@ -44,17 +38,16 @@ def fused(xbuf, ldx, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat
     m = slab_rows * n_slabs
     gflat = torch.full((128 * 128 + 8 * 128 + 128 + 8,), float('nan'), device=dev)
     stats = torch.zeros(8, dtype=torch.float64, device=dev)
-    ws = torch.empty(exp.pbx_mlp_update_fused_workspace_bytes(), dtype=torch.uint8, device=dev)
+    ws = torch.empty(lib.pb_mlp_update_workspace_bytes(), dtype=torch.uint8, device=dev)
     dh = dp = do = None
     if debug:
         dh = torch.full((m, 128), float('nan'), device=dev)
         dp = torch.full((m, 128), float('nan'), device=dev)
         do = torch.full((m, 8), float('nan'), device=dev)
-    rc = exp.pbx_mlp_update_fused(ptr(xbuf), ldx, slab_rows, slab_stride, n_slabs, ptr(w_enc), ptr(b_enc), ptr(w_cat), ptr(b_cat),
+    _native.check(lib.pb_mlp_update_fused(ptr(xbuf), ldx, slab_rows, slab_stride, n_slabs, ptr(w_enc), ptr(b_enc), ptr(w_cat), ptr(b_cat),
                                   ptr(act), ptr(olp), ptr(adv), ptr(ret), ptr(oval), n_act, CFG[0], CFG[1], CFG[2], CFG[3],
                                   CFG[4], ptr(gflat), ptr(stats), ptr(ws), ws.numel(), ptr(dh), ptr(dp), ptr(do),
-                                  C.c_void_p(torch.cuda.current_stream().cuda_stream))
-    assert rc == 0, exp.pbx_muf_last_error().decode()
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return gflat, stats, dh, dp, do
 
 

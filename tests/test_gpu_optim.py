@@ -87,7 +87,7 @@ def test_manual_update_matches_autograd_update():
         vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200)
         torch.manual_seed(0)
         pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=7).cuda()
-        data = clean_pufferl.create(make_config(n, h, env='breakout', manual_update=manual), vec, pol)
+        data = clean_pufferl.create(make_config(n, h, env='breakout', manual_update=manual, fused_update=False), vec, pol)
         clean_pufferl.evaluate(data)
         clean_pufferl.train(data)
         params[manual] = [p.detach().cpu().clone() for p in pol.parameters()]
@@ -104,3 +104,77 @@ def test_manual_update_matches_autograd_update():
     diff = max(float((a - b).abs().max()) for a, b in zip(params[True], params[False]))
     assert diff <= 2e-5, diff
     assert np.allclose(losses[True], losses[False], rtol=1e-4, atol=1e-6), (losses[True], losses[False])
+
+
+def test_fused_update_kernel_matches_kernel_chain():
+    """train() through pb_mlp_update_fused (ONE tcgen05 kernel per minibatch: csrc/mlp_update.cu) vs the kernel chain it
+    replaces (cuBLAS GEMMs + pb_ppo_loss + pb_mlp_tail_backward + split-K dW): same rollout, same minibatches.  Both
+    compute the dense products in TF32 (operands truncated by the tensor core), so gradients agree to TF32 noise; the
+    statistics come from the same row math."""
+    import pufferlib_b200.vector as pvec
+    from pufferlib_b200 import clean_pufferl, models
+    from pufferlib_b200.environments import ocean
+    from pufferlib_b200.frameworks import cleanrl
+    from test_gpu_experience import make_config
+    n, h = 256, 32          # 2 minibatches of 4096 rows = 32 tiles of 128 rows; slabs of bptt * n = 2048 rows
+    grads, losses, params, used = {}, {}, {}, {}
+    for fused in (True, False):
+        vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200)
+        torch.manual_seed(0)
+        pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=7).cuda()
+        cfg = make_config(n, h, env='breakout', manual_update=True, fused_update=fused)
+        cfg.update_epochs = 1
+        cfg.minibatch_size = n * h          # ONE minibatch: gflat after train() is its gradient
+        data = clean_pufferl.create(cfg, vec, pol)
+        clean_pufferl.evaluate(data)
+        clean_pufferl.train(data)
+        mu = data.manual_update
+        used[fused] = mu.used_fused
+        grads[fused] = mu.gflat.detach().cpu().clone()
+        params[fused] = torch.cat([p.detach().reshape(-1).cpu() for p in pol.parameters()])
+        losses[fused] = np.array([data.losses.policy_loss, data.losses.value_loss, data.losses.entropy,
+                                  data.losses.approx_kl, data.losses.clipfrac])
+        clean_pufferl.evaluate(data)
+        clean_pufferl.train(data)
+        assert np.isfinite(data.losses.policy_loss)
+        clean_pufferl.close(data)
+    assert used[True] and not used[False]
+    ga, gb = grads[True], grads[False]
+    sections = {'dW_enc': slice(0, 128 * 128), 'dW_heads': slice(128 * 128, 128 * 128 + 1024),
+                'db_enc': slice(128 * 128 + 1024, 128 * 128 + 1152), 'db_heads': slice(128 * 128 + 1152, None)}
+    for name, sl in sections.items():
+        err = float((ga[sl] - gb[sl]).abs().max()) / (float(gb[sl].abs().max()) + 1e-30)
+        assert err < 5e-3, (name, err)
+    assert np.allclose(losses[True], losses[False], rtol=2e-4, atol=1e-6), (losses[True], losses[False])
+    # one Adam step of size lr = 2.5e-4 from nearly identical gradients
+    assert float((params[True] - params[False]).abs().max()) < 2.5e-4
+    assert float((params[True] - params[False]).abs().mean()) < 2e-6
+
+
+def test_fused_update_kernel_inside_train_graph():
+    """The fused update inside the captured train graph (cudaMemcpyToSymbolAsync nodes + tensor-map kernel parameters)
+    replays to the same parameters as eager execution."""
+    import pufferlib_b200.vector as pvec
+    from pufferlib_b200 import clean_pufferl, models
+    from pufferlib_b200.environments import ocean
+    from pufferlib_b200.frameworks import cleanrl
+    from test_gpu_experience import make_config
+    n, h = 128, 32
+    out = {}
+    for graph in (False, True):
+        vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200)
+        torch.manual_seed(0)
+        pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=7).cuda()
+        cfg = make_config(n, h, env='breakout', manual_update=True, fused_update=True, cuda_graph_train=graph,
+                          cuda_graph_rollout=False)
+        data = clean_pufferl.create(cfg, vec, pol)
+        for _ in range(3):
+            clean_pufferl.evaluate(data)
+            clean_pufferl.train(data)
+        assert data.manual_update.used_fused
+        assert (data.train_graph_state == 2) == graph
+        out[graph] = torch.cat([p.detach().reshape(-1).cpu() for p in pol.parameters()])
+        clean_pufferl.close(data)
+    # same program, eager vs replayed: identical up to the GAE look-back's run-to-run fp32 noise (see
+    # test_graphed_training_matches_eager_training)
+    assert float((out[True] - out[False]).abs().max()) < 1e-4
