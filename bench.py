@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra-configs', action='store_true', help='skip the C3 / C4 per-kernel rooflines')
     ap.add_argument('--minibatches', type=int, default=4, help='batch_size / minibatch_size (reference ratio: 4)')
     ap.add_argument('--epochs', type=int, default=4)
     ap.add_argument('--kernels-only', action='store_true', help='skip the PPO loop; report the per-kernel rooflines')
@@ -219,7 +220,9 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                                  _native.stream_ptr()))
     t_gae = time_launches(gae, 16)
     del sets
-    out['gae'] = dict(kernel='k_gae<16>', bytes_per_launch=n * h * 20, seconds=t_gae, launches_per_step=1)
+    # pb_gae's dispatch (csrc/gae.cu): the single-pass tile kernel for H in {128, 256, 512} and N % 4 == 0, else the general one
+    gae_kernel = 'k_gae_fast' if (h in (128, 256, 512) and n % 4 == 0) else 'k_gae'
+    out['gae'] = dict(kernel=gae_kernel, bytes_per_launch=n * h * 20, seconds=t_gae, launches_per_step=1)
 
     # minibatch gather of the observations: read + write of every row
     def gather(i):
@@ -283,6 +286,36 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
         out['ppo_loss'] = dict(kernel='k_ppo_loss', seconds=t_loss, bytes_per_launch=mb * (8 * n_act + 32 + 4),
                                launches_per_step=args.minibatches * args.epochs)
         del hid, douts, dpre, outs, gouts
+        # the fused tcgen05 minibatch update (forward + loss + backward in one kernel): algorithmic bytes = the observation
+        # rows (read once) + 24 B of per-row scalars; launched on zero-copy slab views of the rollout like train() does
+        mu = getattr(data, 'manual_update', None)
+        if mu is not None and getattr(mu, 'used_fused', False) and o == 512:
+            from pufferlib_b200 import clean_pufferl as cp_
+            nm = args.minibatches
+            layout = cp_.slab_layout(n, h, nm, 16)
+            if layout is not None:
+                g_, r_ = layout
+                xs = [exp.obs.view(g_, nm, r_, 128)[:, k] for k in range(nm)]
+                ws = torch.empty(lib.pb_mlp_update_workspace_bytes(), dtype=torch.uint8, device='cuda')
+                gfl = torch.empty(128 * 128 + 8 * 128 + 128 + 8, device='cuda')
+                st8 = torch.zeros(8, dtype=torch.float64, device='cuda')
+                model = data.policy.policy
+                w_cat, b_cat = model.head_matrix()
+
+                def upd(i):
+                    x = xs[i % nm]
+                    _native.check(lib.pb_mlp_update_fused(
+                        _native.ptr(x), 128, r_, x.stride(0) // 128 if g_ > 1 else r_, g_, _native.ptr(model.encoder.weight),
+                        _native.ptr(model.encoder.bias), _native.ptr(w_cat), _native.ptr(b_cat), _native.ptr(acts),
+                        _native.ptr(f32[0]), _native.ptr(f32[1]), _native.ptr(f32[2]), _native.ptr(f32[3]), n_act, C.c_float(0.1), 1,
+                        C.c_float(0.1), C.c_float(0.5), C.c_float(0.01), _native.ptr(gfl), _native.ptr(st8), _native.ptr(ws),
+                        ws.numel(), None, None, None, _native.stream_ptr()))
+                with torch.no_grad():
+                    upd(0)
+                    t_upd = time_launches(upd, 8)
+                out['mlp_update'] = dict(kernel='k_mlp_update_fused (tcgen05) + k_update_reduce', seconds=t_upd,
+                                         bytes_per_launch=mb * (512 + 28), launches_per_step=nm * args.epochs,
+                                         tf32_tflops=round(2 * 2 * mb * 128 * 128 / t_upd / 1e12, 1))
     for k, v in out.items():
         v['achieved'] = v['bytes_per_launch'] / v['seconds'] / 1e9
         v['frac'] = v['achieved'] / peak_gbs
@@ -301,7 +334,8 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
             'peak_source': peak_src, 'unit': 'GB/s', 'frac': round(d['frac'], 4), 'traffic': traffic,
             'algorithmic_bytes_per_launch': d['bytes_per_launch'], 'avg_launch_us': round(d['seconds'] * 1e6, 2)}
     others = {k: {'kernel': v['kernel'], 'achieved': round(v['achieved'], 1), 'frac': round(v['frac'], 4),
-                  'avg_launch_us': round(v['seconds'] * 1e6, 2), 'algorithmic_bytes_per_launch': v['bytes_per_launch']}
+                  'avg_launch_us': round(v['seconds'] * 1e6, 2), 'algorithmic_bytes_per_launch': v['bytes_per_launch'],
+                  'launches_per_step': v['launches_per_step'], **({'tf32_tflops': v['tf32_tflops']} if 'tf32_tflops' in v else {})}
               for k, v in out.items()}
     return roof, others
 
@@ -367,9 +401,29 @@ def run_b200(args):
                'api': 'pufferlib_b200.vector.make(backend=B200.options(host_buffers=True)) + clean_pufferl.evaluate/train'}
         cp.close(hdata)
 
+    # ---- the other single-GPU configs of BASELINE.json (C3 snake: the GAE / obs-write HBM roofline config; C4 pong: the
+    # TMA image pack): per-kernel rooflines only (their full PPO loops are covered by tests/test_gpu_configs.py)
+    extra = {}
+    if world == 1 and not args.no_extra_configs:
+        import copy
+        for key, kw in (('c3_snake', dict(env='snake', num_envs=65536, horizon=256)),
+                        ('c4_pong', dict(env='pong', num_envs=8192, horizon=128))):
+            try:
+                a2 = copy.copy(args)
+                for k_, v_ in kw.items():
+                    setattr(a2, k_, v_)
+                d2, _ = make_b200(a2, rank, world, host_buffers=False, cuda_graph=False)
+                r2, all2 = kernel_rooflines(d2, a2, peak, peak_src)
+                extra[key] = {'workload': f"{kw['env']} num_envs={kw['num_envs']} horizon={kw['horizon']}", 'roofline_kernels': all2}
+                cp.close(d2)
+                del d2
+                torch.cuda.empty_cache()
+            except Exception as e:           # never lose the headline line to an auxiliary measurement
+                extra[key] = {'error': f'{type(e).__name__}: {e}'}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = reference_arm(args, steps=2, warmup=1)
+        cpu = reference_arm(args, steps=5, warmup=1)
 
     if rank == 0:
         line = {
@@ -385,6 +439,7 @@ def run_b200(args):
                        'cuda_graph_rollout': not args.no_graph,
                        'cuda_graph_train': 'whole' if data.train_graph_state == 2 else ('segments' if data.train_segments else False), 'zero_copy_minibatches': getattr(data.experience, '_slabs', None) is not None, 'note': data.msg},
             'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof, 'roofline_kernels': roof_all,
+            'roofline_other_configs': extra,
             'cpu_baseline': cpu, 'clocks': clk, 'profile_s': prof, 'env_stats': stats,
         }
         print(json.dumps(line))

@@ -676,8 +676,9 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
     experience = Experience(config.batch_size, config.bptt_horizon, config.minibatch_size, obs_shape, obs_dtype,
                             atn_shape, config.cpu_offload, config.device, lstm, total_agents)
     experience.num_envs = total_agents      # rows arrive in arrival order t*N + e (also in pool mode: (t, group) blocks)
-    if hasattr(vecenv, 'bind_rollout') and not getattr(vecenv, 'host_buffers', False):
-        vecenv.bind_rollout(experience)     # env-step kernels write rollout rows directly
+    if hasattr(vecenv, 'bind_rollout'):
+        vecenv.bind_rollout(experience)     # env-step kernels write rollout rows directly (host_buffers mode too: the
+                                            # host arrays are filled FROM the rows, the policy reads the rows)
 
     uncompiled_policy = policy
     if getattr(config, 'compile', False):
@@ -706,8 +707,7 @@ def create(config, vecenv, policy, optimizer=None, wandb=None):
         msg=msg, last_log_time=0, utilization=None, grad_bucket=grad_bucket,
         io=pufferlib_b200.namespace(h2d=0, d2h=0), graph_state=0, rollout_graph=None, graph_steps=0,
         graph_launches=0, graph_replays=0, train_graph_state=0, train_graph=None, train_result=None, train_graph_launches=0, train_graph_replays=0, train_segments=None, train_acc=None, own_optimizer=own_optimizer, manual_update=None,
-        fused_rows=bool(getattr(policy, 'fused_sample', False)) and hasattr(vecenv, 'bind_rollout')
-        and not getattr(vecenv, 'host_buffers', False),
+        fused_rows=bool(getattr(policy, 'fused_sample', False)) and hasattr(vecenv, 'bind_rollout'),
         # one-kernel PPO loss (pb_ppo_loss): needs a wrapper exposing .policy(obs) -> (logits, value), one Discrete head
         fused_loss=bool(getattr(config, 'fused_loss', True)) and hasattr(policy, 'policy')
         and not hasattr(policy, 'lstm') and len(tuple(vecenv.single_action_space.shape)) == 0,
@@ -721,17 +721,20 @@ def _rollout_loop(data, infos):
     policy, vecenv = data.policy, data.vecenv
     on_device = not getattr(vecenv, 'host_buffers', False)
     io = data.io
+    device_feed = not on_device and hasattr(vecenv, 'recv_device')
     while not experience.full:
         with profile.env:
-            o, r, d, t, info, env_id, mask = vecenv.recv()
+            # host_buffers mode: the step as DEVICE tensors; its copy into the pinned host arrays (what recv() returns to
+            # a host-side caller) runs on the copy stream beside the policy forward and is awaited once, before send()
+            o, r, d, t, info, env_id, mask = vecenv.recv_device() if device_feed else vecenv.recv()
 
         with profile.eval_misc:
             # sum(mask) of clean_pufferl.py:90; count_nonzero instead of the Python-level sum over a numpy array, which
             # costs 1 ms per env step at N = 16384
-            data.global_step += len(env_id) if on_device else int(np.count_nonzero(mask))
-            if on_device:
-                o_device = o
-            else:   # host buffers: the reference's H2D of the observation batch (clean_pufferl.py:92-95)
+            data.global_step += len(env_id) if (on_device or device_feed) else int(np.count_nonzero(mask))
+            if on_device or device_feed:
+                o_device = o      # the device copy of the observations already exists: no H2D (clean_pufferl.py:92-95)
+            else:   # a host-only vecenv: the reference's H2D of the observation batch
                 o_device = vecenv.pinned(o).to(config.device, non_blocking=True)
                 r = vecenv.pinned(r).to(config.device, non_blocking=True)
                 d = vecenv.pinned(d).to(config.device, non_blocking=True)
@@ -757,6 +760,9 @@ def _rollout_loop(data, infos):
         with profile.eval_misc:
             value = value.flatten()
             experience.store(o_device, value, actions, logprob, r, d, env_id, mask)
+            if device_feed:   # the reference's D2H of the actions (clean_pufferl.py:114) + the ONE host wait of this env step
+                a_host = vecenv.actions_to_host(actions)
+                info = vecenv.host_sync()[4]
             for i in info:
                 for k, v in i.items():
                     infos[k].append(v)
@@ -764,7 +770,9 @@ def _rollout_loop(data, infos):
         with profile.env:
             if on_device:
                 vecenv.send(actions)
-            else:   # the reference's D2H of the actions (clean_pufferl.py:114)
+            elif device_feed:
+                vecenv.send(a_host)
+            else:
                 a_host = actions.cpu().numpy()
                 io.d2h += a_host.nbytes
                 vecenv.send(a_host)

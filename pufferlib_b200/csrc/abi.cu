@@ -178,3 +178,16 @@ extern "C" int pb_env_stats_read(pb_env* env, double* out4_host, int clear, void
         for (int k = 0; k < 4; ++k) out4_host[k] += env->h_stats_pinned[slot * 4 + k];
     return PB_OK;
 }
+
+// cudaDevAttrMultiProcessorCount of the current device, cached per device ordinal
+int pb_num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cache[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}

@@ -570,15 +570,7 @@ int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t row
     return PB_OK;
 }
 
-int g_sms = 0;
-int num_sms() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return g_sms;
-}
+int num_sms() { return pb_num_sms(); }
 
 }  // namespace
 

@@ -37,7 +37,9 @@ static inline int64_t pb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b
 __device__ __forceinline__ int64_t pb_ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
 #endif
 
-constexpr int PB_NUM_SMS = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SM count of the current device (B200: 148 = 2 dies x 74), queried once per device; grids are sized in multiples of it
+int pb_num_sms();
+#define PB_NUM_SMS (pb_num_sms())
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t pb_ld_acquire(const uint32_t* p) {

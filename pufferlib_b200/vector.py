@@ -215,6 +215,11 @@ class B200:
                 actions=torch.zeros(num_envs, dtype=torch.int64).pin_memory(),
             )
             self._host_np = namespace(**{k: v.numpy() for k, v in self._host.items()})
+            with torch.cuda.device(self.device):
+                # device->host copies run on their own stream, behind the env kernel and beside the policy forward
+                self._copy_stream = torch.cuda.Stream()
+                self._ev_step, self._ev_copy, self._ev_act = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+            self._host_pending = False
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -274,7 +279,8 @@ class B200:
             else:
                 a_np = np.ascontiguousarray(np.asarray(actions), dtype=np.int64)
                 if self.host_buffers:
-                    self._host_np.actions[:] = a_np
+                    if a_np.ctypes.data != self._host_np.actions.ctypes.data:     # else: already in the pinned array
+                        self._host_np.actions[:] = a_np
                     self._actions_dev.copy_(self._host.actions, non_blocking=True)
                 else:
                     self._actions_dev.copy_(torch.from_numpy(a_np), non_blocking=False)
@@ -295,7 +301,7 @@ class B200:
                     self._cursor = row
         self._stepped = True
 
-    def recv(self):
+    def recv(self, _device=False):
         recv_precheck(self)
         b = self.buf
         with torch.cuda.device(self.device):
@@ -314,22 +320,56 @@ class B200:
             else:
                 obs, rewards = b.observations, b.rewards
             if self.host_buffers:
-                h = self._host
-                h.observations.copy_(obs, non_blocking=True)
-                h.rewards.copy_(rewards, non_blocking=True)
-                h.terminals.copy_(b.terminals, non_blocking=True)
-                h.truncations.copy_(b.truncations, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                # the step's rows go to the pinned host arrays on the copy stream (ordered behind the env kernel that
+                # produced them); recv() waits for them, recv_device() leaves the wait to host_sync()
+                h, cs = self._host, self._copy_stream
+                self._ev_step.record()
+                cs.wait_event(self._ev_step)
+                with torch.cuda.stream(cs):
+                    h.observations.copy_(obs, non_blocking=True)
+                    h.rewards.copy_(rewards, non_blocking=True)
+                    h.terminals.copy_(b.terminals, non_blocking=True)
+                    h.truncations.copy_(b.truncations, non_blocking=True)
+                    self._ev_copy.record(cs)
+                self._host_pending = True
                 self.d2h_bytes += (h.observations.numel() * h.observations.element_size()
                                    + 4 * self.num_agents + 2 * self.num_agents)
-                hn = self._host_np
-                # the terminal flags are on the host already: no second D2H for the info dicts
-                infos = self._collect_infos(hn.terminals) if self.exact_infos else []
-                self.infos = infos
-                return (hn.observations, hn.rewards, hn.terminals, hn.truncations, infos, self.agent_ids, hn.masks)
+                self._device_view = (obs, rewards, b.terminals, b.truncations, [], self.agent_ids, b.masks)
+                return self.host_sync() if not _device else self._device_view
             infos = self._collect_infos() if self.exact_infos else []
             self.infos = infos
         return (obs, rewards, b.terminals, b.truncations, infos, self.agent_ids, b.masks)
+
+    def recv_device(self):
+        """host_buffers mode, for callers that keep computing on the device (clean_pufferl.evaluate): the same step as
+        recv(), returned as DEVICE tensors, while the copies into the pinned host arrays are still in flight on the copy
+        stream.  host_sync() completes the step on the host side (one wait per env step)."""
+        if not self.host_buffers:
+            return self.recv()
+        return self.recv(_device=True)
+
+    def actions_to_host(self, actions):
+        """Device actions -> the pinned host action array (async, on the caller's stream); valid after host_sync()."""
+        self._host.actions.copy_(actions.reshape(-1), non_blocking=True)
+        self._ev_act.record()
+        self._act_pending = True
+        self.d2h_bytes += 8 * self.num_agents
+        return self._host_np.actions
+
+    def host_sync(self):
+        """Wait for the step's device->host copies (and an outstanding actions_to_host); returns what recv() returns in
+        host_buffers mode: pinned numpy arrays + the info dicts."""
+        if self._host_pending:
+            self._ev_copy.synchronize()
+            self._host_pending = False
+        if getattr(self, '_act_pending', False):
+            self._ev_act.synchronize()
+            self._act_pending = False
+        hn = self._host_np
+        # the terminal flags are on the host already: no second D2H for the info dicts
+        infos = self._collect_infos(hn.terminals) if self.exact_infos else []
+        self.infos = infos
+        return (hn.observations, hn.rewards, hn.terminals, hn.truncations, infos, self.agent_ids, hn.masks)
 
     def pinned(self, array):
         """The pinned torch tensor behind one of the numpy arrays recv() returned in host_buffers mode (so the
