@@ -219,6 +219,21 @@ int pb_policy_mlp_sample(const float* obs, int64_t obs_stride, const float* w_en
                          int32_t n_act, uint64_t seed, uint64_t* counter_dev, uint32_t* ticket_dev, int64_t* actions,
                          float* logprobs, float* values, float* entropies, void* stream);
 
+/* -- persistent rollout (env steps with the policy in the loop) -------------------------------------------------------
+ * The H-iteration body of clean_pufferl.evaluate (clean_pufferl.py:84-124: recv -> policy -> store -> send) for a
+ * breakout handle and models.Default (128 features, 128 hidden, n_act <= 4) in ONE launch: a CTA owns 128 envs for all
+ * `horizon` steps, env state in registers, observation tile in shared memory feeding both the TMA store to the rollout
+ * tensor and the tcgen05 encoder GEMM (W_enc resident in shared memory), heads + sampling + value / logprob / action row
+ * stores by the env's own thread.  Rollout tensors are time-major [horizon * N] (row t*N + e); row 0 takes reward / done
+ * from the carry buffers (the vecenv's own buffers, pb_env_out with dones_f32), the step that closes the rollout writes
+ * the carry buffers (obs / rewards / terminals / dones_f32) -- the bound-rollout convention of vector.B200.  Sampling:
+ * the counter-based inverse CDF of pb_policy_mlp_sample with step counters *counter_dev .. *counter_dev + horizon - 1;
+ * *counter_dev is advanced by `horizon`.  num_envs must be a multiple of 128. */
+int pb_rollout_breakout_mlp(pb_env* env, int32_t horizon, float* obs, float* rewards, float* dones, float* values,
+                            float* logprobs, int64_t* actions, const pb_env_out* carry, const float* w_enc,
+                            const float* b_enc, const float* w_heads, const float* b_heads, int32_t n_act, uint64_t seed,
+                            uint64_t* counter_dev, void* stream);
+
 /* -- policy tail backward ---------------------------------------------------------------------------------------------
  * For models.Default (pufferlib/models.py:12-62: Linear+ReLU encoder, action head + value head): everything of the
  * backward pass after the encoder GEMM, in ONE pass over the hidden layer instead of five ATen launches:

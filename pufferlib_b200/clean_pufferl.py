@@ -189,6 +189,8 @@ def slab_row_index(num_envs, horizon, num_minibatches, bptt_horizon):
 # the fused tcgen05 minibatch-update kernel (csrc/mlp_update.cu) is the default where it applies; config.fused_update
 # overrides
 FUSED_UPDATE_DEFAULT = True
+# the persistent rollout kernel (pb_rollout_breakout_mlp) likewise; config.fused_rollout overrides
+FUSED_ROLLOUT_DEFAULT = True
 
 
 class _DefaultMLPUpdate:
@@ -721,6 +723,16 @@ def _rollout_loop(data, infos):
     policy, vecenv = data.policy, data.vecenv
     on_device = not getattr(vecenv, 'host_buffers', False)
     io = data.io
+    # the whole horizon as ONE persistent kernel (env state in registers, tcgen05 policy, csrc/env_breakout.cu) where it applies
+    if bool(getattr(config, 'fused_rollout', FUSED_ROLLOUT_DEFAULT)) and hasattr(vecenv, 'fused_rollout_ok') and \
+            data.fused_rows and vecenv.fused_rollout_ok(experience, policy):
+        with profile.env:
+            vecenv.fused_rollout(experience, policy)
+        data.global_step += experience.batch_size
+        experience.ptr = experience.batch_size
+        experience.step = experience.batch_size // experience.num_envs
+        data.fused_rollouts = getattr(data, 'fused_rollouts', 0) + 1
+        return
     device_feed = not on_device and hasattr(vecenv, 'recv_device')
     while not experience.full:
         with profile.env:

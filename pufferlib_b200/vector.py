@@ -371,6 +371,41 @@ class B200:
         self.infos = infos
         return (hn.observations, hn.rewards, hn.terminals, hn.truncations, infos, self.agent_ids, hn.masks)
 
+    def fused_rollout_ok(self, experience, policy):
+        """Can the whole rollout run as ONE persistent kernel (pb_rollout_breakout_mlp)?  breakout, one RNG shard, device
+        path, rollout bound to `experience` and standing at a rollout boundary, models.Default 128 -> 128 -> <= 4 actions
+        behind a cleanrl.Policy with the fused sampler."""
+        model = getattr(policy, 'policy', None)
+        if not (self.kind == 'breakout' and not self.host_buffers and not self.exact_infos and len(self._shards) == 1
+                and self._rollout is experience and self._pending_own and self._cursor == 0 and self.flag == RECV
+                and self.num_agents % 128 == 0 and experience.ptr == 0 and experience.lstm_h is None):
+            return False
+        if not (getattr(policy, 'fused_sample', False) and hasattr(model, 'head_matrix') and getattr(model, 'fast_path', False)):
+            return False
+        n_act, hid = model.decoder.weight.shape
+        w = model.encoder.weight
+        return (hid == 128 and tuple(w.shape) == (128, 128) and n_act <= 4 and w.is_cuda and w.dtype == torch.float32
+                and w.is_contiguous() and experience.obs.dtype == torch.float32)
+
+    def fused_rollout(self, experience, policy):
+        """evaluate's recv -> policy -> store -> send loop for the whole horizon in one launch; leaves the vecenv exactly
+        where the loop would: the closing step's outputs in its own buffers, waiting for recv()."""
+        x, model = experience, policy.policy
+        if policy._counter is None:
+            policy._counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.no_grad():
+            w_cat, b_cat = model.head_matrix()
+        carry = self._env_out(None)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().pb_rollout_breakout_mlp(
+                self._handle, self._horizon, _native.ptr(x.obs), _native.ptr(x.rewards), _native.ptr(x.dones),
+                _native.ptr(x.values), _native.ptr(x.logprobs), _native.ptr(x.actions), C.byref(carry),
+                _native.ptr(model.encoder.weight), _native.ptr(model.encoder.bias), _native.ptr(w_cat), _native.ptr(b_cat),
+                model.decoder.weight.shape[0], C.c_uint64(policy._seed), _native.ptr(policy._counter), _native.stream_ptr()))
+        self._pending_own, self._cursor = True, 0
+        self.initialized = True
+        self.flag = RECV
+
     def pinned(self, array):
         """The pinned torch tensor behind one of the numpy arrays recv() returned in host_buffers mode (so the
         caller's H2D copy is a true async pinned transfer)."""
