@@ -1152,4 +1152,8 @@ def try_load_checkpoint(data):
 
 
 def close(data):
+    mu = getattr(data, 'manual_update', None)
+    if mu is not None and getattr(mu, 'peer', None) is not None:
+        mu.peer.close()            # collective: every rank closes (unmaps the peers' buffers, then frees its own)
+        mu.peer = None
     data.vecenv.close()
