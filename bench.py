@@ -307,7 +307,8 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                     _native.check(lib.pb_mlp_update_fused(
                         _native.ptr(x), 128, r_, x.stride(0) // 128 if g_ > 1 else r_, g_, _native.ptr(model.encoder.weight),
                         _native.ptr(model.encoder.bias), _native.ptr(w_cat), _native.ptr(b_cat), _native.ptr(acts),
-                        _native.ptr(f32[0]), _native.ptr(f32[1]), _native.ptr(f32[2]), _native.ptr(f32[3]), n_act, C.c_float(0.1), 1,
+                        _native.ptr(f32[0]), _native.ptr(f32[1]), _native.ptr(f32[2]), _native.ptr(f32[3]), None, r_, n_act,
+                        C.c_float(0.1), 1,
                         C.c_float(0.1), C.c_float(0.5), C.c_float(0.01), _native.ptr(gfl), _native.ptr(st8), _native.ptr(ws),
                         ws.numel(), None, None, None, _native.stream_ptr()))
                 with torch.no_grad():

@@ -143,6 +143,14 @@ size_t pb_gae_workspace_bytes(int64_t num_envs, int64_t horizon);
 int pb_gae(const float* rewards, const float* values, const float* dones, float* advantages,
            float* returns_sorted, int64_t num_envs, int64_t horizon, float gamma, float gae_lambda,
            void* workspace, size_t workspace_bytes, void* stream);
+/* pb_gae with an additional advantages output in ARRIVAL (time-major, row t*N + e) order -- the order the rollout
+ * tensors and the zero-copy minibatch slabs are in, so the update can consume it without a re-ordering pass.  Either
+ * advantages output may be null.  Time-major output: horizon in {128, 256, 512} and num_envs % 4 == 0
+ * (pb_gae_time_major_supported). */
+int pb_gae_time_major_supported(int64_t num_envs, int64_t horizon);
+int pb_gae_tm(const float* rewards, const float* values, const float* dones, float* advantages, float* returns_sorted,
+              float* advantages_time_major, int64_t num_envs, int64_t horizon, float gamma, float gae_lambda,
+              void* workspace, size_t workspace_bytes, void* stream);
 
 /* -- minibatch construction --------------------------------------------------------------------------------------
  * Replaces Experience.flatten_batch (clean_pufferl.py:466-482) for the scalar tensors.  Segment k (bptt
@@ -255,7 +263,10 @@ int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_
  *   x            n_slabs slabs of slab_rows rows x 128 features, row stride ldx floats; slab s starts slab_stride_rows rows
  *                after slab s-1 (the zero-copy minibatch view of the time-major rollout; n_slabs = 1: a plain matrix)
  *   w_heads/b_heads  the 8-row padded head matrix of pb_pack_heads (n_act logit rows | value row | zeros)
- *   actions .. old_values   per-row tensors in slab-major order [n_slabs * slab_rows] (advantages already normalised)
+ *   actions .. old_values   per-row tensors; slab s starts at element s * row_slab_stride (row_slab_stride = slab_rows:
+ *                slab-major copies; = the rollout's slab distance: the arrival-order rollout tensors themselves, no copies)
+ *   adv_norm     nullable device (mean, 1/(std + 1e-8)) applied to `advantages` on the fly (clean_pufferl.py:211-213);
+ *   returns      nullable: advantages (raw) + old_values is used (clean_pufferl.py:476-481)
  *   grad_flat    [128*128 + 8*128 + 128 + 8]: dW_enc | dW_heads | db_enc | db_heads  (what pb_clip_adam consumes)
  *   stats8       the six loss sums of pb_ppo_loss (zeroed here)
  *   dbg_*        nullable dumps of relu(h) [M][128], dPre [M][128], dOut [M][8] for validation. */
@@ -263,9 +274,17 @@ size_t pb_mlp_update_workspace_bytes(void);
 int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
                         const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
                         const int64_t* actions, const float* old_logprobs, const float* advantages, const float* returns,
-                        const float* old_values, int32_t n_act, float clip_coef, int32_t clip_vloss, float vf_clip_coef,
+                        const float* old_values, const float* adv_norm, int64_t row_slab_stride, int32_t n_act,
+                        float clip_coef, int32_t clip_vloss, float vf_clip_coef,
                         float vf_coef, float ent_coef, float* grad_flat, double* stats8, void* workspace,
                         size_t workspace_bytes, float* dbg_hidden, float* dbg_dpre, float* dbg_dout, void* stream);
+
+/* Advantage statistics of the zero-copy slab minibatches from ARRIVAL-order advantages (pb_gae_tm): minibatch mb = slabs
+ * g * n_minibatches + mb (g < n_slabs) of slab_rows consecutive rows.  norm_out[mb] = (mean, 1 / (unbiased std + 1e-8)),
+ * the constants of clean_pufferl.py:211-213, which pb_mlp_update_fused applies on the fly.
+ * workspace: pb_adv_norm_workspace_bytes(n_minibatches, slab_rows * n_slabs). */
+int pb_adv_stats_slabs(const float* advantages_time_major, int64_t slab_rows, int32_t n_slabs, int32_t n_minibatches,
+                       float* norm_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* -- optimizer step for small policies -------------------------------------------------------------------------------
  * clip_grad_norm_ + Adam of clean_pufferl.py:240-244 (torch.nn.utils.clip_grad_norm_(params, max_grad_norm);

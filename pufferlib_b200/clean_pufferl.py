@@ -321,11 +321,15 @@ class _DefaultMLPUpdate:
                 and (x.shape[0] == 1 or (x.stride(0) % x.stride(1) == 0 and x.stride(0) >= x.shape[1] * x.stride(1))))
 
     @torch.no_grad()
-    def forward_backward(self, k, n_stats, obs, slab_form, atn, log_probs, adv, ret, val, config):
-        """obs: slab view [G, R, *obs] (slab_form) or [M, *obs]; the rest [M].  Statistics of this minibatch go to
-        row k of self.stats."""
+    def forward_backward(self, k, n_stats, obs, slab_form, atn, log_probs, adv, ret, val, config, row_slab_stride=None,
+                         adv_norm=None):
+        """obs: slab view [G, R, *obs] (slab_form) or [M, *obs]; the rest [M] in slab-major order -- or, with
+        row_slab_stride (fused kernel only), arrival-order tensors whose slab s starts at element s * row_slab_stride;
+        adv_norm: device (mean, 1/(std+1e-8)) applied to `adv` inside the kernel; ret None: adv + val.  Statistics of this
+        minibatch go to row k of self.stats."""
         x = obs if slab_form else obs.reshape(1, atn.numel(), -1)
         x = x.flatten(2)
+        assert row_slab_stride is None or self._fused_ok(x, config)
         if self._fused_ok(x, config):
             # ONE tcgen05 kernel: x read once, hidden / dPre stay on the SM, gradients land in self.gflat
             g_, r_, _ = x.shape
@@ -340,7 +344,9 @@ class _DefaultMLPUpdate:
                 _native.ptr(x), x.stride(1), r_, (x.stride(0) // x.stride(1)) if g_ > 1 else r_, g_,
                 _native.ptr(m_.encoder.weight), _native.ptr(m_.encoder.bias), _native.ptr(self.w_cat), _native.ptr(self.b_cat),
                 _native.ptr(atn.reshape(-1)), _native.ptr(log_probs.reshape(-1)), _native.ptr(adv.reshape(-1)),
-                _native.ptr(ret.reshape(-1)), _native.ptr(val.reshape(-1)), self.n_act, C.c_float(config.clip_coef),
+                _native.ptr(ret.reshape(-1)) if ret is not None else None, _native.ptr(val.reshape(-1)),
+                _native.ptr(adv_norm) if adv_norm is not None else None, r_ if row_slab_stride is None else int(row_slab_stride),
+                self.n_act, C.c_float(config.clip_coef),
                 int(bool(config.clip_vloss)), C.c_float(config.vf_clip_coef), C.c_float(config.vf_coef),
                 C.c_float(config.ent_coef), _native.ptr(self.gflat), C.c_void_p(self.stats.data_ptr() + 64 * k),
                 _native.ptr(self.fused_ws), self.fused_ws.numel(), None, None, None, _native.stream_ptr()))
@@ -468,6 +474,8 @@ class Experience:
         lib = _native.lib()
         self._advnorm_ws = torch.zeros(max(16, lib.pb_adv_norm_workspace_bytes(nm, mb)), dtype=torch.uint8, **z)
         self._gae_ws = None
+        self.advantages_tm = None     # arrival-order advantages (pb_gae_tm) for the in-place (direct slab) update
+        self.adv_norm = None          # [nm, 2]: (mean, 1 / (std + 1e-8)) per minibatch
 
     @property
     def b_obs(self):
@@ -564,18 +572,63 @@ class Experience:
         self.step = 0
         return _LazyIdxs(n, h)
 
-    def compute_gae(self, gamma, gae_lambda):
-        """c_gae.compute_gae on the sorted batch (clean_pufferl.py:164-169) -> self.advantages (sorted order)."""
+    def compute_gae(self, gamma, gae_lambda, time_major=False):
+        """c_gae.compute_gae on the sorted batch (clean_pufferl.py:164-169) -> self.advantages (sorted order).
+        time_major: ALSO self.advantages_tm in arrival order (row t*N + e) and no sorted returns (pb_gae_tm)."""
         n, h = self.num_envs, self.horizon
         lib = _native.lib()
         need = lib.pb_gae_workspace_bytes(n, h)
         if self._gae_ws is None or self._gae_ws.numel() < need:
             self._gae_ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
+        if time_major:
+            if self.advantages_tm is None:
+                self.advantages_tm = torch.zeros(self.batch_size, device=self.device)
+            _native.check(lib.pb_gae_tm(_native.ptr(self.rewards), _native.ptr(self.values), _native.ptr(self.dones),
+                                        _native.ptr(self.advantages), None, _native.ptr(self.advantages_tm), n, h,
+                                        C.c_float(gamma), C.c_float(gae_lambda), _native.ptr(self._gae_ws),
+                                        self._gae_ws.numel(), _native.stream_ptr()))
+            return self.advantages
         _native.check(lib.pb_gae(_native.ptr(self.rewards), _native.ptr(self.values), _native.ptr(self.dones),
                                  _native.ptr(self.advantages), _native.ptr(self.returns_sorted), n, h,
                                  C.c_float(gamma), C.c_float(gae_lambda), _native.ptr(self._gae_ws),
                                  self._gae_ws.numel(), _native.stream_ptr()))
         return self.advantages
+
+    def direct_slabs_ok(self, manual, config):
+        """Can the update read the rollout tensors in place (zero-copy observations AND zero-copy per-row tensors)?  Needs
+        the slab layout, the GAE tile kernel's time-major output and the fused update kernel for these observations."""
+        n, h, nm, bptt = self.num_envs, self.horizon, self.num_minibatches, self.bptt_horizon
+        layout = slab_layout(n, h, nm, bptt)
+        if layout is None or not _native.lib().pb_gae_time_major_supported(n, h):
+            return False
+        g_, r_ = layout
+        x0 = self.obs.view(g_, nm, r_, *self.obs_shape)[:, 0].flatten(2)
+        return manual._fused_ok(x0, config)
+
+    def prepare_direct_slabs(self, norm_adv):
+        """After compute_gae(time_major=True): the returns of clean_pufferl.py:476 (for the explained variance) and the
+        per-minibatch advantage-normalisation constants of :211-213, straight from the arrival-order advantages."""
+        n, h, nm, bptt = self.num_envs, self.horizon, self.num_minibatches, self.bptt_horizon
+        g_, r_ = slab_layout(n, h, nm, bptt)
+        torch.add(self.advantages, self.values, out=self.returns)       # sorted + arrival, same flat index (the reference's)
+        if self._slabs is None:
+            self._slabs = pufferlib_b200.namespace()
+        self._slabs.shape = (g_, r_)
+        if norm_adv:
+            if self.adv_norm is None:
+                self.adv_norm = torch.zeros(nm, 2, device=self.device)
+            _native.check(_native.lib().pb_adv_stats_slabs(
+                _native.ptr(self.advantages_tm), r_, g_, nm, _native.ptr(self.adv_norm), _native.ptr(self._advnorm_ws),
+                self._advnorm_ws.numel(), _native.stream_ptr()))
+
+    def direct_minibatch(self, mb, norm_adv):
+        """Minibatch mb as views of the rollout tensors: slab s of the minibatch = rows (s*nm + mb)*R .. +R."""
+        g_, r_ = self._slabs.shape
+        lo = mb * r_
+        return pufferlib_b200.namespace(
+            obs=self.slab_obs(mb), actions=self.actions[lo:], logprobs=self.logprobs[lo:], old_values=self.values[lo:],
+            advantages=self.advantages_tm[lo:], row_slab_stride=self.num_minibatches * r_,
+            adv_norm=self.adv_norm[mb] if norm_adv else None)
 
     def flatten_batch(self, advantages=None):
         """clean_pufferl.py:466-482 (advantages: sorted-order device tensor, default self.advantages)."""
@@ -606,7 +659,7 @@ class Experience:
         if layout is None:
             return False
         g_, r_ = layout
-        if self._slabs is None:
+        if self._slabs is None or getattr(self._slabs, 'actions', None) is None:
             z = dict(device=self.device)
             mb = self.minibatch_size
             self._slabs = pufferlib_b200.namespace(
@@ -888,14 +941,27 @@ def _train_device_part(data, seg=None):
     model = getattr(data.policy, 'policy', None)
     want_slabs = data.fused_loss and experience.lstm_h is None and hasattr(model, 'forward_packed_slabs') and \
         bool(getattr(config, 'zero_copy_minibatches', True))
+    manual = None
+    if _DefaultMLPUpdate.eligible(data):
+        if getattr(data, 'manual_update', None) is None or data.manual_update.stale():
+            data.manual_update = _DefaultMLPUpdate(data)
+        manual = data.manual_update
     with profile.train_misc:
         experience.sort_training_data()
-        experience.compute_gae(config.gamma, config.gae_lambda)
-        slabs = want_slabs and experience.flatten_batch_slabs()
-        if not slabs:
-            experience.flatten_batch()
-        if config.norm_adv:
-            experience.normalize_advantages(slabs=slabs)
+        # the fused update kernel reads the ARRIVAL-order rollout tensors through slab strides: no minibatch copies at all
+        # (GAE writes the advantages in arrival order as well; the advantage normalisation constants are applied on the fly)
+        direct = want_slabs and manual is not None and experience.direct_slabs_ok(manual, config)
+        if direct:
+            experience.compute_gae(config.gamma, config.gae_lambda, time_major=True)
+            experience.prepare_direct_slabs(config.norm_adv)
+            slabs = True
+        else:
+            experience.compute_gae(config.gamma, config.gae_lambda)
+            slabs = want_slabs and experience.flatten_batch_slabs()
+            if not slabs:
+                experience.flatten_batch()
+            if config.norm_adv:
+                experience.normalize_advantages(slabs=slabs)
 
     n_mb = experience.num_minibatches
     if seg is not None:                        # persistent accumulator: the segment graphs update it in place
@@ -908,15 +974,17 @@ def _train_device_part(data, seg=None):
     obs_shape = data.vecenv.single_observation_space.shape
     fused = data.fused_loss and experience.lstm_h is None
     carry = {'lstm_state': None, 'approx_kl': None}
-    manual = None
-    if _DefaultMLPUpdate.eligible(data):
-        if getattr(data, 'manual_update', None) is None or data.manual_update.stale():
-            data.manual_update = _DefaultMLPUpdate(data)
-        manual = data.manual_update
+    if manual is not None:
         manual.pack_heads()                      # the parameters may have changed since the last train() (checkpoints)
     n_stats = config.update_epochs * n_mb
 
     def forward_backward(mb, k=0):              # k = epoch * n_mb + mb: the manual path's statistics row
+        if direct:
+            with profile.train_forward:
+                d = experience.direct_minibatch(mb, config.norm_adv)
+                manual.forward_backward(k, n_stats, d.obs, True, d.actions, d.logprobs, d.advantages, None, d.old_values, config,
+                                        row_slab_stride=d.row_slab_stride, adv_norm=d.adv_norm)
+            return
         if slabs:
             sl = experience._slabs
             obs = experience.slab_obs(mb)

@@ -41,6 +41,7 @@ struct GaeParams {
     const float* d;
     float* adv;
     float* ret;
+    float* adv_tm;     // optional: advantages in arrival (time-major) order [H][N] as well (fast path only)
     int64_t N, H, B;
     float gamma, gl;
     int E, logE;       // envs per tile (power of two) or 0 in flat mode
@@ -514,10 +515,16 @@ __global__ void __launch_bounds__(FAST_THREADS) k_gae_fast(GaeParams p) {
                     A = fmaf(b[kc][j], A, a[kc][j]);
                     outA[j] = A;
                 }
-                float4* pa = reinterpret_cast<float4*>(p.adv + f);
+                if (p.adv) {
+                    float4* pa = reinterpret_cast<float4*>(p.adv + f);
 #pragma unroll
-                for (int j4 = 0; j4 < FC / 4; ++j4)
-                    __stcs(pa + j4, make_float4(outA[4 * j4], outA[4 * j4 + 1], outA[4 * j4 + 2], outA[4 * j4 + 3]));
+                    for (int j4 = 0; j4 < FC / 4; ++j4)
+                        __stcs(pa + j4, make_float4(outA[4 * j4], outA[4 * j4 + 1], outA[4 * j4 + 2], outA[4 * j4 + 3]));
+                }
+                if (p.adv_tm) {   // stage in the (now idle) reward tile, same [t][32] layout: conflict-free, lanes = envs
+#pragma unroll
+                    for (int j = 0; j < FC; ++j) sR[(c * FC + j) * FE + lane] = outA[j];
+                }
                 if (p.ret) {
                     const int base = c * FC * FE + lane;
                     float4* pr = reinterpret_cast<float4*>(p.ret + f);
@@ -528,6 +535,14 @@ __global__ void __launch_bounds__(FAST_THREADS) k_gae_fast(GaeParams p) {
                                                     outA[4 * j4 + 2] + sV[base + (4 * j4 + 2) * FE],
                                                     outA[4 * j4 + 3] + sV[base + (4 * j4 + 3) * FE]));
                 }
+            }
+        }
+        if (p.adv_tm) {   // arrival-order rows: one fully coalesced 128-byte store per time step of the tile
+            __syncthreads();
+            if (lane < Et) {
+                float* dst = p.adv_tm + e0 + lane;
+#pragma unroll 4
+                for (int t = warp; t < H; t += FAST_THREADS / 32) __stcs(dst + (int64_t)t * p.N, sR[t * FE + lane]);
             }
         }
         __syncthreads();          // the tile buffers, s_cagg / s_eagg / s_carry are free again
@@ -607,16 +622,31 @@ extern "C" size_t pb_gae_workspace_bytes(int64_t num_envs, int64_t horizon) {
 extern "C" int pb_gae(const float* rewards, const float* values, const float* dones, float* advantages,
                       float* returns_sorted, int64_t num_envs, int64_t horizon, float gamma, float gae_lambda,
                       void* workspace, size_t workspace_bytes, void* stream) {
+    PB_REQUIRE(advantages || num_envs == 0 || horizon == 0, PB_ERR_INVALID, "pb_gae: null pointer");
+    return pb_gae_tm(rewards, values, dones, advantages, returns_sorted, nullptr, num_envs, horizon, gamma, gae_lambda,
+                     workspace, workspace_bytes, stream);
+}
+
+extern "C" int pb_gae_time_major_supported(int64_t num_envs, int64_t horizon) {
+    return (num_envs > 0 && horizon > 0 && gae_plan(num_envs, horizon).fastKC > 0) ? 1 : 0;
+}
+
+extern "C" int pb_gae_tm(const float* rewards, const float* values, const float* dones, float* advantages,
+                         float* returns_sorted, float* advantages_time_major, int64_t num_envs, int64_t horizon,
+                         float gamma, float gae_lambda, void* workspace, size_t workspace_bytes, void* stream) {
     PB_REQUIRE(num_envs >= 0 && horizon >= 0, PB_ERR_INVALID, "pb_gae: negative size");
     if (num_envs == 0 || horizon == 0) return PB_OK;
-    PB_REQUIRE(rewards && values && dones && advantages, PB_ERR_INVALID, "pb_gae: null pointer");
+    PB_REQUIRE(rewards && values && dones && (advantages || advantages_time_major), PB_ERR_INVALID, "pb_gae: null pointer");
+    PB_REQUIRE(!advantages_time_major || gae_plan(num_envs, horizon).fastKC > 0, PB_ERR_UNSUPPORTED,
+               "pb_gae_tm: the time-major output needs the tile kernel (horizon in {128, 256, 512}, num_envs %% 4 == 0)");
+    PB_REQUIRE(advantages || gae_plan(num_envs, horizon).fastKC > 0, PB_ERR_INVALID, "pb_gae: null advantages");
     PB_REQUIRE(num_envs * horizon < (1ll << 40), PB_ERR_INVALID, "pb_gae: batch too large");
     GaePlan g = gae_plan(num_envs, horizon);
     const size_t need = sizeof(GaeHeader) + (size_t)g.numTiles * sizeof(GaeStatus);
     PB_REQUIRE(workspace && workspace_bytes >= need, PB_ERR_INVALID,
                "pb_gae: workspace too small (%zu < %zu)", workspace_bytes, need);
     GaeParams p{};
-    p.r = rewards; p.v = values; p.d = dones; p.adv = advantages; p.ret = returns_sorted;
+    p.r = rewards; p.v = values; p.d = dones; p.adv = advantages; p.ret = returns_sorted; p.adv_tm = advantages_time_major;
     p.N = num_envs; p.H = horizon; p.B = num_envs * horizon;
     p.gamma = gamma;
     p.gl = gamma * gae_lambda;  // float product, as `gamma * gae_lambda` in c_gae.pyx:29
@@ -627,7 +657,7 @@ extern "C" int pb_gae(const float* rewards, const float* values, const float* do
     // persistent grid: every resident slot of the chip, never more blocks than tiles (one wave, no tail)
     int per_sm = 0;
     if (g.fastKC > 0) {
-        PB_REQUIRE(((uintptr_t)advantages & 15) == 0 && (!returns_sorted || ((uintptr_t)returns_sorted & 15) == 0),
+        PB_REQUIRE((!advantages || ((uintptr_t)advantages & 15) == 0) && (!returns_sorted || ((uintptr_t)returns_sorted & 15) == 0),
                    PB_ERR_INVALID, "pb_gae: advantages / returns must be 16-byte aligned");
         PB_REQUIRE(((uintptr_t)rewards & 15) == 0 && ((uintptr_t)values & 15) == 0 && ((uintptr_t)dones & 15) == 0,
                    PB_ERR_INVALID, "pb_gae: rewards / values / dones must be 16-byte aligned");

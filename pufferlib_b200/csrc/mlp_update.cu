@@ -61,8 +61,10 @@ struct FusedParams {
     const int64_t* actions;
     const float* old_logprobs;
     const float* adv;
-    const float* returns;
+    const float* returns;      // nullable: returns = advantages (raw) + old_values (clean_pufferl.py:476-481)
     const float* old_values;
+    const float* adv_norm;     // nullable: (mean, 1 / (std + 1e-8)) of this minibatch's raw advantages (:211-213)
+    int64_t row_slab_stride;   // per-row arrays: slab s starts at element s * row_slab_stride (slab_rows: slab-major)
     int64_t m;                 // rows of the minibatch (all slabs): the 1/M of the loss means
     int64_t slab_rows;         // R
     int64_t slab_stride_rows;  // distance between slab starts, in rows of the x tensor map
@@ -354,15 +356,17 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const int slab = tile / p.tiles_per_slab;
             const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
             const bool valid = lrow < p.slab_rows;
-            const int64_t i = (int64_t)slab * p.slab_rows + lrow;
+            const int64_t i = (int64_t)slab * p.slab_rows + lrow;            // slab-major position (debug dumps)
+            const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;     // position in the per-row arrays
             int act = 0;
             float old_lp = 0.f, adv = 0.f, ret = 0.f, old_v = 0.f;
             if (valid) {
-                act = (int)p.actions[i];
-                old_lp = p.old_logprobs[i];
-                adv = p.adv[i];
-                ret = p.returns[i];
-                old_v = p.clip_vloss ? p.old_values[i] : 0.f;
+                act = (int)p.actions[ri];
+                old_lp = p.old_logprobs[ri];
+                adv = p.adv[ri];
+                old_v = (p.clip_vloss || !p.returns) ? p.old_values[ri] : 0.f;
+                ret = p.returns ? p.returns[ri] : adv + old_v;
+                if (p.adv_norm) adv = (adv - p.adv_norm[0]) * p.adv_norm[1];
             }
             mbar_wait(&h_full[s], ph);
             tc_fence_after();
@@ -581,13 +585,15 @@ extern "C" size_t pb_mlp_update_workspace_bytes(void) {
 extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
                                    const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
                                    const int64_t* actions, const float* old_logprobs, const float* advantages,
-                                   const float* returns, const float* old_values, int32_t n_act, float clip_coef,
+                                   const float* returns, const float* old_values, const float* adv_norm,
+                                   int64_t row_slab_stride, int32_t n_act, float clip_coef,
                                    int32_t clip_vloss, float vf_clip_coef, float vf_coef, float ent_coef, float* grad_flat,
                                    double* stats8, void* workspace, size_t workspace_bytes, float* dbg_hidden,
                                    float* dbg_dpre, float* dbg_dout, void* stream) {
-    PB_REQUIRE(x && w_enc && b_enc && w_heads && b_heads && actions && old_logprobs && advantages && returns && grad_flat &&
-                   stats8 && workspace,
+    PB_REQUIRE(x && w_enc && b_enc && w_heads && b_heads && actions && old_logprobs && advantages && grad_flat && stats8 &&
+                   workspace && (returns || old_values),
                PB_ERR_INVALID, "pb_mlp_update_fused: null pointer");
+    PB_REQUIRE(n_slabs == 1 || row_slab_stride >= slab_rows, PB_ERR_INVALID, "pb_mlp_update_fused: row slabs overlap");
     PB_REQUIRE(slab_rows >= 1 && n_slabs >= 1 && n_act >= 1 && n_act <= 7 && (!clip_vloss || old_values), PB_ERR_INVALID,
                "pb_mlp_update_fused: bad sizes (slab_rows %lld, n_slabs %d, n_act %d)", (long long)slab_rows, n_slabs, n_act);
     PB_REQUIRE(ldx >= FEAT && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)w_enc & 15) == 0, PB_ERR_INVALID,
@@ -612,6 +618,7 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
     const int grid = n_tiles < num_sms() ? (int)n_tiles : num_sms();
     FusedParams p;
     p.actions = actions; p.old_logprobs = old_logprobs; p.adv = advantages; p.returns = returns; p.old_values = old_values;
+    p.adv_norm = adv_norm; p.row_slab_stride = n_slabs > 1 ? row_slab_stride : slab_rows;
     p.m = slab_rows * n_slabs; p.slab_rows = slab_rows; p.slab_stride_rows = n_slabs > 1 ? slab_stride_rows : slab_rows;
     p.tiles_per_slab = (int)tiles_per_slab; p.n_tiles = (int)n_tiles; p.n_act = n_act;
     p.clip = clip_coef; p.vclip = vf_clip_coef; p.vf_coef = vf_coef; p.ent_coef = ent_coef; p.clip_vloss = clip_vloss;

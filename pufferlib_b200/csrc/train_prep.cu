@@ -224,6 +224,66 @@ __global__ void __launch_bounds__(AN_THREADS) k_adv_apply(const float* __restric
     for (int64_t i = lo + threadIdx.x; i < hi; i += AN_THREADS) o[i] = (a[i] - mean) / den;
 }
 
+// Advantage statistics of the zero-copy slab minibatches (clean_pufferl.Experience.flatten_batch_slabs) straight from the
+// ARRIVAL-order advantages: minibatch mb = slabs (g*n_mb + mb), g = 0..G-1, of R consecutive rows each.
+// grid (parts, n_mb); partials[mb][part] = (sum, sum of squares) in fp64.
+__global__ void __launch_bounds__(AN_THREADS) k_adv_stats_slabs(const float* __restrict__ adv, int64_t slab_rows, int n_slabs,
+                                                               int n_mb, double2* __restrict__ partials) {
+    const int part = blockIdx.x, parts = gridDim.x, mb = blockIdx.y;
+    const int64_t total = slab_rows * n_slabs;
+    const int64_t chunk = (pb_ceil_div_dev(total, parts) + 3) & ~(int64_t)3;
+    const int64_t lo = (int64_t)part * chunk, hi = min(lo + chunk, total);
+    double s = 0.0, ss = 0.0;
+    const bool vec = (slab_rows & 3) == 0 && (reinterpret_cast<uintptr_t>(adv) & 15) == 0;
+    if (vec) {
+        for (int64_t i = lo + 4 * (int64_t)threadIdx.x; i < hi; i += 4 * AN_THREADS) {
+            const int64_t g = i / slab_rows, r = i - g * slab_rows;
+            const float4 x = *reinterpret_cast<const float4*>(adv + ((g * n_mb + mb) * slab_rows + r));
+            s += (double)x.x + (double)x.y + (double)x.z + (double)x.w;
+            ss += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
+        }
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += AN_THREADS) {
+            const int64_t g = i / slab_rows, r = i - g * slab_rows;
+            const double x = adv[(g * n_mb + mb) * slab_rows + r];
+            s += x;
+            ss += x * x;
+        }
+    }
+    __shared__ double sh_s[AN_THREADS / 32], sh_ss[AN_THREADS / 32];
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) {
+        sh_s[threadIdx.x >> 5] = s;
+        sh_ss[threadIdx.x >> 5] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tss = 0.0;
+        for (int w = 0; w < AN_THREADS / 32; ++w) {
+            ts += sh_s[w];
+            tss += sh_ss[w];
+        }
+        partials[(int64_t)mb * parts + part] = make_double2(ts, tss);
+    }
+}
+
+// norm[mb] = (mean, 1 / (std + 1e-8)) with the unbiased std of clean_pufferl.py:211-213 (torch.Tensor.std default)
+__global__ void k_adv_finalize(const double2* __restrict__ partials, int parts, int64_t mb_size, float2* __restrict__ norm) {
+    const int mb = threadIdx.x;       // one block of n_mb threads
+    double ts = 0.0, tss = 0.0;
+    for (int q = 0; q < parts; ++q) {
+        const double2 v = partials[(int64_t)mb * parts + q];
+        ts += v.x;
+        tss += v.y;
+    }
+    const double n = (double)mb_size;
+    const double mean = ts / n;
+    double var = (tss - ts * mean) / (n - 1.0);
+    if (var < 0.0) var = 0.0;
+    norm[mb] = make_float2((float)mean, 1.0f / ((float)sqrt(var) + 1e-8f));
+}
+
 template <typename V>
 int launch_copy_rows(const void* src, int64_t ss, void* dst, int64_t ds, int64_t row_bytes, int64_t n_rows,
                      cudaStream_t s) {
@@ -362,6 +422,26 @@ extern "C" int pb_adv_norm(const float* adv, float* out, int64_t n_mb, int64_t m
     k_adv_stats<<<grid, AN_THREADS, 0, s>>>(adv, mb_size, (double2*)workspace);
     PB_LAUNCH_CHECK();
     k_adv_apply<<<grid, AN_THREADS, 0, s>>>(adv, out, mb_size, (const double2*)workspace);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+}
+
+extern "C" int pb_adv_stats_slabs(const float* advantages_time_major, int64_t slab_rows, int32_t n_slabs, int32_t n_minibatches,
+                                  float* norm_out, void* workspace, size_t workspace_bytes, void* stream) {
+    PB_REQUIRE(advantages_time_major && norm_out && workspace, PB_ERR_INVALID, "pb_adv_stats_slabs: null pointer");
+    PB_REQUIRE(slab_rows >= 1 && n_slabs >= 1 && n_minibatches >= 1 && n_minibatches <= 65535, PB_ERR_INVALID,
+               "pb_adv_stats_slabs: bad sizes");
+    const int64_t mb_size = slab_rows * n_slabs;
+    PB_REQUIRE(workspace_bytes >= pb_adv_norm_workspace_bytes(n_minibatches, mb_size), PB_ERR_INVALID,
+               "pb_adv_stats_slabs: workspace too small");
+    PB_REQUIRE(n_minibatches <= 1024, PB_ERR_UNSUPPORTED, "pb_adv_stats_slabs: at most 1024 minibatches");
+    const int parts = adv_norm_parts(n_minibatches, mb_size);
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((unsigned)parts, (unsigned)n_minibatches);
+    k_adv_stats_slabs<<<grid, AN_THREADS, 0, s>>>(advantages_time_major, slab_rows, n_slabs, n_minibatches,
+                                                   (double2*)workspace);
+    PB_LAUNCH_CHECK();
+    k_adv_finalize<<<1, n_minibatches, 0, s>>>((const double2*)workspace, parts, mb_size, (float2*)norm_out);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

@@ -45,7 +45,7 @@ def fused(xbuf, ldx, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat
         dp = torch.full((m, 128), float('nan'), device=dev)
         do = torch.full((m, 8), float('nan'), device=dev)
     _native.check(lib.pb_mlp_update_fused(ptr(xbuf), ldx, slab_rows, slab_stride, n_slabs, ptr(w_enc), ptr(b_enc), ptr(w_cat), ptr(b_cat),
-                                  ptr(act), ptr(olp), ptr(adv), ptr(ret), ptr(oval), n_act, CFG[0], CFG[1], CFG[2], CFG[3],
+                                  ptr(act), ptr(olp), ptr(adv), ptr(ret), ptr(oval), None, slab_rows, n_act, CFG[0], CFG[1], CFG[2], CFG[3],
                                   CFG[4], ptr(gflat), ptr(stats), ptr(ws), ws.numel(), ptr(dh), ptr(dp), ptr(do),
                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return gflat, stats, dh, dp, do
