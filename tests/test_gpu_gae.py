@@ -126,3 +126,46 @@ def test_gae_vs_reference_compiled_c_gae():
         ref = np.asarray(ref_mod.compute_gae(ds, vs, rs, gamma, lam))
         ref64 = ogae.compute_gae_f64(ds, vs, rs, gamma, lam)
         gae_tolerance_check(adv, ref, ref64)
+
+
+@pytest.mark.parametrize('h,n', [(128, 64), (128, 36), (256, 1024), (512, 40), (128, 16384)])
+def test_gae_time_major_output_and_slab_statistics(h, n):
+    """pb_gae_tm: the arrival-order (time-major) advantages are the sorted-order ones transposed, bit for bit; and
+    pb_adv_stats_slabs gives the (mean, 1/(std+1e-8)) of clean_pufferl.py:211-213 for the zero-copy slab minibatches."""
+    import ctypes as C
+    import torch
+    from pufferlib_b200 import _native, clean_pufferl
+    lib = _native.lib()
+    assert lib.pb_gae_time_major_supported(n, h) == 1 and lib.pb_gae_time_major_supported(n, h + 1) == 0
+    r, v, d = make_inputs(h, n, seed=h + n, p_done=0.02)
+    dev = torch.device('cuda')
+    tr, tv, td = (torch.as_tensor(x, device=dev) for x in (r, v, d))
+    adv = torch.full((n * h,), float('nan'), device=dev)
+    adv_tm = torch.full((n * h,), float('nan'), device=dev)
+    ws = torch.zeros(lib.pb_gae_workspace_bytes(n, h), dtype=torch.uint8, device=dev)
+    for sorted_out in (adv, None):       # with and without the sorted output
+        adv_tm.fill_(float('nan'))
+        _native.check(lib.pb_gae_tm(_native.ptr(tr), _native.ptr(tv), _native.ptr(td), _native.ptr(sorted_out), None,
+                                    _native.ptr(adv_tm), n, h, C.c_float(0.99), C.c_float(0.95), _native.ptr(ws), ws.numel(),
+                                    _native.stream_ptr()))
+        torch.cuda.synchronize()
+        a_sorted = adv.cpu().numpy().reshape(n, h)
+        assert np.array_equal(adv_tm.cpu().numpy().reshape(h, n).view(np.uint32), a_sorted.T.view(np.uint32))
+    ref = ogae.compute_gae(sorted_from_time_major(d), sorted_from_time_major(v), sorted_from_time_major(r), 0.99, 0.95)
+    ref64 = ogae.compute_gae_f64(sorted_from_time_major(d), sorted_from_time_major(v), sorted_from_time_major(r), 0.99, 0.95)
+    gae_tolerance_check(adv.cpu().numpy(), ref, ref64)
+    # slab statistics: minibatch mb = time windows k = mb, mb + nm, ... of bptt steps (all envs)
+    bptt, nm = 16, 4
+    g_, r_ = clean_pufferl.slab_layout(n, h, nm, bptt)
+    norm = torch.zeros(nm, 2, device=dev)
+    ws2 = torch.zeros(max(16, lib.pb_adv_norm_workspace_bytes(nm, g_ * r_)), dtype=torch.uint8, device=dev)
+    _native.check(lib.pb_adv_stats_slabs(_native.ptr(adv_tm), r_, g_, nm, _native.ptr(norm), _native.ptr(ws2), ws2.numel(),
+                                         _native.stream_ptr()))
+    torch.cuda.synchronize()
+    rows = clean_pufferl.slab_row_index(n, h, nm, bptt)
+    a = adv_tm.cpu().numpy().astype(np.float64)
+    got = norm.cpu().numpy()
+    for mb in range(nm):
+        x = a[rows[mb]]
+        assert np.isclose(got[mb, 0], x.mean(), rtol=1e-5, atol=1e-7)
+        assert np.isclose(got[mb, 1], 1.0 / (x.std(ddof=1) + 1e-8), rtol=1e-5)
