@@ -248,6 +248,20 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
         t_pol = time_launches(pstep, h)
         out['policy_step'] = dict(kernel='k_policy_mlp_sample', seconds=t_pol,
                                   bytes_per_launch=n * (o + 16) + 128 * 128 * 4, launches_per_step=h)
+    # the persistent rollout kernel (H env steps + policy in ONE launch): when evaluate() uses it, the per-step kernels above
+    # are off the step path.  Algorithmic bytes per agent-step: obs row + reward + done + value + logprob + action (int64).
+    if getattr(data, 'fused_rollouts', 0) > 0 and vec.fused_rollout_ok(exp, pol):
+        def roll(i):
+            with torch.no_grad():
+                vec.fused_rollout(exp, pol)
+        roll(0)
+        t_roll = time_launches(roll, 4)
+        out['rollout'] = dict(kernel='k_breakout_rollout (tcgen05 policy + env, persistent)', seconds=t_roll,
+                              bytes_per_launch=n * h * (o + 4 + 4 + 4 + 4 + 8), launches_per_step=1)
+        exp.ptr = 0
+        for k_ in ('env_step', 'policy_step'):
+            if k_ in out:
+                out[k_]['launches_per_step'] = 0
     # train-side kernels at the minibatch size of the workload (rotating buffers > L2 where the working set is small)
     if args.env != 'pong' and args.hidden == 128:
         mb = n * h // args.minibatches
