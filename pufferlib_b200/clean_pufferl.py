@@ -1114,6 +1114,8 @@ def train(data):
     if getattr(data, 'manual_update', None) is not None and data.manual_update.stale():
         # optimizer.load_state_dict() (try_load_checkpoint) replaced the Adam state tensors: the hand-written update
         # and any captured graph hold the old addresses -- rebuild both (eager call now, re-capture on the next one)
+        if getattr(data.manual_update, 'peer', None) is not None:
+            data.manual_update.peer.close()          # collective: every rank loaded the same checkpoint
         data.manual_update = None
         if data.train_graph_state > 0:
             data.train_graph, data.train_segments, data.train_graph_state = None, None, 0
