@@ -202,6 +202,7 @@ constexpr int RO_TILE_BYTES = 4 * RO_KBLK_BYTES;         // 64 KiB
 constexpr int RO_SMEM_W = 0, RO_SMEM_X = RO_TILE_BYTES, RO_SMEM_BAR = 3 * RO_TILE_BYTES;
 constexpr int RO_SMEM_TOTAL = RO_SMEM_BAR + 128;
 constexpr int RO_TMEM_COLS = 128;
+constexpr int RO_HEADS = 5;                  // live rows of the 8-row head matrix: breakout has 4 actions + the value
 
 __constant__ float c_ro_wh[8 * 128];
 __constant__ float c_ro_benc[128];
@@ -391,7 +392,7 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
                 for (int k = 0; k < 32; ++k) {
                     const float rh = fmaxf(v[k] + c_ro_benc[32 * c + k], 0.f);
 #pragma unroll
-                    for (int a = 0; a < 8; ++a) out[a] = fmaf(rh, c_ro_wh[a * 128 + 32 * c + k], out[a]);
+                    for (int a = 0; a < RO_HEADS; ++a) out[a] = fmaf(rh, c_ro_wh[a * 128 + 32 * c + k], out[a]);   // rows >= 5: zero padding
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

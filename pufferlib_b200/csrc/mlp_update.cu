@@ -232,6 +232,8 @@ __device__ __forceinline__ uint32_t chunk_off(int r, int j) {
     return (uint32_t)(r * 128 + ((((j >> 2) ^ (r & 7))) << 4) + ((j & 3) << 2));
 }
 
+// NH = live rows of the 8-row head matrix (n_act logits + the value): rows >= NH are zero padding, their products are skipped
+template <int NH>
 __global__ void __launch_bounds__(THREADS, 1)
 k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -384,7 +386,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 for (int k = 0; k < 32; ++k) {
                     const float rh = fmaxf(v[k] + c_benc[32 * c + k], 0.f);
 #pragma unroll
-                    for (int a = 0; a < NO; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * c + k], out[a]);
+                    for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * c + k], out[a]);
                 }
             }
             // ---- loss row math -> dOut
@@ -433,7 +435,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     const float pre = v[k] + c_benc[32 * c + k];
                     float gk = 0.f;
 #pragma unroll
-                    for (int a = 0; a < NO; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * c + k], gk);
+                    for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * c + k], gk);
                     dp[k] = pre > 0.f ? gk : 0.f;
                     v[k] = fmaxf(pre, 0.f);                    // relu(h)
                 }
@@ -628,12 +630,15 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
     PB_CUDA(cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_benc, b_enc, sizeof(float) * HID, 0, cudaMemcpyDeviceToDevice, s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_bh, b_heads, sizeof(float) * NO, 0, cudaMemcpyDeviceToDevice, s));
+    // dispatch on the live head rows (n_act + 1): 5 for the 4-action configs, 8 = generic
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         attr_set = true;
     }
-    k_mlp_update_fused<<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
+    if (n_act + 1 <= 5) k_mlp_update_fused<5><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
+    else k_mlp_update_fused<8><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
     PB_LAUNCH_CHECK();
     k_update_reduce<<<(FEAT * HID + TAIL + 63) / 64, 256, 0, s>>>(p.part_dw, p.part_tail, grid, grad_flat);
     PB_LAUNCH_CHECK();

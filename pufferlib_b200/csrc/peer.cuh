@@ -21,6 +21,12 @@ __device__ __forceinline__ float pb_ld_relaxed_sys_f32(const float* p) {   // pe
     return v;
 }
 
+__device__ __forceinline__ float4 pb_ld_relaxed_sys_f32x4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
 // One CTA (any size that is a multiple of 32): flat[0..n) <- sum over ranks, in rank order (bit-identical everywhere).
 __device__ __forceinline__ void pb_peer_allreduce_sum(const pb_peer_comm& c, float* flat, int64_t n) {
     if (c.world <= 1) return;
@@ -31,7 +37,12 @@ __device__ __forceinline__ void pb_peer_allreduce_sum(const pb_peer_comm& c, flo
     const uint64_t e = s_epoch;
     const int64_t slot_off = PB_PEER_HEADER_BYTES / 4 + (int64_t)(e & 1) * c.capacity;
     float* mine = reinterpret_cast<float*>(c.base[c.rank]) + slot_off;
-    for (int64_t i = tid; i < n; i += nt) mine[i] = flat[i];
+    // 128-bit accesses where the layout allows (capacity % 4 == 0 keeps both slots 16-byte aligned): at 68 KB per rank the
+    // exchange is latency-bound, so every thread should have all its peer loads in flight at once
+    const bool vec = (c.capacity & 3) == 0 && (reinterpret_cast<uintptr_t>(flat) & 15) == 0;
+    const int64_t n4 = vec ? n >> 2 : 0;
+    for (int64_t i = tid; i < n4; i += nt) reinterpret_cast<float4*>(mine)[i] = reinterpret_cast<const float4*>(flat)[i];
+    for (int64_t i = 4 * n4 + tid; i < n; i += nt) mine[i] = flat[i];
     __threadfence_system();
     __syncthreads();
     if (tid < c.world) {   // raise my flag in every rank's buffer (mine included)
@@ -46,7 +57,18 @@ __device__ __forceinline__ void pb_peer_allreduce_sum(const pb_peer_comm& c, flo
         }
     }
     __syncthreads();
-    for (int64_t i = tid; i < n; i += nt) {
+    for (int64_t i = tid; i < n4; i += nt) {
+        float4 v[PB_PEER_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < PB_PEER_MAX_RANKS; ++r)
+            if (r < c.world) v[r] = pb_ld_relaxed_sys_f32x4(reinterpret_cast<const float*>(c.base[r]) + slot_off + 4 * i);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < PB_PEER_MAX_RANKS; ++r)      // rank order: the same bits on every rank
+            if (r < c.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        reinterpret_cast<float4*>(flat)[i] = s;
+    }
+    for (int64_t i = 4 * n4 + tid; i < n; i += nt) {
         float s = 0.f;
         for (int r = 0; r < c.world; ++r) s += pb_ld_relaxed_sys_f32(reinterpret_cast<const float*>(c.base[r]) + slot_off + i);
         flat[i] = s;

@@ -102,7 +102,7 @@ class PeerComm:
         if self.world > 8:
             raise RuntimeError('PeerComm: at most 8 ranks (one NVSwitch node)')
         lib = _native.lib()
-        self.capacity = int(capacity_floats)
+        self.capacity = (int(capacity_floats) + 3) & ~3      # multiple of 4 floats: both slots stay 16-byte aligned
         nbytes = lib.pb_peer_buffer_bytes(self.capacity)
         own, handle = C.c_void_p(), C.create_string_buffer(64)
         _native.check(lib.pb_peer_alloc(nbytes, C.byref(own), handle))
