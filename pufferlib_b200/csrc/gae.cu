@@ -564,6 +564,245 @@ __global__ void __launch_bounds__(FAST_THREADS) k_gae_fast(GaeParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tile kernel v2 (same shapes as k_gae_fast: N % 4 == 0, H in {128, 256, 512}; same arithmetic, bit-identical results).
+// What changes is how the bytes move:
+//   * DOUBLE-BUFFERED tiles: the cp.async loads of the next tile (claimed by ticket at the top of the iteration) are in
+//     flight while this tile is scanned and written out, so DRAM does not idle during the scan (NBUF = 2 where 2 tiles
+//     fit in shared memory: 96 KB at H = 128 -> 2 CTAs / SM, 192 KB at H = 256 -> 1 CTA / SM);
+//   * COALESCED OUTPUTS: pass 3 stages its results in the tile arrays that are dead after pass 1 -- sorted order
+//     ([env][t], 16-byte chunks XOR-swizzled by env & 7: conflict-free for the lane = env writes and for the row reads)
+//     or arrival order ([t][32]) -- and the block then writes whole 512-byte env rows / 128-byte time rows, instead of
+//     32 scattered 16-byte pieces per store instruction;
+//   * one warp per 16-step chunk of all 32 envs (THREADS = 32 * min(H / 16, 16)): H = 256 runs 16 warps.
+template <int KC, int NBUF, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_gae_tile(GaeParams p) {
+    constexpr int NW = THREADS / 32;
+    constexpr int H = FC * NW * KC;
+    constexpr int CE = H / FC;                 // chunks per env
+    constexpr int ARR = H * FE;                // floats per array
+    extern __shared__ __align__(16) float smem[];   // NBUF x {r, v, d} x [H][32]
+    __shared__ int s_ticket[2];
+    __shared__ float s_halo[2][4];
+    __shared__ float2 s_cagg[CE][FE];
+    __shared__ float2 s_eagg[FE];
+    __shared__ float s_carry;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    auto issue_loads = [&](int tile, int b) {
+        float* sR = smem + (size_t)b * 3 * ARR;
+        float* sV = sR + ARR;
+        float* sD = sR + 2 * ARR;
+        const int64_t e0 = (int64_t)tile * FE;
+        const int Et = (int)min((int64_t)FE, p.N - e0);
+        const int quad = tid & 7, t0 = tid >> 3;         // 8 float4 per row, THREADS / 8 rows per sweep
+        if (4 * quad < Et) {
+            const int64_t g0 = (int64_t)t0 * p.N + e0 + 4 * quad;
+            const int64_t gstep = (int64_t)(THREADS / 8) * p.N;
+            const float* pr = p.r + g0;
+            const float* pv = p.v + g0;
+            const float* pd = p.d + g0;
+            int sp = t0 * FE + 4 * quad;
+#pragma unroll
+            for (int k = 0; k < H / (THREADS / 8); ++k) {
+                cp_async16(sR + sp, pr);
+                cp_async16(sV + sp, pv);
+                cp_async16(sD + sp, pd);
+                pr += gstep; pv += gstep; pd += gstep;
+                sp += (THREADS / 8) * FE;
+            }
+        }
+        if (tid == 0) {
+            const int64_t en = e0 + Et;                  // first env after the tile; its t = 0 row entry
+            if (en < p.N) {
+                cp_async4(&s_halo[b][0], p.r + en);
+                cp_async4(&s_halo[b][1], p.v + en);
+                cp_async4(&s_halo[b][2], p.d + en);
+            } else {
+                s_halo[b][0] = 0.f; s_halo[b][1] = 0.f; s_halo[b][2] = 1.f;
+            }
+        }
+        cp_async_commit();
+    };
+
+    if (tid == 0) s_ticket[0] = (int)atomicAdd(&p.hdr->ticket, 1u);
+    __syncthreads();
+    int ticket = s_ticket[0];
+    int cur = 0;
+    if (ticket < p.numTiles) issue_loads(p.numTiles - 1 - ticket, 0);
+
+    while (ticket < p.numTiles) {
+        const int tile = p.numTiles - 1 - ticket;          // suffix order: last tile first
+        const int64_t e0 = (int64_t)tile * FE;
+        const int Et = (int)min((int64_t)FE, p.N - e0);     // multiple of 4 (N % 4 == 0)
+        float* sR = smem + (size_t)cur * 3 * ARR;
+        float* sV = sR + ARR;
+        float* sD = sR + 2 * ARR;
+        const float* halo = s_halo[cur];
+
+        // ---- claim the next tile and (NBUF == 2) start its loads before touching this one
+        if (tid == 0) s_ticket[1] = (int)atomicAdd(&p.hdr->ticket, 1u);
+        __syncthreads();
+        const int next_ticket = s_ticket[1];
+        const bool prefetch = NBUF == 2 && next_ticket < p.numTiles;
+        if (prefetch) {
+            issue_loads(p.numTiles - 1 - next_ticket, cur ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        // ---- pass 1: per-chunk serial composition (suffix order), element maps kept in registers
+        float a[KC][FC], b[KC][FC];
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
+            const int c = warp + kc * NW;                       // chunk index; env = lane
+            float P = 0.f, Q = 1.f;
+            if (lane < Et) {
+                const int base = c * FC * FE + lane;
+                float rn, vn, dn;
+                if (c < CE - 1) { rn = sR[base + FC * FE]; vn = sV[base + FC * FE]; dn = sD[base + FC * FE]; }
+                else if (lane + 1 < Et) { rn = sR[lane + 1]; vn = sV[lane + 1]; dn = sD[lane + 1]; }
+                else { rn = halo[0]; vn = halo[1]; dn = halo[2]; }
+                const bool last_of_batch = (e0 + lane == p.N - 1) && (c == CE - 1);
+#pragma unroll
+                for (int j = FC - 1; j >= 0; --j) {
+                    const float r0 = sR[base + j * FE], v0 = sV[base + j * FE], d0 = sD[base + j * FE];
+                    const float nnt = __fsub_rn(1.0f, dn);
+                    float aj = __fsub_rn(__fadd_rn(rn, __fmul_rn(__fmul_rn(p.gamma, vn), nnt)), v0);
+                    float bj = __fmul_rn(p.gl, nnt);
+                    if (last_of_batch && j == FC - 1) { aj = 0.f; bj = 0.f; }   // A[B-1] = 0
+                    a[kc][j] = aj;
+                    b[kc][j] = bj;
+                    P = fmaf(bj, P, aj);
+                    Q = bj * Q;
+                    rn = r0; vn = v0; dn = d0;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < FC; ++j) { a[kc][j] = 0.f; b[kc][j] = 1.f; }
+            }
+            s_cagg[c][lane] = make_float2(P, Q);
+        }
+        __syncthreads();
+
+        // ---- pass 2 (warp 0): chunk carries inside each env, env carries inside the tile, then the look-back
+        if (warp == 0) {
+            float cP = 0.f, cQ = 1.f;
+#pragma unroll
+            for (int c = CE - 1; c >= 0; --c) {
+                const float2 g = s_cagg[c][lane];
+                s_cagg[c][lane] = make_float2(cP, cQ);
+                const float nP = fmaf(g.y, cP, g.x), nQ = g.y * cQ;
+                cP = nP; cQ = nQ;
+            }
+            float x = cP, y = cQ;
+#pragma unroll
+            for (int off = 1; off < FE; off <<= 1) {
+                const float x2 = __shfl_down_sync(0xffffffffu, x, off);
+                const float y2 = __shfl_down_sync(0xffffffffu, y, off);
+                if (lane + off < FE) compose(x, y, x2, y2);
+            }
+            const float tP = __shfl_sync(0xffffffffu, x, 0), tQ = __shfl_sync(0xffffffffu, y, 0);
+            float exP = __shfl_down_sync(0xffffffffu, x, 1), exQ = __shfl_down_sync(0xffffffffu, y, 1);
+            if (lane == FE - 1) { exP = 0.f; exQ = 1.f; }
+            s_eagg[lane] = make_float2(exP, exQ);
+            const float carry = tile_lookback(p.status, tile, p.numTiles, tP, tQ, lane);
+            if (lane == 0) s_carry = carry;
+        }
+        __syncthreads();
+
+        // ---- pass 3: apply carries; results staged in the dead tile arrays:
+        //      sR <- advantages, sorted layout [env][t] (16-byte chunk q of env row at position q ^ (env & 7))
+        //      sD <- returns in the same layout, or (time-major output) advantages as [t][32]
+        const float C = s_carry;
+        if (lane < Et) {
+            const float2 em = s_eagg[lane];
+            const float a_env_end = fmaf(em.y, C, em.x);
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+                const int c = warp + kc * NW;
+                const float2 cm = s_cagg[c][lane];
+                float A = fmaf(cm.y, a_env_end, cm.x);
+                float outA[FC];
+#pragma unroll
+                for (int j = FC - 1; j >= 0; --j) {
+                    A = fmaf(b[kc][j], A, a[kc][j]);
+                    outA[j] = A;
+                }
+                const int base = c * FC * FE + lane;
+                float vv[FC];
+                if (p.ret) {
+#pragma unroll
+                    for (int j = 0; j < FC; ++j) vv[j] = sV[base + j * FE];
+                }
+                if (p.adv) {
+#pragma unroll
+                    for (int j4 = 0; j4 < FC / 4; ++j4) {
+                        const int q = c * (FC / 4) + j4;
+                        *reinterpret_cast<float4*>(sR + lane * H + ((q ^ (lane & 7)) << 2)) =
+                            make_float4(outA[4 * j4], outA[4 * j4 + 1], outA[4 * j4 + 2], outA[4 * j4 + 3]);
+                    }
+                }
+                if (p.ret) {
+#pragma unroll
+                    for (int j4 = 0; j4 < FC / 4; ++j4) {
+                        const int q = c * (FC / 4) + j4;
+                        *reinterpret_cast<float4*>(sD + lane * H + ((q ^ (lane & 7)) << 2)) =
+                            make_float4(outA[4 * j4] + vv[4 * j4], outA[4 * j4 + 1] + vv[4 * j4 + 1],
+                                        outA[4 * j4 + 2] + vv[4 * j4 + 2], outA[4 * j4 + 3] + vv[4 * j4 + 3]);
+                    }
+                } else if (p.adv_tm) {
+#pragma unroll
+                    for (int j = 0; j < FC; ++j) sD[(c * FC + j) * FE + lane] = outA[j];
+                }
+            }
+        }
+        __syncthreads();
+        // NOTE: pass 1 of this tile has finished for every warp (barriers above), so overwriting sR / sD was safe; sV
+        // is only read.  Now the coalesced stores: one warp per env row (sorted) / per time row (arrival order).
+        {
+            const int64_t f0 = e0 * (int64_t)H;
+            for (int env = warp; env < Et; env += NW) {
+#pragma unroll
+                for (int q0 = 0; q0 < H / 4; q0 += 32) {
+                    const int q = q0 + lane;
+                    const int sp = env * H + ((q ^ (env & 7)) << 2);
+                    if (p.adv) __stcs(reinterpret_cast<float4*>(p.adv + f0 + (int64_t)env * H) + q, *reinterpret_cast<const float4*>(sR + sp));
+                    if (p.ret) __stcs(reinterpret_cast<float4*>(p.ret + f0 + (int64_t)env * H) + q, *reinterpret_cast<const float4*>(sD + sp));
+                }
+            }
+            if (p.adv_tm && !p.ret && lane < Et) {
+                float* dst = p.adv_tm + e0 + lane;
+#pragma unroll 4
+                for (int t = warp; t < H; t += NW) __stcs(dst + (int64_t)t * p.N, sD[t * FE + lane]);
+            }
+        }
+        __syncthreads();          // this buffer, s_cagg / s_eagg / s_carry are free again
+        ticket = next_ticket;
+        if (NBUF == 2) cur ^= 1;
+        else if (ticket < p.numTiles) issue_loads(p.numTiles - 1 - ticket, 0);
+    }
+
+    if (tid == 0) {
+        __threadfence();
+        const uint32_t prev = atomicAdd(&p.hdr->exited, 1u);
+        s_ticket[0] = (prev == gridDim.x - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_ticket[0]) {
+        for (int j = tid; j < p.numTiles; j += THREADS) {
+            p.status[j].P = 0.f; p.status[j].Q = 0.f; p.status[j].X = 0.f; p.status[j].flag = 0u;
+        }
+        if (tid == 0) { p.hdr->ticket = 0u; p.hdr->exited = 0u; }
+    }
+}
+
+int g_gae_variant = 2;   // 2: k_gae_tile (double-buffered, coalesced outputs); 1: k_gae_fast
+
 struct GaePlan {
     int fastKC;   // > 0: k_gae_fast<fastKC, nbuf>
     int nbuf;
@@ -670,7 +909,24 @@ extern "C" int pb_gae_tm(const float* rewards, const float* values, const float*
         if (grid > g.numTiles) grid = g.numTiles;                                                                     \
         k_gae_fast<KC><<<grid, FAST_THREADS, g.smem, s>>>(p);                                                         \
     }
-        if (g.fastKC == 1) PB_GAE_FAST(1) else if (g.fastKC == 2) PB_GAE_FAST(2) else PB_GAE_FAST(4)
+#define PB_GAE_TILE(KC, NBUF, THREADS)                                                                                \
+    {                                                                                                                 \
+        const size_t smem2 = (size_t)NBUF * g.smem;                                                                   \
+        PB_CUDA(cudaFuncSetAttribute(k_gae_tile<KC, NBUF, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)smem2));                                                                    \
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gae_tile<KC, NBUF, THREADS>, THREADS, smem2)); \
+        PB_REQUIRE(per_sm >= 1, PB_ERR_CUDA, "pb_gae: kernel does not fit on an SM (smem %zu)", smem2);               \
+        int grid = per_sm * PB_NUM_SMS;                                                                               \
+        if (grid > g.numTiles) grid = g.numTiles;                                                                     \
+        k_gae_tile<KC, NBUF, THREADS><<<grid, THREADS, smem2, s>>>(p);                                                \
+    }
+        const bool v2_ok = !(returns_sorted && advantages_time_major);   // v2 stages two outputs: adv + (ret | adv_tm)
+        if (g_gae_variant == 2 && v2_ok) {
+            if (g.fastKC == 1) PB_GAE_TILE(1, 2, 256) else if (g.fastKC == 2) PB_GAE_TILE(1, 2, 512) else PB_GAE_TILE(2, 1, 512)
+        } else {
+            if (g.fastKC == 1) PB_GAE_FAST(1) else if (g.fastKC == 2) PB_GAE_FAST(2) else PB_GAE_FAST(4)
+        }
+#undef PB_GAE_TILE
 #undef PB_GAE_FAST
         PB_LAUNCH_CHECK();
         return PB_OK;
@@ -688,5 +944,12 @@ extern "C" int pb_gae_tm(const float* rewards, const float* values, const float*
     if (g.RW == 16) k_gae<16><<<grid, GAE_THREADS, g.smem, s>>>(p);
     else k_gae<32><<<grid, GAE_THREADS, g.smem, s>>>(p);
     PB_LAUNCH_CHECK();
+    return PB_OK;
+}
+
+// 2 (default): k_gae_tile (double-buffered tiles, coalesced outputs); 1: the round-1 k_gae_fast.  For A/B measurements.
+extern "C" int pb_gae_set_variant(int32_t variant) {
+    PB_REQUIRE(variant == 1 || variant == 2, PB_ERR_INVALID, "pb_gae_set_variant: 1 or 2");
+    g_gae_variant = variant;
     return PB_OK;
 }

@@ -169,3 +169,23 @@ def test_gae_time_major_output_and_slab_statistics(h, n):
         x = a[rows[mb]]
         assert np.isclose(got[mb, 0], x.mean(), rtol=1e-5, atol=1e-7)
         assert np.isclose(got[mb, 1], 1.0 / (x.std(ddof=1) + 1e-8), rtol=1e-5)
+
+
+@pytest.mark.parametrize('h,n', [(128, 64), (128, 36), (128, 16384), (256, 96), (256, 4096), (512, 40), (512, 1000)])
+def test_gae_tile_kernel_variants_agree(h, n):
+    """k_gae_tile (double-buffered, coalesced outputs; default) and the round-1 k_gae_fast are the same arithmetic: the
+    element maps are identical, only the tile look-back may compose in a different order run to run -> compare to 1e-6."""
+    from pufferlib_b200 import _native
+    lib = _native.lib()
+    r, v, d = make_inputs(h, n, seed=3 * h + n, p_done=0.02)
+    out = {}
+    try:
+        for variant in (1, 2):
+            _native.check(lib.pb_gae_set_variant(variant))
+            out[variant] = gae_device(r, v, d, 0.99, 0.95)
+    finally:
+        lib.pb_gae_set_variant(2)
+    for k in (0, 1):
+        assert np.allclose(out[1][k], out[2][k], rtol=1e-6, atol=1e-6)
+    rs, vs, ds = (sorted_from_time_major(x) for x in (r, v, d))
+    gae_tolerance_check(out[2][0], ogae.compute_gae(ds, vs, rs, 0.99, 0.95), ogae.compute_gae_f64(ds, vs, rs, 0.99, 0.95))
