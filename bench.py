@@ -219,10 +219,22 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                                  C.c_float(0.99), C.c_float(0.95), _native.ptr(exp._gae_ws), exp._gae_ws.numel(),
                                  _native.stream_ptr()))
     t_gae = time_launches(gae, 16)
+    t_gae_v1 = None
+    if h in (128, 256, 512) and n % 4 == 0:      # A/B: the round-1 single-buffered tile kernel on the same inputs
+        try:
+            _native.check(lib.pb_gae_set_variant(1))
+            gae(0)
+            t_gae_v1 = time_launches(gae, 16)
+        finally:
+            lib.pb_gae_set_variant(2)
     del sets
     # pb_gae's dispatch (csrc/gae.cu): the single-pass tile kernel for H in {128, 256, 512} and N % 4 == 0, else the general one
     gae_kernel = 'k_gae_fast' if (h in (128, 256, 512) and n % 4 == 0) else 'k_gae'
+    gae_kernel = 'k_gae_tile' if gae_kernel == 'k_gae_fast' else gae_kernel
     out['gae'] = dict(kernel=gae_kernel, bytes_per_launch=n * h * 20, seconds=t_gae, launches_per_step=1)
+    if t_gae_v1 is not None:
+        out['gae_round1_kernel'] = dict(kernel='k_gae_fast (round 1, for comparison)', bytes_per_launch=n * h * 20,
+                                        seconds=t_gae_v1, launches_per_step=0)
 
     # minibatch gather of the observations: read + write of every row
     def gather(i):
