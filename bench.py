@@ -198,8 +198,16 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     # previous row (the obs is the state), pong reads the three surviving frames of it
     extra = {'snake': o, 'pong': 3 * (o // 4)}.get(args.env, 0)
     bytes_env = n * (o + 16 + extra)
-    out['env_step'] = dict(kernel=f'k_{args.env}<1>', bytes_per_launch=bytes_env, seconds=t_env,
-                           launches_per_step=h)
+    env_kernel = {'snake': 'k_snake4<1> (4 lanes / env)'}.get(args.env, f'k_{args.env}<1>')
+    out['env_step'] = dict(kernel=env_kernel, bytes_per_launch=bytes_env, seconds=t_env, launches_per_step=h)
+    if args.env == 'snake':      # A/B: the 16-lanes-per-env kernel of round 1
+        try:
+            _native.check(lib.pb_snake_set_variant(16))
+            env_step(0)
+            out['env_step_round1_kernel'] = dict(kernel='k_snake<1> (16 lanes / env, round 1)', bytes_per_launch=bytes_env,
+                                                 seconds=time_launches(env_step, h), launches_per_step=0)
+        finally:
+            lib.pb_snake_set_variant(4)
 
     # GAE (+returns): 20 B per agent-step.  8 rotating input/output sets (8 x 42 MB > the 126 MB L2) so every launch
     # streams from HBM like it does after a 1 GiB rollout has passed through the cache.

@@ -110,6 +110,9 @@ int pb_env_reset(pb_env* env, uint64_t seed, const pb_env_out* out, void* stream
  * action_space.contains check (vector.py:36-39). */
 int pb_env_step(pb_env* env, const int64_t* actions, const pb_env_out* out, void* stream);
 
+/* Snake step kernel variant for A/B measurements: lanes per env, 4 (default) or 16 (round 1); bit-identical results. */
+int pb_snake_set_variant(int32_t lanes_per_env);
+
 /* Episode statistics (EpisodeStats, postprocess.py:22-54).
  * pb_env_episode_rows: per-env values of the episode that ENDED on the most recent step -- valid where that
  * step's terminals[e] != 0: episode_return (fp64 sum), episode_length, score.  Pointers are device arrays [N]

@@ -85,6 +85,7 @@ SIGNATURES = {
                             [C.c_size_t] + [C.c_void_p] * 4),
     'pb_adv_stats_slabs': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p]),
+    'pb_snake_set_variant': (C.c_int, [C.c_int32]),
     'pb_gae_set_variant': (C.c_int, [C.c_int32]),
     'pb_gae_time_major_supported': (C.c_int, [C.c_int64, C.c_int64]),
     'pb_gae_tm': (C.c_int, [C.c_void_p] * 6 + [C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_void_p, C.c_size_t,

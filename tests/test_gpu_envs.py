@@ -168,3 +168,16 @@ def test_pool_mode_through_evaluate_train():
         assert np.isfinite(data.losses.policy_loss)
         assert data.global_step == (it + 1) * n * h
     clean_pufferl.close(data)
+
+
+def test_snake_kernel_variants():
+    """The 16-lanes-per-env kernel of round 1 stays selectable (A/B measurements) and bit-exact against the oracle too."""
+    from pufferlib_b200 import _native
+    lib = _native.lib()
+    try:
+        _native.check(lib.pb_snake_set_variant(16))
+        compare_run('snake', 37, h=120, seed=21, env_kwargs=FAST_END['snake'])
+    finally:
+        lib.pb_snake_set_variant(4)
+    compare_run('snake', 37, h=120, seed=21, env_kwargs=FAST_END['snake'])
+    compare_run('snake', 3, h=300, seed=22, env_kwargs={})          # n * 4 lanes not a multiple of 32
