@@ -227,12 +227,15 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                                  C.c_float(0.99), C.c_float(0.95), _native.ptr(exp._gae_ws), exp._gae_ws.numel(),
                                  _native.stream_ptr()))
     t_gae = time_launches(gae, 16)
-    t_gae_v1 = None
-    if h in (128, 256, 512) and n % 4 == 0:      # A/B: the round-1 single-buffered tile kernel on the same inputs
+    t_gae_v1 = t_gae_v3 = None
+    if h in (128, 256, 512) and n % 4 == 0:      # A/B: the other tile-kernel variants on the same inputs
         try:
             _native.check(lib.pb_gae_set_variant(1))
             gae(0)
             t_gae_v1 = time_launches(gae, 16)
+            _native.check(lib.pb_gae_set_variant(3))
+            gae(0)
+            t_gae_v3 = time_launches(gae, 16)
         finally:
             lib.pb_gae_set_variant(2)
     del sets
@@ -240,6 +243,9 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     gae_kernel = 'k_gae_fast' if (h in (128, 256, 512) and n % 4 == 0) else 'k_gae'
     gae_kernel = 'k_gae_tile' if gae_kernel == 'k_gae_fast' else gae_kernel
     out['gae'] = dict(kernel=gae_kernel, bytes_per_launch=n * h * 20, seconds=t_gae, launches_per_step=1)
+    if t_gae_v3 is not None:
+        out['gae_single_buffered'] = dict(kernel='k_gae_tile, NBUF = 1 (for comparison)', bytes_per_launch=n * h * 20,
+                                          seconds=t_gae_v3, launches_per_step=0)
     if t_gae_v1 is not None:
         out['gae_round1_kernel'] = dict(kernel='k_gae_fast (round 1, for comparison)', bytes_per_launch=n * h * 20,
                                         seconds=t_gae_v1, launches_per_step=0)
@@ -344,12 +350,15 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                         _native.ptr(f32[0]), _native.ptr(f32[1]), _native.ptr(f32[2]), _native.ptr(f32[3]), None, r_, n_act,
                         C.c_float(0.1), 1,
                         C.c_float(0.1), C.c_float(0.5), C.c_float(0.01), _native.ptr(gfl), _native.ptr(st8), _native.ptr(ws),
-                        ws.numel(), None, None, None, _native.stream_ptr()))
+                        ws.numel(), _native.ptr(dpre_b) if dpre_b is not None else None, None, None, None, _native.stream_ptr()))
+                dw_mode = str(getattr(data.config, 'fused_update_dw', cp_.FUSED_UPDATE_DW_DEFAULT))
+                dpre_b = None if dw_mode == 'kernel' else torch.empty(mb, 128, device='cuda')
                 with torch.no_grad():
                     upd(0)
                     t_upd = time_launches(upd, 8)
-                out['mlp_update'] = dict(kernel='k_mlp_update_fused (tcgen05) + k_update_reduce', seconds=t_upd,
-                                         bytes_per_launch=mb * (512 + 28), launches_per_step=nm * args.epochs,
+                out['mlp_update'] = dict(kernel=f'k_mlp_update_fused (tcgen05, dW: {dw_mode}) + k_update_reduce', seconds=t_upd,
+                                         bytes_per_launch=mb * (512 + 28 + (512 if dpre_b is not None else 0)),
+                                         launches_per_step=nm * args.epochs,
                                          tf32_tflops=round(2 * 2 * mb * 128 * 128 / t_upd / 1e12, 1))
     for k, v in out.items():
         v['achieved'] = v['bytes_per_launch'] / v['seconds'] / 1e9

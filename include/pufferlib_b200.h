@@ -275,6 +275,9 @@ int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_
  *   returns      nullable: advantages (raw) + old_values is used (clean_pufferl.py:476-481)
  *   grad_flat    [128*128 + 8*128 + 128 + 8]: dW_enc | dW_heads | db_enc | db_heads  (what pb_clip_adam consumes)
  *   stats8       the six loss sums of pb_ppo_loss (zeroed here)
+ *   dpre_out     null: dW_enc = dPre^T x is accumulated inside the kernel (MN-major UMMAs; x is loaded a second time in the
+ *                SWIZZLE_128B_BASE32B layout the tensor core requires for transposed 32-bit operands).  Non-null: dPre
+ *                [M][128] (slab-major rows) is written there instead and the dW_enc part of grad_flat is left to the caller
  *   dbg_*        nullable dumps of relu(h) [M][128], dPre [M][128], dOut [M][8] for validation. */
 size_t pb_mlp_update_workspace_bytes(void);
 int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
@@ -283,7 +286,8 @@ int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t 
                         const float* old_values, const float* adv_norm, int64_t row_slab_stride, int32_t n_act,
                         float clip_coef, int32_t clip_vloss, float vf_clip_coef,
                         float vf_coef, float ent_coef, float* grad_flat, double* stats8, void* workspace,
-                        size_t workspace_bytes, float* dbg_hidden, float* dbg_dpre, float* dbg_dout, void* stream);
+                        size_t workspace_bytes, float* dpre_out, float* dbg_hidden, float* dbg_dpre, float* dbg_dout,
+                        void* stream);
 
 /* Advantage statistics of the zero-copy slab minibatches from ARRIVAL-order advantages (pb_gae_tm): minibatch mb = slabs
  * g * n_minibatches + mb (g < n_slabs) of slab_rows consecutive rows.  norm_out[mb] = (mean, 1 / (unbiased std + 1e-8)),

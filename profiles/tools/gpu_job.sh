@@ -14,8 +14,8 @@ run smoke 120 python -c "import __graft_entry__ as g; g.smoke()"
 run t_rest 500 python -m pytest tests/test_gpu_squared.py tests/test_gpu_experience.py tests/test_gpu_configs.py tests/test_gpu_envs.py -q
 opt encgemm 100 python tests/experimental/check_enc_gemm_tcgen05.py
 B="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-graph --no-extra-configs"
-opt launches 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_r02.csv $B
-for K in k_mlp_update_fused:4 k_breakout_rollout:2 k_gae_fast:2; do
+opt launches 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv $B
+for K in k_mlp_update_fused:4 k_breakout_rollout:2 k_gae_tile:2; do
   NAME=${K%%:*}; SKIP=${K##*:}
   opt ncu_$NAME 150 ncu --set full --clock-control none --import-source on -k regex:$NAME -s $SKIP -c 1 -o gpurun_out/prof_${NAME}_r02 $B
 done

@@ -48,13 +48,16 @@ __device__ __forceinline__ uint32_t bk_draw(uint64_t seed_e, uint32_t& ctr) {
 __device__ __forceinline__ void bk_physics(int& px, int& lives, int& in_play, int& wait, int& vx, int& vy, int& bx, int& by,
                                            int& tick, uint4& bricks, uint32_t& ctr, int a, uint64_t seed_e, int max_ticks,
                                            int& reward, bool& terminal, float& score) {
-    a = a < 0 ? 0 : (a > 3 ? 3 : a);
-    if (a == 2) px = min(px + 4, 136);
-    if (a == 3) px = max(px - 4, 0);
+    // actions are clamped to [0, 3] by the spec (a < 0 -> NOOP, a > 3 -> LEFT).  Written as three comparisons on the raw
+    // value: ptxas 12.9 turned `a = clamp(a, 0, 3); if (a == 3) ..` into a VIMNMX.RELU with predicate outputs whose
+    // predicate came out true for a == 2 on sm_100a (the paddle moved left instead of right; caught by the oracle tests)
+    const bool fire = a == 1, go_right = a == 2, go_left = a >= 3;
+    if (go_right) px = min(px + 4, 136);
+    if (go_left) px = max(px - 4, 0);
     if (!in_play) {
         wait += 1;
         bx = px + 11; by = 188;
-        if (a == 1 || wait >= 16) {
+        if (fire || wait >= 16) {
             in_play = 1; vy = -2;
             const int k = (int)(bk_draw(seed_e, ctr) & 3u);
             vx = k < 2 ? k - 2 : k - 1;   // {-2,-1,1,2}

@@ -923,6 +923,8 @@ extern "C" int pb_gae_tm(const float* rewards, const float* values, const float*
         const bool v2_ok = !(returns_sorted && advantages_time_major);   // v2 stages two outputs: adv + (ret | adv_tm)
         if (g_gae_variant == 2 && v2_ok) {
             if (g.fastKC == 1) PB_GAE_TILE(1, 2, 256) else if (g.fastKC == 2) PB_GAE_TILE(1, 2, 512) else PB_GAE_TILE(2, 1, 512)
+        } else if (g_gae_variant == 3 && v2_ok) {   // single-buffered tiles (more CTAs per SM), coalesced outputs
+            if (g.fastKC == 1) PB_GAE_TILE(1, 1, 256) else if (g.fastKC == 2) PB_GAE_TILE(2, 1, 256) else PB_GAE_TILE(2, 1, 512)
         } else {
             if (g.fastKC == 1) PB_GAE_FAST(1) else if (g.fastKC == 2) PB_GAE_FAST(2) else PB_GAE_FAST(4)
         }
@@ -947,9 +949,10 @@ extern "C" int pb_gae_tm(const float* rewards, const float* values, const float*
     return PB_OK;
 }
 
-// 2 (default): k_gae_tile (double-buffered tiles, coalesced outputs); 1: the round-1 k_gae_fast.  For A/B measurements.
+// 2 (default): k_gae_tile (double-buffered tiles, coalesced outputs); 3: k_gae_tile single-buffered; 1: the round-1
+// k_gae_fast.  For A/B measurements.
 extern "C" int pb_gae_set_variant(int32_t variant) {
-    PB_REQUIRE(variant == 1 || variant == 2, PB_ERR_INVALID, "pb_gae_set_variant: 1 or 2");
+    PB_REQUIRE(variant >= 1 && variant <= 3, PB_ERR_INVALID, "pb_gae_set_variant: 1, 2 or 3");
     g_gae_variant = variant;
     return PB_OK;
 }

@@ -42,13 +42,16 @@ constexpr int KBLK_BYTES = TILE_M * KBLK * 4;          // 16 KiB: one [128 rows]
 constexpr int TILE_BYTES = 4 * KBLK_BYTES;             // 64 KiB
 constexpr int NCHUNK = 4, CHUNK_COLS = 32;
 constexpr int CHUNK_BYTES = TILE_M * CHUNK_COLS * 4;   // 16 KiB: [128 rows][32 hid] MN-major (N contiguous)
-constexpr int NBUF = 2;                                // dPre chunk buffers
-constexpr int SMEM_W = 0, SMEM_X = TILE_BYTES, SMEM_CH = 3 * TILE_BYTES;
-constexpr int SMEM_BAR = SMEM_CH + NBUF * CHUNK_BYTES;
+constexpr int SMEM_W = 0;                              // W_enc, K-major SWIZZLE_128B, resident
+constexpr int SMEM_XK = TILE_BYTES;                    // x tile for the forward product: K-major SWIZZLE_128B
+constexpr int SMEM_XM = 2 * TILE_BYTES;                // x tile for the dW product: MN-major SWIZZLE_128B_BASE32B
+constexpr int SMEM_CH = 3 * TILE_BYTES;                // two dPre chunk buffers (one per column half)
+constexpr int SMEM_BAR = SMEM_CH + 2 * CHUNK_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;                           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_DW = 256;                           // first column of the dW^T accumulator
+constexpr int TMEM_XCHG = 384;                         // 16 columns: the partial head sums the two warps of a row exchange
 constexpr int TAIL = NO * HID + HID + NO;              // dW_heads | db_enc | db_heads
 static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
 
@@ -75,6 +78,7 @@ struct FusedParams {
     float* part_dw;            // [grid][FEAT][HID]
     float* part_tail;          // [grid][TAIL]
     double* stats;             // [8]
+    float* dpre_out;           // DW_KERNEL = false: dPre [m][128] (slab-major rows) for the caller's dW GEMM
     float* dbg_hidden;         // nullable [m][128]
     float* dbg_dpre;           // nullable [m][128]
     float* dbg_dout;           // nullable [m][8]
@@ -96,11 +100,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+// MN-major 32-bit operands: layout type 1 (SWIZZLE_128B_BASE32B), atoms of 4 k x 128 B, SBO = 512 B between 4-k groups,
+// LBO = distance between 32-element MN groups
+__device__ __forceinline__ uint64_t desc_mn32(uint32_t saddr, uint32_t lbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
 }
 // instruction descriptor: D fmt F32 (1<<4) | A TF32 (2<<7) | B TF32 (2<<10) | A major bit 15 | B major bit 16 | N>>3 <<17 | M>>4 <<24
 constexpr uint32_t IDESC_FWD = (1u << 4) | (2u << 7) | (2u << 10) | ((HID >> 3) << 17) | ((TILE_M >> 4) << 24);
+constexpr uint32_t IDESC_HEADS = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((TILE_M >> 4) << 24);
 constexpr uint32_t IDESC_DW = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((CHUNK_COLS >> 3) << 17) |
                               ((FEAT >> 4) << 24);
 
@@ -113,6 +120,47 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
         "}\n" ::"r"(tmem_d),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(   // A operand from tensor memory: lanes = rows (M), columns = K
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
+        "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])),
+        "r"(__float_as_uint(r[8])), "r"(__float_as_uint(r[9])), "r"(__float_as_uint(r[10])), "r"(__float_as_uint(r[11])),
+        "r"(__float_as_uint(r[12])), "r"(__float_as_uint(r[13])), "r"(__float_as_uint(r[14])), "r"(__float_as_uint(r[15])),
+        "r"(__float_as_uint(r[16])), "r"(__float_as_uint(r[17])), "r"(__float_as_uint(r[18])), "r"(__float_as_uint(r[19])),
+        "r"(__float_as_uint(r[20])), "r"(__float_as_uint(r[21])), "r"(__float_as_uint(r[22])), "r"(__float_as_uint(r[23])),
+        "r"(__float_as_uint(r[24])), "r"(__float_as_uint(r[25])), "r"(__float_as_uint(r[26])), "r"(__float_as_uint(r[27])),
+        "r"(__float_as_uint(r[28])), "r"(__float_as_uint(r[29])), "r"(__float_as_uint(r[30])), "r"(__float_as_uint(r[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
+                 "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -233,31 +281,44 @@ __device__ __forceinline__ uint32_t chunk_off(int r, int j) {
 }
 
 // NH = live rows of the 8-row head matrix (n_act logits + the value): rows >= NH are zero padding, their products are skipped
-template <int NH>
+// byte offset of element (row r, column j) of a [128 rows][32 floats] chunk in the SWIZZLE_128B_BASE32B layout (32-byte
+// pieces of a 128-byte row, piece index ^= row & 3): the layout the tensor core requires for MN-major 32-bit operands
+// (UMMA layout type 1; TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Conflict-free for the fragment loads of
+// the dW_heads mma.sync and for the column sums; 2-way for the row-owner 128-bit stores.
+__device__ __forceinline__ uint32_t chunk32_off(int r, int j) {
+    return (uint32_t)(r * 128 + ((((j >> 3) ^ (r & 3))) << 5) + ((j & 7) << 2));
+}
+
+// DW_KERNEL = true : dW_enc^T accumulated in TMEM by MN-major UMMAs (x tile loaded a second time in the BASE32B layout)
+// DW_KERNEL = false: dPre goes to HBM (p.dpre_out) and the caller forms dW_enc = dPre^T x with a library GEMM
+template <int NH, bool DW_KERNEL>
 __global__ void __launch_bounds__(THREADS, 1)
-k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
+k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_x32,
+                   const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
-    uint64_t* w_full = bars;              // [1]
-    uint64_t* x_full = bars + 1;          // [2]
-    uint64_t* x_empty = bars + 3;         // [2]
-    uint64_t* h_full = bars + 5;          // [2]
-    uint64_t* h_empty = bars + 7;         // [2]  count 4 (epilogue warps)
-    uint64_t* dp_full = bars + 9;         // [NBUF] count 4
-    uint64_t* dp_empty = bars + 9 + NBUF; // [NBUF]
-    uint64_t* dw_done = bars + 9 + 2 * NBUF;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * NBUF);
+    uint64_t* w_full = bars;              // W_enc resident
+    uint64_t* xk_full = bars + 1;         // forward operand tile (K-major SW128) landed
+    uint64_t* xk_empty = bars + 2;        // ... consumed by the forward MMAs
+    uint64_t* xm_full = bars + 3;         // dW operand tile (MN-major BASE32B) landed
+    uint64_t* xm_empty = bars + 4;        // ... consumed by the dW MMAs of the tile
+    uint64_t* h_full = bars + 5;          // [2] forward accumulator complete
+    uint64_t* h_empty = bars + 7;         // [2] drained by the 8 epilogue warps
+    uint64_t* dp_full = bars + 9;         // [2] dPre chunk of column half hh written (4 warps)
+    uint64_t* dp_empty = bars + 11;       // [2] ... consumed by its dW MMAs
+    uint64_t* dw_done = bars + 13;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(w_full, 1);
+        mbar_init(xk_full, 1);
+        mbar_init(xk_empty, 1);
+        mbar_init(xm_full, 1);
+        mbar_init(xm_empty, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&x_full[i], 1);
-            mbar_init(&x_empty[i], 1);
             mbar_init(&h_full[i], 1);
-            mbar_init(&h_empty[i], 4);
-        }
-        for (int i = 0; i < NBUF; ++i) {
+            mbar_init(&h_empty[i], 8);
             mbar_init(&dp_full[i], 4);
             mbar_init(&dp_empty[i], 1);
         }
@@ -276,16 +337,17 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
     const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA (>= 1)
 
-    // per-thread results of the epilogue warps, reduced after the role loops
-    float acc_wh[NCHUNK][4][2];          // dW_heads[a = lane>>2][j = 32c + 8nb + 2(lane&3) + {0,1}]  (this warp's rows)
-    float acc_benc[NCHUNK];              // db_enc[32c + lane]
-    float acc_bh[NO];                    // db_heads (this thread's rows)
+    // per-thread results of the epilogue warps, reduced after the role loops.  Epilogue warp (q, hh): TMEM lane quadrant q
+    // (tile rows 32q..32q+31), column half hh = hidden units 64hh..64hh+63 = chunks 2hh, 2hh+1.
+    float acc_wh[2][4][2];               // dW_heads[a = lane>>2][j = 32(2hh+cc) + 8nb + 2(lane&3) + {0,1}]  (this warp's rows)
+    float acc_benc[2];                   // db_enc[32(2hh+cc) + lane]
+    float acc_bh[NO];                    // db_heads (this thread's rows; hh == 0 only)
     double st[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) {
-        acc_benc[c] = 0.f;
+    for (int cc = 0; cc < 2; ++cc) {
+        acc_benc[cc] = 0.f;
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) acc_wh[c][nb][0] = acc_wh[c][nb][1] = 0.f;
+        for (int nb = 0; nb < 4; ++nb) acc_wh[cc][nb][0] = acc_wh[cc][nb][1] = 0.f;
     }
 #pragma unroll
     for (int k = 0; k < NO; ++k) acc_bh[k] = 0.f;
@@ -297,60 +359,72 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
             for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + SMEM_W + kb * KBLK_BYTES, &map_w, kb * KBLK, 0, w_full);
             for (int it = 0; it < n_my; ++it) {
                 const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-                const int s = it & 1, ph = (it >> 1) & 1;
                 const int64_t row0 = (int64_t)(tile / p.tiles_per_slab) * p.slab_stride_rows +
                                      (int64_t)(tile % p.tiles_per_slab) * TILE_M;
-                mbar_wait(&x_empty[s], ph ^ 1);
-                mbar_expect_tx(&x_full[s], TILE_BYTES);
-                uint8_t* dst = smem + SMEM_X + s * TILE_BYTES;
-                for (int kb = 0; kb < 4; ++kb) tma_load_2d(dst + kb * KBLK_BYTES, &map_x, kb * KBLK, (int)row0, &x_full[s]);
+                mbar_wait(xk_empty, (uint32_t)((it & 1) ^ 1));          // forward MMAs of tile it-1 have read the buffer
+                mbar_expect_tx(xk_full, TILE_BYTES);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + SMEM_XK + kb * KBLK_BYTES, &map_x, kb * KBLK, (int)row0, xk_full);
+                if (DW_KERNEL) {   // the same rows again (L2 hits) in the MN-major layout of the dW product
+                    mbar_wait(xm_empty, (uint32_t)((it & 1) ^ 1));      // dW MMAs of tile it-1 done
+                    mbar_expect_tx(xm_full, TILE_BYTES);
+                    for (int kb = 0; kb < 4; ++kb)
+                        tma_load_2d(smem + SMEM_XM + kb * KBLK_BYTES, &map_x32, kb * KBLK, (int)row0, xm_full);
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             const uint32_t w_addr = smem_u32(smem + SMEM_W);
+            const uint32_t xk_addr = smem_u32(smem + SMEM_XK), xm_addr = smem_u32(smem + SMEM_XM);
             auto forward = [&](int it) {
                 const int s = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(&h_empty[s], ph ^ 1);     // epilogue drained accumulator stage s (tile it - 2)
-                mbar_wait(&x_full[s], ph);          // x tile landed
+                mbar_wait(&h_empty[s], ph ^ 1);                  // epilogue drained accumulator stage s (tile it - 2)
+                mbar_wait(xk_full, (uint32_t)(it & 1));          // x tile landed
                 tc_fence_after();
-                const uint32_t x_addr = smem_u32(smem + SMEM_X + s * TILE_BYTES);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(s * HID);
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_tf32(d_tmem, desc_kmajor(x_addr + kb * KBLK_BYTES + k * 32),
+                        umma_tf32(d_tmem, desc_kmajor(xk_addr + kb * KBLK_BYTES + k * 32),
                                   desc_kmajor(w_addr + kb * KBLK_BYTES + k * 32), IDESC_FWD, (kb | k) ? 1u : 0u);
                 umma_commit(&h_full[s]);
+                umma_commit(xk_empty);                           // the K-major tile may be overwritten: next tile's load starts
             };
             mbar_wait(w_full, 0);
             forward(0);
             for (int it = 0; it < n_my; ++it) {
-                if (it + 1 < n_my) forward(it + 1);            // overlaps the epilogue of tile `it`
-                const uint32_t x_addr = smem_u32(smem + SMEM_X + (it & 1) * TILE_BYTES);
-                for (int c = 0; c < NCHUNK; ++c) {
-                    const int n = it * NCHUNK + c, b = n % NBUF;
-                    mbar_wait(&dp_full[b], (uint32_t)((n / NBUF) & 1));
-                    tc_fence_after();
-                    const uint32_t ch_addr = smem_u32(smem + SMEM_CH + b * CHUNK_BYTES);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(TMEM_DW + c * CHUNK_COLS);
+                if (it + 1 < n_my) forward(it + 1);              // overlaps the epilogue of tile `it`
+                if (DW_KERNEL) {
+                    mbar_wait(xm_full, (uint32_t)(it & 1));
+                    // chunks arrive alternately from the two column halves: 0 (hh 0), 2 (hh 1), 1 (hh 0), 3 (hh 1)
+#pragma unroll 1
+                    for (int i = 0; i < NCHUNK; ++i) {
+                        const int hh = i & 1, cc = i >> 1, c = 2 * hh + cc;
+                        const int u = it * 2 + cc;               // use count of chunk buffer hh
+                        mbar_wait(&dp_full[hh], (uint32_t)(u & 1));
+                        tc_fence_after();
+                        const uint32_t ch_addr = smem_u32(smem + SMEM_CH + hh * CHUNK_BYTES);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(TMEM_DW + c * CHUNK_COLS);
 #pragma unroll
-                    for (int k = 0; k < TILE_M / 8; ++k)      // K = 8 rows per MMA: one 1 KiB swizzle atom per step
-                        umma_tf32(d_tmem, desc_mnmajor(x_addr + k * 1024, KBLK_BYTES), desc_mnmajor(ch_addr + k * 1024, KBLK_BYTES),
-                                  IDESC_DW, (it | k) ? 1u : 0u);
-                    umma_commit(&dp_empty[b]);
+                        for (int k = 0; k < TILE_M / 8; ++k)      // K = 8 rows per MMA = two 512-byte atoms
+                            umma_tf32(d_tmem, desc_mn32(xm_addr + k * 1024, KBLK_BYTES), desc_mn32(ch_addr + k * 1024, KBLK_BYTES),
+                                      IDESC_DW, (it | k) ? 1u : 0u);
+                        umma_commit(&dp_empty[hh]);
+                    }
+                    umma_commit(xm_empty);
                 }
-                umma_commit(&x_empty[it & 1]);                 // x stage reusable once the dW MMAs have read it
             }
             umma_commit(dw_done);
         }
     } else {
-        // ================= epilogue warps: thread = tile row = TMEM lane 32q + lane =================
-        const int q = warp & 3;
+        // ================= epilogue warps: thread = tile row (TMEM lane 32q + lane), column half hh =================
+        const int q = warp & 3, hh = (warp - 2) >> 2;
         const int g = lane >> 2, t = lane & 3;
         const int rloc = 32 * q + lane;                        // row inside the tile
+        uint8_t* buf = smem + SMEM_CH + hh * CHUNK_BYTES;      // this half's chunk buffer; this warp owns rows 32q..32q+31
+        const uint32_t xchg = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)TMEM_XCHG;
         float z0 = 0.f, z1 = 0.f;                              // dummy accumulators of the zero A rows
         for (int it = 0; it < n_my; ++it) {
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
@@ -358,7 +432,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
             const int slab = tile / p.tiles_per_slab;
             const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
             const bool valid = lrow < p.slab_rows;
-            const int64_t i = (int64_t)slab * p.slab_rows + lrow;            // slab-major position (debug dumps)
+            const int64_t i = (int64_t)slab * p.slab_rows + lrow;            // slab-major position (dPre / debug rows)
             const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;     // position in the per-row arrays
             int act = 0;
             float old_lp = 0.f, adv = 0.f, ret = 0.f, old_v = 0.f;
@@ -374,43 +448,68 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * HID);
 
-            // ---- pass 1: heads
+            // ---- pass 1: this half's share of the head products, exchanged with the partner warp through tensor memory
             float out[NO];
 #pragma unroll
-            for (int a = 0; a < NO; ++a) out[a] = c_bh[a];
+            for (int a = 0; a < NO; ++a) out[a] = 0.f;
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {     // fully unrolled: every c_wh / c_benc operand is a constant-bank immediate
+            for (int cc = 0; cc < 2; ++cc) {
                 float v[32];
-                tmem_ld32(taddr + 32 * c, v);
+                if (hh == 0) {      // (compile-time column offsets: every c_wh / c_benc operand is a constant-bank immediate)
+                    tmem_ld32(taddr + 32 * cc, v);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float rh = fmaxf(v[k] + c_benc[32 * c + k], 0.f);
+                    for (int k = 0; k < 32; ++k) {
+                        const float rh = fmaxf(v[k] + c_benc[32 * cc + k], 0.f);
 #pragma unroll
-                    for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * c + k], out[a]);
+                        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * cc + k], out[a]);
+                    }
+                } else {
+                    tmem_ld32(taddr + 64 + 32 * cc, v);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const float rh = fmaxf(v[k] + c_benc[64 + 32 * cc + k], 0.f);
+#pragma unroll
+                        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 64 + 32 * cc + k], out[a]);
+                    }
                 }
             }
-            // ---- loss row math -> dOut
+            tmem_st8(xchg + 8 * hh, out);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // the two warps of quadrant q
+            tc_fence_after();
+            {
+                float other[NO];
+                tmem_ld8(xchg + 8 * (hh ^ 1), other);
+#pragma unroll
+                for (int a = 0; a < NO; ++a) out[a] = (hh == 0 ? out[a] + other[a] : other[a] + out[a]) + c_bh[a];   // same order in both
+            }
+            // the partner must have read my partial before the next tile overwrites it: second rendezvous at the end of the tile
+
+            // ---- loss row math -> dOut (both warps of the pair compute it; the statistics are taken by hh == 0)
             float dO[NO];
 #pragma unroll
             for (int a = 0; a < NO; ++a) dO[a] = 0.f;
             if (valid) {
                 const RowStats rs = ppo_row(out, p, act, old_lp, adv, ret, old_v, dO);
-                st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
-                if (p.dbg_dout) {
-                    *reinterpret_cast<float4*>(p.dbg_dout + i * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-                    *reinterpret_cast<float4*>(p.dbg_dout + i * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                if (hh == 0) {
+                    st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
+                    if (p.dbg_dout) {
+                        *reinterpret_cast<float4*>(p.dbg_dout + i * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+                        *reinterpret_cast<float4*>(p.dbg_dout + i * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                    }
                 }
             }
+            if (hh == 0) {
 #pragma unroll
-            for (int a = 0; a < NO; ++a) acc_bh[a] += dO[a];
+                for (int a = 0; a < NO; ++a) acc_bh[a] += dO[a];
+            }
 
-            // ---- A fragments of the dW_heads mma (A[m = head a][k = row]): staged through this warp's rows of the chunk
-            //      buffer the first chunk will use (32 B per row; private to the warp until the dPre chunk is published)
+            // ---- A fragments of the dW_heads mma (A[m = head a][k = row]) staged through this warp's rows of its half's
+            //      chunk buffer (32 B per row; private to the warp until a dPre chunk is published)
             uint32_t afr[4][2];
             {
-                const int n0 = it * NCHUNK, b0 = n0 % NBUF;
-                mbar_wait(&dp_empty[b0], (uint32_t)(((n0 / NBUF) & 1) ^ 1));
-                uint8_t* buf = smem + SMEM_CH + b0 * CHUNK_BYTES;
+                if (DW_KERNEL) mbar_wait(&dp_empty[hh], (uint32_t)(((it * 2) & 1) ^ 1));
                 *reinterpret_cast<float4*>(buf + rloc * 128) = make_float4(dO[0], dO[1], dO[2], dO[3]);
                 *reinterpret_cast<float4*>(buf + rloc * 128 + 16) = make_float4(dO[4], dO[5], dO[6], dO[7]);
                 __syncwarp();
@@ -422,110 +521,137 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 __syncwarp();
             }
 
-            // ---- pass 2: per 32-column chunk  dPre -> shared memory (UMMA operand), dW_heads, db_enc
+            // ---- pass 2: this half's two 32-column chunks: dPre, dW_heads, db_enc
 #pragma unroll
-            for (int c = 0; c < NCHUNK; ++c) {
-                const int n = it * NCHUNK + c, b = n % NBUF;
-                uint8_t* buf = smem + SMEM_CH + b * CHUNK_BYTES;
-                float v[32];
-                tmem_ld32(taddr + 32 * c, v);
-                float dp[32];
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32], dp[32];
+                const int col0 = 64 * hh + 32 * cc;           // first hidden unit of the chunk (hh is warp-uniform)
+                tmem_ld32(taddr + col0, v);
+                if (hh == 0) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const float pre = v[k] + c_benc[32 * c + k];
-                    float gk = 0.f;
+                    for (int k = 0; k < 32; ++k) {
+                        const float pre = v[k] + c_benc[32 * cc + k];
+                        float gk = 0.f;
 #pragma unroll
-                    for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * c + k], gk);
-                    dp[k] = pre > 0.f ? gk : 0.f;
-                    v[k] = fmaxf(pre, 0.f);                    // relu(h)
+                        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * cc + k], gk);
+                        dp[k] = pre > 0.f ? gk : 0.f;
+                        v[k] = fmaxf(pre, 0.f);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const float pre = v[k] + c_benc[64 + 32 * cc + k];
+                        float gk = 0.f;
+#pragma unroll
+                        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 64 + 32 * cc + k], gk);
+                        dp[k] = pre > 0.f ? gk : 0.f;
+                        v[k] = fmaxf(pre, 0.f);
+                    }
                 }
                 if (valid && p.dbg_hidden) {
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
-                        *reinterpret_cast<float4*>(p.dbg_hidden + i * HID + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-                        *reinterpret_cast<float4*>(p.dbg_dpre + i * HID + 32 * c + k) = make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]);
+                        *reinterpret_cast<float4*>(p.dbg_hidden + i * HID + col0 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                        *reinterpret_cast<float4*>(p.dbg_dpre + i * HID + col0 + k) = make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]);
                     }
                 }
-                mbar_wait(&dp_empty[b], (uint32_t)(((n / NBUF) & 1) ^ 1));     // the dW MMAs of the buffer's last use retired
+                if (!DW_KERNEL && valid) {                      // dPre row segment to HBM (128 contiguous bytes per thread)
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4)
+                        __stcs(reinterpret_cast<float4*>(p.dpre_out + i * HID + col0 + k), make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]));
+                }
+                if (DW_KERNEL) mbar_wait(&dp_empty[hh], (uint32_t)(((it * 2 + cc) & 1) ^ 1));   // last use of the buffer consumed
                 // relu(h) chunk of this warp's 32 rows (TF32-rounded) -> B fragments of the dW_heads mma
 #pragma unroll
-                for (int jc = 0; jc < 8; ++jc)
-                    *reinterpret_cast<uint4*>(buf + rloc * 128 + ((jc ^ (rloc & 7)) << 4)) =
-                        make_uint4(to_tf32(v[4 * jc]), to_tf32(v[4 * jc + 1]), to_tf32(v[4 * jc + 2]), to_tf32(v[4 * jc + 3]));
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint8_t* dst = buf + rloc * 128 + ((j8 ^ (rloc & 3)) << 5);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(to_tf32(v[8 * j8]), to_tf32(v[8 * j8 + 1]), to_tf32(v[8 * j8 + 2]), to_tf32(v[8 * j8 + 3]));
+                    *reinterpret_cast<uint4*>(dst + 16) = make_uint4(to_tf32(v[8 * j8 + 4]), to_tf32(v[8 * j8 + 5]), to_tf32(v[8 * j8 + 6]), to_tf32(v[8 * j8 + 7]));
+                }
                 __syncwarp();
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                     const int r0 = 32 * q + 8 * ks + t;
 #pragma unroll
                     for (int nb = 0; nb < 4; ++nb) {
-                        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(buf + chunk_off(r0, 8 * nb + g));
-                        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(buf + chunk_off(r0 + 4, 8 * nb + g));
-                        mma_tf32(acc_wh[c][nb][0], acc_wh[c][nb][1], z0, z1, afr[ks], b0, b1);
+                        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(buf + chunk32_off(r0, 8 * nb + g));
+                        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(buf + chunk32_off(r0 + 4, 8 * nb + g));
+                        mma_tf32(acc_wh[cc][nb][0], acc_wh[cc][nb][1], z0, z1, afr[ks], b0, b1);
                     }
                 }
                 __syncwarp();
-                // dPre chunk -> the same rows (MN-major SW128 operand of the dW UMMA)
+                // dPre chunk -> the same rows, BASE32B layout (the MN-major B operand of the dW UMMA)
 #pragma unroll
-                for (int jc = 0; jc < 8; ++jc)
-                    *reinterpret_cast<float4*>(buf + rloc * 128 + ((jc ^ (rloc & 7)) << 4)) =
-                        make_float4(dp[4 * jc], dp[4 * jc + 1], dp[4 * jc + 2], dp[4 * jc + 3]);
-                fence_proxy_async_smem();
+                for (int j8 = 0; j8 < 4; ++j8) {
+                    uint8_t* dst = buf + rloc * 128 + ((j8 ^ (rloc & 3)) << 5);
+                    *reinterpret_cast<float4*>(dst) = make_float4(dp[8 * j8], dp[8 * j8 + 1], dp[8 * j8 + 2], dp[8 * j8 + 3]);
+                    *reinterpret_cast<float4*>(dst + 16) = make_float4(dp[8 * j8 + 4], dp[8 * j8 + 5], dp[8 * j8 + 6], dp[8 * j8 + 7]);
+                }
+                if (DW_KERNEL) fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&dp_full[b]);
-                // db_enc: column sums over this warp's rows (reads race with nothing: the UMMA only reads)
+                if (DW_KERNEL && lane == 0) mbar_arrive(&dp_full[hh]);
+                // db_enc: column sums over this warp's rows (the UMMA only reads the buffer)
                 float cs = 0.f;
 #pragma unroll 8
-                for (int r = 0; r < 32; ++r) cs += *reinterpret_cast<const float*>(buf + chunk_off(32 * q + r, lane));
-                acc_benc[c] += cs;
+                for (int r = 0; r < 32; ++r) cs += *reinterpret_cast<const float*>(buf + chunk32_off(32 * q + r, lane));
+                acc_benc[cc] += cs;
+                __syncwarp();                                    // (mode without UMMA: the next chunk overwrites the rows)
             }
             tc_fence_before();
-            __syncwarp();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both warps are done with the exchange columns
             if (lane == 0) mbar_arrive(&h_empty[s]);
         }
-        // ---- the dW^T accumulator of this CTA: TMEM lane = feature, column = hidden unit
-        mbar_wait(dw_done, 0);
-        tc_fence_after();
-        float* pd = p.part_dw + ((int64_t)blockIdx.x * FEAT + rloc) * HID;
+        // ---- the dW^T accumulator of this CTA: TMEM lane = feature, column = hidden unit; this warp dumps its column half
+        if (DW_KERNEL) {
+            mbar_wait(dw_done, 0);
+            tc_fence_after();
+            float* pd = p.part_dw + ((int64_t)blockIdx.x * FEAT + rloc) * HID;
 #pragma unroll 1
-        for (int c = 0; c < NCHUNK; ++c) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(TMEM_DW + 32 * c), v);
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                const int col0 = 64 * hh + 32 * cc;
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(TMEM_DW + col0), v);
 #pragma unroll
-            for (int k = 0; k < 32; k += 4)
-                *reinterpret_cast<float4*>(pd + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                for (int k = 0; k < 32; k += 4)
+                    *reinterpret_cast<float4*>(pd + col0 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+            }
         }
-        // loss statistics: warp reduce, one fp64 atomic per warp and statistic
+        if (hh == 0) {   // loss statistics: warp reduce, one fp64 atomic per warp and statistic
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            double x = st[k];
+            for (int k = 0; k < 6; ++k) {
+                double x = st[k];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-            if (lane == 0) atomicAdd(p.stats + k, x);
+                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                if (lane == 0) atomicAdd(p.stats + k, x);
+            }
         }
     }
 
-    // ================= CTA reduction of the small gradients (4 epilogue warps -> one partial row) =================
+    // ================= CTA reduction of the small gradients (8 epilogue warps -> one partial row) =================
     tc_fence_before();
-    __syncthreads();                       // every role is done: all MMAs retired (dw_done), all TMA loads consumed
-    float* red = reinterpret_cast<float*>(smem + SMEM_X);          // [4][TAIL] scratch in the (now idle) x stages
+    __syncthreads();                       // every role is done: all MMAs retired, all TMA loads consumed
+    float* red = reinterpret_cast<float*>(smem + SMEM_XK);         // [4 quadrants][TAIL] scratch in the (now idle) x tile
     if (warp >= 2) {
-        const int q = warp & 3, g = lane >> 2, t = lane & 3;
-        float* mine = red + q * TAIL;
+        const int q = warp & 3, hh = (warp - 2) >> 2, g = lane >> 2, t = lane & 3;
+        float* mine = red + q * TAIL;      // the two warps of a quadrant fill disjoint columns of the same row
 #pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int col0 = 64 * hh + 32 * cc;
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                mine[g * HID + 32 * c + 8 * nb + 2 * t] = acc_wh[c][nb][0];
-                mine[g * HID + 32 * c + 8 * nb + 2 * t + 1] = acc_wh[c][nb][1];
+                mine[g * HID + col0 + 8 * nb + 2 * t] = acc_wh[cc][nb][0];
+                mine[g * HID + col0 + 8 * nb + 2 * t + 1] = acc_wh[cc][nb][1];
             }
-            mine[NO * HID + 32 * c + lane] = acc_benc[c];
+            mine[NO * HID + col0 + lane] = acc_benc[cc];
         }
+        if (hh == 0) {
 #pragma unroll
-        for (int k = 0; k < NO; ++k) {
-            float x = acc_bh[k];
+            for (int k = 0; k < NO; ++k) {
+                float x = acc_bh[k];
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-            if (lane == 0) mine[NO * HID + HID + k] = x;
+                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                if (lane == 0) mine[NO * HID + HID + k] = x;
+            }
         }
     }
     __syncthreads();
@@ -545,6 +671,7 @@ __global__ void __launch_bounds__(256) k_update_reduce(const float* __restrict__
     const int e = blockIdx.x * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
     constexpr int NDW = FEAT * HID;
     float s = 0.f;
+    if (e < NDW && !part_dw) return;          // dW_enc is formed by the caller (dPre went to HBM); whole blocks: NDW % 64 == 0
     if (e < NDW + TAIL) {
         const float* src = e < NDW ? part_dw + e : part_tail + (e - NDW);
         const int64_t stride = e < NDW ? NDW : TAIL;
@@ -564,13 +691,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t rows, int64_t row_stride_floats) {
+int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t rows, int64_t row_stride_floats,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     const cuuint64_t dims[2] = {(cuuint64_t)FEAT, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)row_stride_floats * 4};
     const cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)TILE_M};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PB_REQUIRE(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
     return PB_OK;
@@ -590,8 +718,8 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
                                    const float* returns, const float* old_values, const float* adv_norm,
                                    int64_t row_slab_stride, int32_t n_act, float clip_coef,
                                    int32_t clip_vloss, float vf_clip_coef, float vf_coef, float ent_coef, float* grad_flat,
-                                   double* stats8, void* workspace, size_t workspace_bytes, float* dbg_hidden,
-                                   float* dbg_dpre, float* dbg_dout, void* stream) {
+                                   double* stats8, void* workspace, size_t workspace_bytes, float* dpre_out,
+                                   float* dbg_hidden, float* dbg_dpre, float* dbg_dout, void* stream) {
     PB_REQUIRE(x && w_enc && b_enc && w_heads && b_heads && actions && old_logprobs && advantages && grad_flat && stats8 &&
                    workspace && (returns || old_values),
                PB_ERR_INVALID, "pb_mlp_update_fused: null pointer");
@@ -612,8 +740,9 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
     const int64_t n_tiles = tiles_per_slab * n_slabs;
     const int64_t map_rows = (int64_t)(n_slabs - 1) * slab_stride_rows + slab_rows;
     PB_REQUIRE(n_tiles <= 0x7FFFFFFF && map_rows <= 0x7FFFFFFF, PB_ERR_UNSUPPORTED, "pb_mlp_update_fused: too many rows");
-    alignas(64) CUtensorMap map_x, map_w;
+    alignas(64) CUtensorMap map_x, map_x32, map_w;
     int rc = make_map2((EncodeTiledFn)fn, &map_x, x, map_rows, ldx);
+    if (rc == PB_OK) rc = make_map2((EncodeTiledFn)fn, &map_x32, x, map_rows, ldx, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc == PB_OK) rc = make_map2((EncodeTiledFn)fn, &map_w, w_enc, HID, FEAT);
     if (rc != PB_OK) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -625,22 +754,29 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
     p.tiles_per_slab = (int)tiles_per_slab; p.n_tiles = (int)n_tiles; p.n_act = n_act;
     p.clip = clip_coef; p.vclip = vf_clip_coef; p.vf_coef = vf_coef; p.ent_coef = ent_coef; p.clip_vloss = clip_vloss;
     p.part_dw = (float*)workspace; p.part_tail = (float*)workspace + (size_t)num_sms() * FEAT * HID;
-    p.stats = stats8; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
+    p.stats = stats8; p.dpre_out = dpre_out; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
     PB_CUDA(cudaMemsetAsync(stats8, 0, 8 * sizeof(double), s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_benc, b_enc, sizeof(float) * HID, 0, cudaMemcpyDeviceToDevice, s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_bh, b_heads, sizeof(float) * NO, 0, cudaMemcpyDeviceToDevice, s));
-    // dispatch on the live head rows (n_act + 1): 5 for the 4-action configs, 8 = generic
+    // dispatch on the live head rows (n_act + 1: 5 for the 4-action configs, 8 = generic) and on where dW_enc is formed
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         attr_set = true;
     }
-    if (n_act + 1 <= 5) k_mlp_update_fused<5><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
-    else k_mlp_update_fused<8><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_w, p);
+    if (dpre_out) {
+        if (n_act + 1 <= 5) k_mlp_update_fused<5, false><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
+        else k_mlp_update_fused<8, false><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
+    } else {
+        if (n_act + 1 <= 5) k_mlp_update_fused<5, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
+        else k_mlp_update_fused<8, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
+    }
     PB_LAUNCH_CHECK();
-    k_update_reduce<<<(FEAT * HID + TAIL + 63) / 64, 256, 0, s>>>(p.part_dw, p.part_tail, grid, grad_flat);
+    k_update_reduce<<<(FEAT * HID + TAIL + 63) / 64, 256, 0, s>>>(dpre_out ? nullptr : p.part_dw, p.part_tail, grid, grad_flat);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

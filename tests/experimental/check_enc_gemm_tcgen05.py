@@ -39,7 +39,7 @@ def main():
         ref = torch.relu(x @ w.t() + b)
         err = float((out - ref).abs().max())
         print(f'm={m:8d} max abs err {err:.3e}')
-        assert err < 5e-3, err
+        assert err < 1e-2, err        # TF32: both operands truncated to 10 mantissa bits, K = 128 products
     # strided rows (a [R, 128] window of a wider buffer)
     big = torch.randn(4096, 256, device=dev)
     x = big[:, 64:192]

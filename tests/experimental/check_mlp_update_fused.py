@@ -33,7 +33,8 @@ def rna_tf32(t):
     return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def fused(xbuf, ldx, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval, n_act, debug):
+def fused(xbuf, ldx, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval, n_act, debug,
+          dpre_out=None):
     dev = xbuf.device
     m = slab_rows * n_slabs
     gflat = torch.full((128 * 128 + 8 * 128 + 128 + 8,), float('nan'), device=dev)
@@ -46,7 +47,7 @@ def fused(xbuf, ldx, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat
         do = torch.full((m, 8), float('nan'), device=dev)
     _native.check(lib.pb_mlp_update_fused(ptr(xbuf), ldx, slab_rows, slab_stride, n_slabs, ptr(w_enc), ptr(b_enc), ptr(w_cat), ptr(b_cat),
                                   ptr(act), ptr(olp), ptr(adv), ptr(ret), ptr(oval), None, slab_rows, n_act, CFG[0], CFG[1], CFG[2], CFG[3],
-                                  CFG[4], ptr(gflat), ptr(stats), ptr(ws), ws.numel(), ptr(dh), ptr(dp), ptr(do),
+                                  CFG[4], ptr(gflat), ptr(stats), ptr(ws), ws.numel(), ptr(dpre_out), ptr(dh), ptr(dp), ptr(do),
                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     return gflat, stats, dh, dp, do
 
@@ -120,6 +121,15 @@ def case(slab_rows, n_slabs, slab_stride, n_act, seed):
     dpre32 = (dout32.double() @ w_cat.double()) * (h32 > 0)
     ok &= check('dW_enc vs fp64 chain (TF32 tol)', dw_enc, dpre32.t() @ x.double(), 5e-3)
     ok &= check('dW_heads vs fp64 chain (TF32 tol)', dw_heads, dout32.double().t() @ h32, 5e-3)
+    # dPre-to-HBM mode: same statistics / small gradients, dPre equal to the debug dump, dW_enc section left untouched
+    dpre_hbm = torch.full((m, 128), float('nan'), device=dev)
+    g3, s3, _, _, _ = fused(xbuf, 128, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval,
+                            n_act, debug=False, dpre_out=dpre_hbm)
+    torch.cuda.synchronize()
+    ok &= check('dPre written to HBM', dpre_hbm, dp, 1e-7)
+    ok &= check('small gradients (HBM mode)', g3[128 * 128:], gflat[128 * 128:], 1e-6)
+    ok &= bool(torch.isnan(g3[:128 * 128]).all())
+    ok &= check('loss statistics (HBM mode)', s3[:6], stats[:6], 1e-12)
     # the same launch without the debug dumps must give the same gradients
     g2, s2, _, _, _ = fused(xbuf, 128, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval,
                             n_act, debug=False)
@@ -141,10 +151,14 @@ def timing():
     act = torch.randint(0, n_act, (m,), device=dev)
     olp = -torch.rand(m, device=dev) - 0.5
     adv, ret, oval = torch.randn(m, device=dev), torch.randn(m, device=dev), torch.randn(m, device=dev)
-    for name, (rows, slabs, stride) in (('1 slab of 524288 rows', (m, 1, m)), ('2 slabs of 262144 rows', (m // 2, 2, 2 * m))):
+    dpre_t = torch.empty(m, 128, device=dev)
+    for name, (rows, slabs, stride, dpo) in (('1 slab of 524288 rows, dW in kernel', (m, 1, m, None)),
+                                             ('2 slabs of 262144 rows, dW in kernel', (m // 2, 2, 2 * m, None)),
+                                             ('2 slabs of 262144 rows, dPre to HBM', (m // 2, 2, 2 * m, dpre_t))):
         def fn(k):
             off = (k % 4) * (m // 2) if slabs == 2 else (k % 4) * m
-            return fused(xbuf[off:], 128, rows, stride, slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval, n_act, False)
+            return fused(xbuf[off:], 128, rows, stride, slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval, n_act, False,
+                         dpre_out=dpo)
         for k in range(3):
             fn(k)
         torch.cuda.synchronize()

@@ -45,8 +45,26 @@ def image_mnmajor(mat, lbo, sbo):
     return img
 
 
-def desc(lbo, sbo):
-    return (((lbo >> 4) & 0x3FFF) << 16) | (((sbo >> 4) & 0x3FFF) << 32) | (1 << 46) | (2 << 61)
+def desc(lbo, sbo, layout=2):
+    return (((lbo >> 4) & 0x3FFF) << 16) | (((sbo >> 4) & 0x3FFF) << 32) | (1 << 46) | (layout << 61)
+
+
+def swz128_32(off):
+    """SWIZZLE_128B_BASE32B (UMMA layout type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunks within a 128-byte
+    row, chunk index ^= row index & 3  (byte-address bits [5,7) ^= bits [7,9)) -- the only MN-major layout for 32-bit types."""
+    return off ^ (((off >> 7) & 3) << 5)
+
+
+def image_mnmajor32(mat, lbo, sbo, swz=swz128_32):
+    """mat [MN][K] fp32 -> MN-major image with 4-k atoms: 32 MN elements contiguous (128 B), 4 k's per 512-byte atom (stride
+    128 B), k-groups (of 4) at SBO, MN-groups (of 32) at LBO."""
+    mn, k = mat.shape
+    size = ((mn - 1) // 32) * lbo + ((k - 1) // 4) * sbo + 512
+    img = np.zeros(size // 4, dtype=np.float32)
+    r, c = np.meshgrid(np.arange(mn), np.arange(k), indexing='ij')
+    off = (r % 32) * 4 + (r // 32) * lbo + (c % 4) * 128 + (c // 4) * sbo
+    img[swz(off) // 4] = mat
+    return img
 
 
 def idesc(m, n, a_mn, b_mn):
@@ -114,6 +132,34 @@ def main():
     ref = tf32_trunc(x[:64]).astype(np.float64).T @ tf32_trunc(dp[:64]).astype(np.float64)
     got = run(x_img, dp_img, desc(16384, 1024), desc(16384, 1024), idesc(128, 128, 1, 1), 8, 8, (1024, 1024, 0, 0), 128)
     ok['mn half'] = report('MN-major x MN-major, first 64 rows only (8 MMAs)', got, ref)
+    # ---- 6. the 32-bit MN-major layout: SWIZZLE_128B_BASE32B (layout type 1), 4-k atoms of 512 B.  x tile = what TMA writes
+    #         with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B for a [128 rows][32 floats] box: row r at 128 r, 32-byte chunk c at c ^ (r & 3)
+    for name, (sbo, k_step) in (('SBO=512, +1024 B per K=8', (512, 1024)),):
+        xi = image_mnmajor32(x.T.copy(), 16384, sbo)
+        di = image_mnmajor32(dp.T.copy(), 16384, sbo)
+        # what the TMA tile looks like, computed independently: element (row, f) at kb*16384 + row*128 + ((f%32)*4 ^ ((row&3)<<5))
+        rr, ff = np.meshgrid(np.arange(128), np.arange(128), indexing='ij')
+        tma = np.zeros(16384, dtype=np.float32)
+        tma[((ff // 32) * 16384 + rr * 128 + (((ff % 32) * 4) ^ ((rr & 3) << 5))) // 4] = x
+        assert np.array_equal(tma, xi), 'BASE32B image == TMA ATOM_32B tile'
+        ref = tf32_trunc(x).astype(np.float64).T @ tf32_trunc(dp).astype(np.float64)
+        for lay in (1, 2):
+            got = run(xi, di, desc(16384, sbo, lay), desc(16384, sbo, lay), idesc(128, 128, 1, 1), 16, 16, (k_step, k_step, 0, 0), 128)
+            ok[f'mn32 L{lay} {name}'] = report(f'MN-major BASE32B image, layout type {lay}, {name}', got, ref)
+            print('      got stats: absmax %.3e, zeros %.2f' % (np.abs(got).max(), float((got == 0).mean())))
+        got = run(xi, di, desc(512, 16384, 1), desc(512, 16384, 1), idesc(128, 128, 1, 1), 16, 16, (k_step, k_step, 0, 0), 128)
+        ok['mn32 swapped'] = report('MN-major BASE32B image, layout 1, LBO/SBO swapped', got, ref)
+        for n in (32, 64):
+            dpc = dp[:, :n].copy()
+            refc = tf32_trunc(x).astype(np.float64).T @ tf32_trunc(dpc).astype(np.float64)
+            got = run(xi, image_mnmajor32(dpc.T.copy(), 16384, sbo), desc(16384, sbo, 1), desc(16384, sbo, 1),
+                      idesc(128, n, 1, 1), 16, 16, (k_step, k_step, 0, 0), n)
+            ok[f'mn32 chunk {n}'] = report(f'MN-major BASE32B, dPre chunk N={n}', got, refc)
+        # mixed: A MN-major (x, BASE32B) with B K-major is not needed; A K-major (forward) unaffected
+    # the failing SW128 (16-byte) MN-major cases above: how do they fail?
+    got = run(x_img, dp_img, desc(16384, 1024), desc(16384, 1024), idesc(128, 128, 1, 1), 16, 16, (1024, 1024, 0, 0), 128)
+    print('SW128 MN-major result stats: absmax %.3e, zeros %.2f, nan %.2f' % (np.nanmax(np.abs(got)), float((got == 0).mean()),
+                                                                            float(np.isnan(got).mean())))
     print({k: bool(v) for k, v in ok.items()})
     print('probe done')
 

@@ -67,7 +67,9 @@ def run_config(kind, n, h, bptt, minibatches, cuda_graph, iterations, replay_env
         ref = ogae.compute_gae(done.reshape(-1)[idx], values[idx], rew.reshape(-1)[idx], 0.99, 0.95)
         got = cpu(exp.advantages)
         assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-5
-        assert np.allclose(cpu(exp.returns), ref + values[idx], rtol=1e-5, atol=1e-5)
+        # Experience.returns is the reference's returns_np, literally (clean_pufferl.py:476): SORTED-order advantages plus
+        # ARRIVAL-order values at the same flat index (it only feeds the explained variance)
+        assert np.allclose(cpu(exp.returns), got + values, rtol=1e-5, atol=1e-5)
         for k in ('policy_loss', 'value_loss', 'entropy', 'approx_kl', 'clipfrac'):
             assert np.isfinite(getattr(data.losses, k)), k
         assert data.global_step == (it + 1) * n * h

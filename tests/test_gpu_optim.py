@@ -106,7 +106,8 @@ def test_manual_update_matches_autograd_update():
     assert np.allclose(losses[True], losses[False], rtol=1e-4, atol=1e-6), (losses[True], losses[False])
 
 
-def test_fused_update_kernel_matches_kernel_chain():
+@pytest.mark.parametrize('dw', ['cublas', 'kernel'])
+def test_fused_update_kernel_matches_kernel_chain(dw):
     """train() through pb_mlp_update_fused (ONE tcgen05 kernel per minibatch: csrc/mlp_update.cu) vs the kernel chain it
     replaces (cuBLAS GEMMs + pb_ppo_loss + pb_mlp_tail_backward + split-K dW): same rollout, same minibatches.  Both
     compute the dense products in TF32 (operands truncated by the tensor core), so gradients agree to TF32 noise; the
@@ -122,7 +123,7 @@ def test_fused_update_kernel_matches_kernel_chain():
         vec = pvec.make(ocean.env_creator('breakout'), num_envs=n, backend=pvec.B200)
         torch.manual_seed(0)
         pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=True, seed=7).cuda()
-        cfg = make_config(n, h, env='breakout', manual_update=True, fused_update=fused)
+        cfg = make_config(n, h, env='breakout', manual_update=True, fused_update=fused, fused_update_dw=dw)
         cfg.update_epochs = 1
         cfg.minibatch_size = n * h          # ONE minibatch: gflat after train() is its gradient
         data = clean_pufferl.create(cfg, vec, pol)
