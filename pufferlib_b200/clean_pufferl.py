@@ -845,7 +845,13 @@ def _rollout_loop(data, infos):
             experience.store(o_device, value, actions, logprob, r, d, env_id, mask)
             if device_feed:   # the reference's D2H of the actions (clean_pufferl.py:114) + the ONE host wait of this env step
                 a_host = vecenv.actions_to_host(actions)
-                info = vecenv.host_sync()[4]
+                if getattr(vecenv, 'exact_infos', False) or vecenv._rollout is None:
+                    info = vecenv.host_sync()[4]          # per-step info dicts need the terminal flags on the host
+                else:
+                    # nothing on the host side reads this step's observations: wait for the actions only and let the big
+                    # copies stream behind (each reads its own rollout row); they are awaited when the rollout ends
+                    vecenv.host_sync(actions_only=True)
+                    info = []
             for i in info:
                 for k, v in i.items():
                     infos[k].append(v)
@@ -859,6 +865,8 @@ def _rollout_loop(data, infos):
                 a_host = actions.cpu().numpy()
                 io.d2h += a_host.nbytes
                 vecenv.send(a_host)
+    if device_feed:
+        vecenv.host_sync()       # every device->host copy of the rollout has landed (part of the e2e timed region)
     if hasattr(vecenv, 'join'):
         vecenv.join()            # pool mode: side-stream env steps rejoin the caller's stream (and any graph capture)
 

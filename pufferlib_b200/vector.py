@@ -356,9 +356,16 @@ class B200:
         self.d2h_bytes += 8 * self.num_agents
         return self._host_np.actions
 
-    def host_sync(self):
+    def host_sync(self, actions_only=False):
         """Wait for the step's device->host copies (and an outstanding actions_to_host); returns what recv() returns in
-        host_buffers mode: pinned numpy arrays + the info dicts."""
+        host_buffers mode: pinned numpy arrays + the info dicts.  actions_only: wait for the action copy alone -- the
+        observation / reward / flag copies keep streaming on the copy stream (they are ordered among themselves, each reads
+        its own rollout row) and are awaited by the next full host_sync(); for callers that do not read them every step."""
+        if actions_only:
+            if getattr(self, '_act_pending', False):
+                self._ev_act.synchronize()
+                self._act_pending = False
+            return None
         if self._host_pending:
             self._ev_copy.synchronize()
             self._host_pending = False
