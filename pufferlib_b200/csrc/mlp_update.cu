@@ -30,6 +30,7 @@
 // Descriptor encodings were validated on hardware with csrc/experimental/umma_probe.cu (tests/experimental/
 // check_umma_probe.py).  Every mbarrier wait is bounded (tma.cuh: __trap instead of a hang).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "pb_common.cuh"
 #include "tma.cuh"
@@ -82,6 +83,8 @@ struct FusedParams {
     float* dbg_hidden;         // nullable [m][128]
     float* dbg_dpre;           // nullable [m][128]
     float* dbg_dout;           // nullable [m][8]
+    int skip;                  // profiling only (env PB_MUF_SKIP): bit 0 head FFMAs, 1 loss math, 2 dPre FFMAs, 3 mma.sync + staging,
+                               // 4 dPre stores / chunk hand-off, 5 column sums, 6 partner exchange
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -457,6 +460,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 float v[32];
                 if (hh == 0) {      // (compile-time column offsets: every c_wh / c_benc operand is a constant-bank immediate)
                     tmem_ld32(taddr + 32 * cc, v);
+                    if (!(p.skip & 1))
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const float rh = fmaxf(v[k] + c_benc[32 * cc + k], 0.f);
@@ -465,6 +469,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     }
                 } else {
                     tmem_ld32(taddr + 64 + 32 * cc, v);
+                    if (!(p.skip & 1))
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const float rh = fmaxf(v[k] + c_benc[64 + 32 * cc + k], 0.f);
@@ -473,12 +478,14 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     }
                 }
             }
+            if (!(p.skip & 64)) {
             tmem_st8(xchg + 8 * hh, out);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // the two warps of quadrant q
             tc_fence_after();
-            {
+            }
+            if (!(p.skip & 64)) {
                 float other[NO];
                 tmem_ld8(xchg + 8 * (hh ^ 1), other);
 #pragma unroll
@@ -490,7 +497,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
             float dO[NO];
 #pragma unroll
             for (int a = 0; a < NO; ++a) dO[a] = 0.f;
-            if (valid) {
+            if (valid && !(p.skip & 2)) {
                 const RowStats rs = ppo_row(out, p, act, old_lp, adv, ret, old_v, dO);
                 if (hh == 0) {
                     st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
@@ -527,7 +534,10 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 float v[32], dp[32];
                 const int col0 = 64 * hh + 32 * cc;           // first hidden unit of the chunk (hh is warp-uniform)
                 tmem_ld32(taddr + col0, v);
-                if (hh == 0) {
+                if (p.skip & 4) {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) dp[k] = v[k];
+                } else if (hh == 0) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const float pre = v[k] + c_benc[32 * cc + k];
@@ -555,13 +565,14 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         *reinterpret_cast<float4*>(p.dbg_dpre + i * HID + col0 + k) = make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]);
                     }
                 }
-                if (!DW_KERNEL && valid) {                      // dPre row segment to HBM (128 contiguous bytes per thread)
+                if (!DW_KERNEL && valid && !(p.skip & 16)) {    // dPre row segment to HBM (128 contiguous bytes per thread)
 #pragma unroll
                     for (int k = 0; k < 32; k += 4)
                         __stcs(reinterpret_cast<float4*>(p.dpre_out + i * HID + col0 + k), make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]));
                 }
                 if (DW_KERNEL) mbar_wait(&dp_empty[hh], (uint32_t)(((it * 2 + cc) & 1) ^ 1));   // last use of the buffer consumed
                 // relu(h) chunk of this warp's 32 rows (TF32-rounded) -> B fragments of the dW_heads mma
+                if (!(p.skip & 8)) {
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                     uint8_t* dst = buf + rloc * 128 + ((j8 ^ (rloc & 3)) << 5);
@@ -580,6 +591,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     }
                 }
                 __syncwarp();
+                }
                 // dPre chunk -> the same rows, BASE32B layout (the MN-major B operand of the dW UMMA)
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
@@ -592,13 +604,15 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (DW_KERNEL && lane == 0) mbar_arrive(&dp_full[hh]);
                 // db_enc: column sums over this warp's rows (the UMMA only reads the buffer)
                 float cs = 0.f;
+                if (!(p.skip & 32))
 #pragma unroll 8
                 for (int r = 0; r < 32; ++r) cs += *reinterpret_cast<const float*>(buf + chunk32_off(32 * q + r, lane));
                 acc_benc[cc] += cs;
                 __syncwarp();                                    // (mode without UMMA: the next chunk overwrites the rows)
             }
             tc_fence_before();
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both warps are done with the exchange columns
+            if (!(p.skip & 64)) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both warps are done with the exchange columns
+            __syncwarp();
             if (lane == 0) mbar_arrive(&h_empty[s]);
         }
         // ---- the dW^T accumulator of this CTA: TMEM lane = feature, column = hidden unit; this warp dumps its column half
@@ -754,6 +768,10 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
     p.tiles_per_slab = (int)tiles_per_slab; p.n_tiles = (int)n_tiles; p.n_act = n_act;
     p.clip = clip_coef; p.vclip = vf_clip_coef; p.vf_coef = vf_coef; p.ent_coef = ent_coef; p.clip_vloss = clip_vloss;
     p.part_dw = (float*)workspace; p.part_tail = (float*)workspace + (size_t)num_sms() * FEAT * HID;
+    {
+        const char* sk = getenv("PB_MUF_SKIP");      // profiling only: skip phases of the epilogue (results are then wrong)
+        p.skip = sk ? atoi(sk) : 0;
+    }
     p.stats = stats8; p.dpre_out = dpre_out; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
     PB_CUDA(cudaMemsetAsync(stats8, 0, 8 * sizeof(double), s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s));
