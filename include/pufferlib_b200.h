@@ -248,6 +248,9 @@ int pb_rollout_breakout_mlp(pb_env* env, int32_t horizon, float* obs, float* rew
                             const float* b_enc, const float* w_heads, const float* b_heads, int32_t n_act, uint64_t seed,
                             uint64_t* counter_dev, void* stream);
 
+/* Validation hook: relu(h) [N][128] and the head outputs [N][8] of step 0 of the following rollouts (null: off). */
+int pb_rollout_debug_buffers(float* hidden, float* out);
+
 /* -- policy tail backward ---------------------------------------------------------------------------------------------
  * For models.Default (pufferlib/models.py:12-62: Linear+ReLU encoder, action head + value head): everything of the
  * backward pass after the encoder GEMM, in ONE pass over the hidden layer instead of five ATen launches:

@@ -228,6 +228,8 @@ struct RolloutParams {
     float* out_dones;
     uint64_t seed;              // sampler seed
     const uint64_t* counter;    // sampler step counter at the start of the rollout (advanced by H afterwards)
+    float* dbg_hidden;          // validation only: relu(h) of step 0, [N][128]
+    float* dbg_out;             // validation only: head outputs of step 0, [N][8]
 };
 
 __device__ __forceinline__ void ro_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -394,11 +396,15 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
                     const float rh = fmaxf(v[k] + c_ro_benc[32 * c + k], 0.f);
+                    if (p.dbg_hidden && t == 0) p.dbg_hidden[(int64_t)e * 128 + 32 * c + k] = rh;
 #pragma unroll
                     for (int a = 0; a < RO_HEADS; ++a) out[a] = fmaf(rh, c_ro_wh[a * 128 + 32 * c + k], out[a]);   // rows >= 5: zero padding
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (p.dbg_out && t == 0)
+#pragma unroll
+                for (int a = 0; a < 8; ++a) p.dbg_out[(int64_t)e * 8 + a] = out[a];
             // sample_logits (frameworks/cleanrl.py:25-47) by inverse CDF -- the arithmetic of k_policy_mlp_sample
             float mx = -INFINITY;
 #pragma unroll
@@ -504,6 +510,8 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
 }
 
 __global__ void k_counter_add(uint64_t* c, uint64_t v) { *c += v; }
+float* g_ro_dbg_hidden = nullptr;
+float* g_ro_dbg_out = nullptr;
 
 typedef CUresult (*RoEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -617,7 +625,7 @@ extern "C" int pb_rollout_breakout_mlp(pb_env* env, int32_t horizon, float* obs,
     p.rewards = rewards; p.dones = dones; p.values = values; p.logprobs = logprobs; p.actions = actions;
     p.carry_rewards = carry->rewards; p.carry_dones = carry->dones_f32;
     p.out_rewards = carry->rewards; p.out_terminals = carry->terminals; p.out_dones = carry->dones_f32;
-    p.seed = seed; p.counter = counter_dev;
+    p.seed = seed; p.counter = counter_dev; p.dbg_hidden = g_ro_dbg_hidden; p.dbg_out = g_ro_dbg_out;
     PB_CUDA(cudaMemcpyToSymbolAsync(c_ro_wh, w_heads, sizeof(float) * 8 * 128, 0, cudaMemcpyDeviceToDevice, s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_ro_benc, b_enc, sizeof(float) * 128, 0, cudaMemcpyDeviceToDevice, s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_ro_bh, b_heads, sizeof(float) * 8, 0, cudaMemcpyDeviceToDevice, s));
@@ -633,5 +641,12 @@ extern "C" int pb_rollout_breakout_mlp(pb_env* env, int32_t horizon, float* obs,
     env->write_const = false;
     env->cur_obs = carry->obs;
     env->cur_obs_stride = carry->obs_stride;
+    return PB_OK;
+}
+
+// validation hook: device buffers ([N][128], [N][8]) that receive relu(h) and the head outputs of step 0 of the next rollouts
+extern "C" int pb_rollout_debug_buffers(float* hidden, float* out) {
+    g_ro_dbg_hidden = hidden;
+    g_ro_dbg_out = out;
     return PB_OK;
 }

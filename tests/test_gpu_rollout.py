@@ -64,8 +64,13 @@ def test_fused_rollout_replays_through_oracle(n, h, kwargs):
     w_cat, b_cat = (t.detach().double() for t in model.head_matrix())
     n_act = 4
     episodes = []
+    from pufferlib_b200 import _native
+    dbg_h = torch.full((n, 128), float('nan'), device='cuda')
+    dbg_o = torch.full((n, 8), float('nan'), device='cuda')
+    _native.lib().pb_rollout_debug_buffers(_native.ptr(dbg_h), _native.ptr(dbg_o))
     for it in range(3):          # rollout boundaries: the closing step's outputs are row 0 of the next rollout
         clean_pufferl.evaluate(data)
+        _native.lib().pb_rollout_debug_buffers(None, None)
         assert data.fused_rollouts == it + 1
         exp = data.experience
         assert exp.ptr == n * h and data.global_step == (it + 1) * n * h
@@ -86,6 +91,15 @@ def test_fused_rollout_replays_through_oracle(n, h, kwargs):
         logits, value = out[:, :n_act], out[:, n_act]
         norm = logits - logits.logsumexp(-1, keepdim=True)
         lp = norm.gather(-1, exp.actions.view(-1, 1)).squeeze(-1)
+        if it == 0:      # step 0: hidden layer and head outputs straight from the kernel
+            h0 = hid[:n]
+            eh = (dbg_h.double() - h0).abs()
+            print(f'[diag] hidden step 0: max err {float(eh.max()):.3e}; per 32-col chunk', [f'{float(eh[:, 32*c:32*c+32].max()):.2e}' for c in range(4)],
+                  'rows with err>1e-4:', int((eh.max(1).values > 1e-4).sum()), flush=True)
+            eo = (dbg_o[:, :5].double() - out[:n, :5]).abs()
+            print(f'[diag] head outputs step 0: max err per head {[f"{float(eo[:, a].max()):.2e}" for a in range(5)]}', flush=True)
+            o_from_h = dbg_h.double() @ w_cat.t() + b_cat
+            print(f'[diag] heads recomputed from the kernel hidden vs kernel out: {float((dbg_o[:, :5].double() - o_from_h[:, :5]).abs().max()):.3e}', flush=True)
         dv = float((exp.values.double() - value).abs().max())
         if dv >= 2e-4:       # diagnostics: which reference is the kernel closest to?
             for name, w_ in (('exact W', model.encoder.weight.detach().double()), ('truncated W', w_t)):
