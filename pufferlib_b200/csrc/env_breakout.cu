@@ -405,33 +405,33 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
             if (p.dbg_out && t == 0)
 #pragma unroll
                 for (int a = 0; a < 8; ++a) p.dbg_out[(int64_t)e * 8 + a] = out[a];
-            // sample_logits (frameworks/cleanrl.py:25-47) by inverse CDF -- the arithmetic of k_policy_mlp_sample
-            float mx = -INFINITY;
+            // sample_logits (frameworks/cleanrl.py:25-47) by inverse CDF -- the arithmetic of k_policy_mlp_sample, with the
+            // action count fixed at compile time (breakout: 4 logits, value in column 4)
+            constexpr int NA = RO_HEADS - 1;
+            float mx = out[0];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (k < p.n_act) mx = fmaxf(mx, out[k]);
+            for (int k = 1; k < NA; ++k) mx = fmaxf(mx, out[k]);
             float sum = 0.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) if (k < p.n_act) sum += expf(out[k] - mx);
+            for (int k = 0; k < NA; ++k) sum += expf(out[k] - mx);
             const float lse = mx + logf(sum);
             const uint32_t rnd = pb_mix32(p.seed * 0x9E3779B97F4A7C15ull + (offset0 + (uint64_t)t) * 0xD1B54A32D192ED03ull +
                                           (uint64_t)e * 0x2545F4914F6CDD1Dull);
             const float u = (float)(rnd >> 8) * (1.0f / 16777216.0f);
-            float cdf = 0.f, lp = 0.f, value = 0.f;
+            const float value = out[NA];
+            float cdf = 0.f, lp = 0.f;
             int act = -1;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k < p.n_act) {
-                    const float nl = out[k] - lse, pk = expf(nl);
-                    cdf += pk;
-                    if (act < 0 && u < cdf) { act = k; lp = nl; }
-                }
-                if (k == p.n_act) value = out[k];
+            for (int k = 0; k < NA; ++k) {
+                const float nl = out[k] - lse, pk = expf(nl);
+                cdf += pk;
+                if (act < 0 && u < cdf) { act = k; lp = nl; }
             }
-            if (act < 0) {
+            if (act < 0) {   // rounding left cdf a hair below u: last action with non-negligible probability
 #pragma unroll
-                for (int k = 7; k >= 0; --k)
-                    if (act < 0 && k < p.n_act && out[k] - lse > -80.f) { act = k; lp = out[k] - lse; }
-                if (act < 0) { act = p.n_act - 1; lp = out[act] - lse; }
+                for (int k = NA - 1; k >= 0; --k)
+                    if (act < 0 && out[k] - lse > -80.f) { act = k; lp = out[k] - lse; }
+                if (act < 0) { act = NA - 1; lp = out[NA - 1] - lse; }
             }
             const int64_t row = (int64_t)t * p.n + e;
             p.values[row] = value;
@@ -603,7 +603,7 @@ extern "C" int pb_rollout_breakout_mlp(pb_env* env, int32_t horizon, float* obs,
     PB_REQUIRE(obs && rewards && dones && values && logprobs && actions && carry && carry->obs && carry->rewards &&
                    carry->terminals && carry->dones_f32 && w_enc && b_enc && w_heads && b_heads && counter_dev,
                PB_ERR_INVALID, "pb_rollout_breakout_mlp: null pointer (the carry buffers need dones_f32)");
-    PB_REQUIRE(n_act >= 1 && n_act <= 7 && n_act <= 4, PB_ERR_INVALID, "pb_rollout_breakout_mlp: breakout has 4 actions");
+    PB_REQUIRE(n_act == RO_HEADS - 1, PB_ERR_INVALID, "pb_rollout_breakout_mlp: breakout has %d actions", RO_HEADS - 1);
     PB_REQUIRE(carry->obs_stride == 512 && ((uintptr_t)obs & 15) == 0 && ((uintptr_t)carry->obs & 15) == 0 &&
                    ((uintptr_t)w_enc & 15) == 0,
                PB_ERR_INVALID, "pb_rollout_breakout_mlp: 16-byte aligned, densely packed observation rows required");

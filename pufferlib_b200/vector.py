@@ -391,7 +391,7 @@ class B200:
             return False
         n_act, hid = model.decoder.weight.shape
         w = model.encoder.weight
-        return (hid == 128 and tuple(w.shape) == (128, 128) and n_act <= 4 and w.is_cuda and w.dtype == torch.float32
+        return (hid == 128 and tuple(w.shape) == (128, 128) and n_act == 4 and w.is_cuda and w.dtype == torch.float32
                 and w.is_contiguous() and experience.obs.dtype == torch.float32)
 
     def fused_rollout(self, experience, policy):

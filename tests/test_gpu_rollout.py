@@ -98,6 +98,7 @@ def test_fused_rollout_replays_through_oracle(n, h, kwargs):
                   'rows with err>1e-4:', int((eh.max(1).values > 1e-4).sum()), flush=True)
             eo = (dbg_o[:, :5].double() - out[:n, :5]).abs()
             print(f'[diag] head outputs step 0: max err per head {[f"{float(eo[:, a].max()):.2e}" for a in range(5)]}', flush=True)
+            print(f'[diag] stored values vs kernel out[4] at step 0: {float((exp.values[:n].double() - dbg_o[:, 4].double()).abs().max()):.3e}', flush=True)
             o_from_h = dbg_h.double() @ w_cat.t() + b_cat
             print(f'[diag] heads recomputed from the kernel hidden vs kernel out: {float((dbg_o[:, :5].double() - o_from_h[:, :5]).abs().max()):.3e}', flush=True)
         dv = float((exp.values.double() - value).abs().max())
