@@ -85,6 +85,8 @@ def test_fused_rollout_replays_through_oracle(n, h, kwargs):
             ora.send(acts[t])
         # policy outputs on the stored observations (W_enc truncated to TF32 by the tensor core; obs exact in TF32)
         w_t = (model.encoder.weight.detach().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        b_enc = model.encoder.bias.detach().double()          # the parameters move every train() call
+        w_cat, b_cat = (t.detach().double() for t in model.head_matrix())
         x = exp.obs.double()
         hid = torch.relu(x @ w_t.t() + b_enc)
         out = hid @ w_cat.t() + b_cat
