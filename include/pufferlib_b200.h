@@ -283,6 +283,8 @@ int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_
  *                [M][128] (slab-major rows) is written there instead and the dW_enc part of grad_flat is left to the caller
  *   dbg_*        nullable dumps of relu(h) [M][128], dPre [M][128], dOut [M][8] for validation. */
 size_t pb_mlp_update_workspace_bytes(void);
+/* 1 = two x layouts per tile (K-major + MN-major TMA loads), 2 = one x layout, x^T formed on the tensor core */
+int pb_mlp_update_set_variant(int32_t variant);
 int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
                         const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
                         const int64_t* actions, const float* old_logprobs, const float* advantages, const float* returns,

@@ -676,6 +676,377 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                      : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Variant 2: ONE x layout.  The tensor core only takes MN-major 32-bit operands in the BASE32B layout, so variant 1 loads
+// every x tile twice (K-major for the forward product, MN-major for dW) and has no shared memory left to overlap anything.
+// Here the dW product takes x^T from TENSOR memory instead:
+//     x^T[feat][row]    = I . x^T           SS MMA: A = an 8 KB "sliding identity" (no-swizzle K-major, see x2_write_identity),
+//                                           B = the K-major x tile the forward product just read
+//     dW^T[feat][hid]  += x^T . dPre        TS MMA: A = that accumulator (lanes = feat, columns = rows), B = dPre written by the
+//                                           epilogue as K-major SWIZZLE_128B blocks [128 hid][32 rows] (one per row quadrant)
+// (validated on hardware by tests/experimental/check_umma_transpose.py).  The 64 KB the second x tile used to take hold a
+// whole tile of dPre, so the epilogue never waits for the tensor core inside a tile, and there are 16 epilogue warps
+// (4 per scheduler: row quadrant q x column quarter c) instead of 8.
+// TMEM: [0,256) two forward accumulators, [256,384) x^T, [384,512) dW^T (lives across all tiles of the CTA).
+constexpr int X2_THREADS = 576;                          // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int X2_W = 0, X2_XK = TILE_BYTES, X2_G = 2 * TILE_BYTES;     // W_enc | x tile | 4 dPre blocks of 16 KiB
+constexpr int X2_XCH = 3 * TILE_BYTES;                   // [4 q][4 c][32 rows][8 floats] partial head sums
+constexpr int X2_ID = X2_XCH + 16384;                    // sliding identity: 2 strips of 32 core matrices
+constexpr int X2_BAR = X2_ID + 8192;
+constexpr int X2_TOTAL = X2_BAR + 256;
+constexpr int X2_TMEM_XT = 256, X2_TMEM_DW = 384;
+constexpr int X2_ID_GROUP = 128, X2_ID_STRIP = 32 * X2_ID_GROUP;
+static_assert(X2_TOTAL <= 232448, "shared memory budget");
+
+// no-swizzle K-major descriptor: 8-row x 16-byte core matrices, LBO = distance between the two core matrices of a K = 8
+// slice, SBO = distance between 8-row groups
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+
+// byte offset of element (hidden unit n, tile row r) inside dPre block r >> 5: K-major SWIZZLE_128B, n = MN row of 128 B,
+// the 32 rows of the quadrant along K
+__device__ __forceinline__ uint32_t g_off(int n, int l) {
+    return (uint32_t)(n * 128 + ((((l >> 2) ^ (n & 7))) << 4) + ((l & 3) << 2));
+}
+
+// pass 1 / pass 2 bodies with the column quarter as a template parameter: every c_wh / c_benc operand is a constant-bank
+// immediate
+template <int NH, int C>
+__device__ __forceinline__ void x2_heads(const float (&v)[32], float (&out)[NO]) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const float rh = fmaxf(v[k] + c_benc[32 * C + k], 0.f);
+#pragma unroll
+        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * C + k], out[a]);
+    }
+}
+template <int NH, int C>
+__device__ __forceinline__ void x2_dpre(float (&v)[32], float (&dp)[32], const float (&dO)[NO]) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        const float pre = v[k] + c_benc[32 * C + k];
+        float gk = 0.f;
+#pragma unroll
+        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * C + k], gk);
+        dp[k] = pre > 0.f ? gk : 0.f;
+        v[k] = fmaxf(pre, 0.f);
+    }
+}
+
+template <int NH, int REGS>
+__global__ void __maxnreg__(REGS)
+k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + X2_BAR);
+    uint64_t* w_full = bars;
+    uint64_t* xk_full = bars + 1;         // x tile landed
+    uint64_t* xk_empty = bars + 2;        // ... read by the forward AND the transposing MMAs
+    uint64_t* h_full = bars + 3;          // [2] forward accumulator complete
+    uint64_t* h_empty = bars + 5;         // [2] drained by the 16 epilogue warps
+    uint64_t* dp_full = bars + 7;         // [4] dPre block of row quadrant q written (4 warps)
+    uint64_t* dp_empty = bars + 11;       // [4] ... consumed by its dW MMAs
+    uint64_t* dw_done = bars + 15;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        mbar_init(xk_full, 1);
+        mbar_init(xk_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&h_full[i], 1);
+            mbar_init(&h_empty[i], 16);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&dp_full[i], 4);
+            mbar_init(&dp_empty[i], 1);
+        }
+        mbar_init(dw_done, 1);
+        mbar_fence_init();
+    }
+    // sliding identity: strip s (features 4s..4s+3 of a K = 8 slice) is 32 core matrices of 8 rows x 16 B, all zero except
+    // number 15, whose row r holds a 1 at column r - 4s.  MMA k reads from (15 - k) core matrices in: row group k of A sees
+    // the identity block, every other row group zeros.
+    for (int i = threadIdx.x; i < 8192 / 16; i += X2_THREADS) reinterpret_cast<uint4*>(smem + X2_ID)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        const int r = threadIdx.x;
+        *reinterpret_cast<float*>(smem + X2_ID + (r >> 2) * X2_ID_STRIP + 15 * X2_ID_GROUP + r * 16 + (r & 3) * 4) = 1.0f;
+    }
+    fence_proxy_async_smem();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    // epilogue warp (q, c): TMEM lane quadrant q (tile rows 32q..32q+31), hidden units 32c..32c+31
+    float acc_wh[4][2];                  // dW_heads[a = lane>>2][32c + 8nb + 2(lane&3) + {0,1}] (this warp's rows)
+    float acc_benc = 0.f;                // db_enc[32c + lane]
+    float acc_bh[NO];                    // db_heads (c == 0)
+    float st[6] = {0, 0, 0, 0, 0, 0};    // per-thread statistics of <= 28 tiles: fp32 here, fp64 across threads
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) acc_wh[nb][0] = acc_wh[nb][1] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NO; ++k) acc_bh[k] = 0.f;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_full, TILE_BYTES);
+            for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + X2_W + kb * KBLK_BYTES, &map_w, kb * KBLK, 0, w_full);
+            for (int it = 0; it < n_my; ++it) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                const int64_t row0 = (int64_t)(tile / p.tiles_per_slab) * p.slab_stride_rows +
+                                     (int64_t)(tile % p.tiles_per_slab) * TILE_M;
+                mbar_wait(xk_empty, (uint32_t)((it & 1) ^ 1));
+                mbar_expect_tx(xk_full, TILE_BYTES);
+                for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + X2_XK + kb * KBLK_BYTES, &map_x, kb * KBLK, (int)row0, xk_full);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t w_addr = smem_u32(smem + X2_W), xk_addr = smem_u32(smem + X2_XK);
+            const uint32_t g_addr = smem_u32(smem + X2_G), id_addr = smem_u32(smem + X2_ID);
+            auto forward = [&](int it) {
+                const int s = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(&h_empty[s], ph ^ 1);
+                mbar_wait(xk_full, (uint32_t)(it & 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * HID);
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32(d_tmem, desc_kmajor(xk_addr + kb * KBLK_BYTES + k * 32),
+                                  desc_kmajor(w_addr + kb * KBLK_BYTES + k * 32), IDESC_FWD, (kb | k) ? 1u : 0u);
+                umma_commit(&h_full[s]);
+            };
+            auto transpose = [&]() {     // x^T of the tile in the x buffer (the dW MMAs of the previous tile were issued before)
+#pragma unroll
+                for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_tf32(tmem_base + X2_TMEM_XT,
+                                  desc_nosw(id_addr + (15 - (4 * kb + k)) * X2_ID_GROUP, X2_ID_STRIP, X2_ID_GROUP),
+                                  desc_kmajor(xk_addr + kb * KBLK_BYTES + k * 32), IDESC_FWD, (kb | k) ? 1u : 0u);
+                umma_commit(xk_empty);   // the x tile may be overwritten: the next load starts
+            };
+            mbar_wait(w_full, 0);
+            forward(0);
+            transpose();
+            for (int it = 0; it < n_my; ++it) {
+                if (it + 1 < n_my) forward(it + 1);
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    mbar_wait(&dp_full[q], (uint32_t)(it & 1));
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)      // K = 8 tile rows per MMA
+                        umma_tf32_ts(tmem_base + X2_TMEM_DW, tmem_base + (uint32_t)(X2_TMEM_XT + 32 * q + 8 * k),
+                                     desc_kmajor(g_addr + q * KBLK_BYTES + k * 32), IDESC_FWD, (it | q | k) ? 1u : 0u);
+                    umma_commit(&dp_empty[q]);
+                }
+                if (it + 1 < n_my) transpose();
+            }
+            umma_commit(dw_done);
+        }
+    } else {
+        const int q = warp & 3, c = (warp - 2) >> 2;
+        const int g = lane >> 2, t = lane & 3;
+        const int rloc = 32 * q + lane;
+        uint8_t* gq = smem + X2_G + q * KBLK_BYTES;             // dPre block of this row quadrant
+        uint8_t* mine = gq + 32 * c * 128;                      // its hidden units 32c..32c+31: private until published
+        float* xch = reinterpret_cast<float*>(smem + X2_XCH) + (q * 4 * 32 + lane) * 8;   // + c' * 256 floats
+        float z0 = 0.f, z1 = 0.f;
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            const int s = it & 1, ph = (it >> 1) & 1;
+            const int slab = tile / p.tiles_per_slab;
+            const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
+            const bool valid = lrow < p.slab_rows;
+            const int64_t i = (int64_t)slab * p.slab_rows + lrow;
+            const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;
+            int act = 0;
+            float old_lp = 0.f, adv = 0.f, ret = 0.f, old_v = 0.f;
+            if (valid) {
+                act = (int)p.actions[ri];
+                old_lp = p.old_logprobs[ri];
+                adv = p.adv[ri];
+                old_v = (p.clip_vloss || !p.returns) ? p.old_values[ri] : 0.f;
+                ret = p.returns ? p.returns[ri] : adv + old_v;
+                if (p.adv_norm) adv = (adv - p.adv_norm[0]) * p.adv_norm[1];
+            }
+            mbar_wait(&h_full[s], ph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * HID + 32 * c);
+
+            // ---- pass 1: this quarter's share of the head products; the four warps of the quadrant exchange them
+            float out[NO], v[32];
+#pragma unroll
+            for (int a = 0; a < NO; ++a) out[a] = 0.f;
+            tmem_ld32(taddr, v);
+            switch (c) {
+                case 0: x2_heads<NH, 0>(v, out); break;
+                case 1: x2_heads<NH, 1>(v, out); break;
+                case 2: x2_heads<NH, 2>(v, out); break;
+                default: x2_heads<NH, 3>(v, out); break;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // everybody has read the previous tile's partials
+            *reinterpret_cast<float4*>(xch + c * 256) = make_float4(out[0], out[1], out[2], out[3]);
+            *reinterpret_cast<float4*>(xch + c * 256 + 4) = make_float4(out[4], out[5], out[6], out[7]);
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+#pragma unroll
+            for (int a = 0; a < NO; ++a) out[a] = 0.f;
+#pragma unroll
+            for (int cq = 0; cq < 4; ++cq) {                                 // same order in all four warps
+                const float4 lo = *reinterpret_cast<const float4*>(xch + cq * 256);
+                const float4 hi = *reinterpret_cast<const float4*>(xch + cq * 256 + 4);
+                out[0] += lo.x; out[1] += lo.y; out[2] += lo.z; out[3] += lo.w;
+                out[4] += hi.x; out[5] += hi.y; out[6] += hi.z; out[7] += hi.w;
+            }
+#pragma unroll
+            for (int a = 0; a < NO; ++a) out[a] += c_bh[a];
+
+            // ---- loss row math -> dOut (all four warps; statistics and db_heads by c == 0)
+            float dO[NO];
+#pragma unroll
+            for (int a = 0; a < NO; ++a) dO[a] = 0.f;
+            if (valid) {
+                const RowStats rs = ppo_row(out, p, act, old_lp, adv, ret, old_v, dO);
+                if (c == 0) {
+                    st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
+                    if (p.dbg_dout) {
+                        *reinterpret_cast<float4*>(p.dbg_dout + i * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+                        *reinterpret_cast<float4*>(p.dbg_dout + i * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                    }
+                }
+            }
+            if (c == 0) {
+#pragma unroll
+                for (int a = 0; a < NO; ++a) acc_bh[a] += dO[a];
+            }
+
+            // ---- A fragments of the dW_heads mma (A[m = head a][k = row]) through this warp's part of the dPre block
+            //      (row r of the warp at byte r * 128 + (r & 3) * 32: conflict-free fragment loads)
+            mbar_wait(&dp_empty[q], (uint32_t)((it & 1) ^ 1));               // the dW MMAs of the previous tile have read the block
+            uint32_t afr[4][2];
+            *reinterpret_cast<float4*>(mine + lane * 128 + (lane & 3) * 32) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+            *reinterpret_cast<float4*>(mine + lane * 128 + (lane & 3) * 32 + 16) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                afr[ks][0] = to_tf32(*reinterpret_cast<const float*>(mine + (8 * ks + t) * 128 + t * 32 + g * 4));
+                afr[ks][1] = to_tf32(*reinterpret_cast<const float*>(mine + (8 * ks + t + 4) * 128 + t * 32 + g * 4));
+            }
+            __syncwarp();
+
+            // ---- pass 2: dPre, dW_heads, db_enc of this quarter
+            float dp[32];
+            tmem_ld32(taddr, v);
+            switch (c) {
+                case 0: x2_dpre<NH, 0>(v, dp, dO); break;
+                case 1: x2_dpre<NH, 1>(v, dp, dO); break;
+                case 2: x2_dpre<NH, 2>(v, dp, dO); break;
+                default: x2_dpre<NH, 3>(v, dp, dO); break;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_empty[s]);                          // the accumulator stage is free
+            if (valid && p.dbg_hidden) {
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    *reinterpret_cast<float4*>(p.dbg_hidden + i * HID + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                    *reinterpret_cast<float4*>(p.dbg_dpre + i * HID + 32 * c + k) = make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]);
+                }
+            }
+            // relu(h) of the warp's 32 rows x 32 hidden units (TF32-rounded), K-major like the dPre that replaces it
+#pragma unroll
+            for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(mine + g_off(k, lane)) = to_tf32(v[k]);
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * nb + g, 8 * ks + t));
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * nb + g, 8 * ks + t + 4));
+                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[ks], b0, b1);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(mine + g_off(k, lane)) = dp[k];
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dp_full[q]);
+            // db_enc: lane n sums hidden unit 32c + n over the warp's 32 rows (the UMMA only reads the block)
+            float cs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 x4 = *reinterpret_cast<const float4*>(mine + lane * 128 + ((j ^ (lane & 7)) << 4));
+                cs += (x4.x + x4.y) + (x4.z + x4.w);
+            }
+            acc_benc += cs;
+        }
+        // ---- the dW^T accumulator: TMEM lane = feature, column = hidden unit
+        mbar_wait(dw_done, 0);
+        tc_fence_after();
+        {
+            float v[32];
+            float* pd = p.part_dw + ((int64_t)blockIdx.x * FEAT + rloc) * HID + 32 * c;
+            tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(X2_TMEM_DW + 32 * c), v);
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(pd + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+        }
+        if (c == 0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double x = (double)st[k];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                if (lane == 0) atomicAdd(p.stats + k, x);
+            }
+        }
+    }
+
+    // ================= CTA reduction of the small gradients =================
+    tc_fence_before();
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem + X2_XK);           // [4 quadrants][TAIL] scratch in the idle x tile
+    if (warp >= 2) {
+        const int q = warp & 3, c = (warp - 2) >> 2, g = lane >> 2, t = lane & 3;
+        float* mine = red + q * TAIL;
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            mine[g * HID + 32 * c + 8 * nb + 2 * t] = acc_wh[nb][0];
+            mine[g * HID + 32 * c + 8 * nb + 2 * t + 1] = acc_wh[nb][1];
+        }
+        mine[NO * HID + 32 * c + lane] = acc_benc;
+        if (c == 0) {
+#pragma unroll
+            for (int k = 0; k < NO; ++k) {
+                float x = acc_bh[k];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+                if (lane == 0) mine[NO * HID + HID + k] = x;
+            }
+        }
+    }
+    __syncthreads();
+    float* pt = p.part_tail + (int64_t)blockIdx.x * TAIL;
+    for (int j = threadIdx.x; j < TAIL; j += X2_THREADS) pt[j] = red[j] + red[TAIL + j] + red[2 * TAIL + j] + red[3 * TAIL + j];
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+}
+
 // Deterministic sum of the per-CTA partials into the flat gradient buffer:
 //   gflat = [ dW_enc[hid][feat] (transposed from the partials' [feat][hid]) | dW_heads 8 x hid | db_enc | db_heads ]
 // Block = 64 outputs x 4 partial groups; consecutive threads read consecutive partial elements (coalesced).
@@ -720,7 +1091,16 @@ int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t row
 
 int num_sms() { return pb_num_sms(); }
 
+int g_xt_regs = 96;
+int g_update_variant = 1;     // 1 = two x layouts (k_mlp_update_fused), 2 = one x layout + transposing MMA (k_mlp_update_xt)
+
 }  // namespace
+
+extern "C" int pb_mlp_update_set_variant(int32_t variant) {
+    PB_REQUIRE(variant == 1 || variant == 2, PB_ERR_INVALID, "pb_mlp_update_set_variant: 1 or 2");
+    g_update_variant = variant;
+    return PB_OK;
+}
 
 extern "C" size_t pb_mlp_update_workspace_bytes(void) {
     return (size_t)num_sms() * (FEAT * HID + TAIL) * sizeof(float);
@@ -784,11 +1164,26 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<5, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<8, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<5, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<8, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
+        int blocks = 0;      // 576 threads x 112 registers only fit if the register file is allocated at warp granularity
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_mlp_update_xt<5, 112>, X2_THREADS, X2_TOTAL));
+        g_xt_regs = blocks >= 1 ? 112 : 96;
         attr_set = true;
     }
     if (dpre_out) {
         if (n_act + 1 <= 5) k_mlp_update_fused<5, false><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
         else k_mlp_update_fused<8, false><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
+    } else if (g_update_variant == 2) {
+        if (g_xt_regs == 112) {
+            if (n_act + 1 <= 5) k_mlp_update_xt<5, 112><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
+            else k_mlp_update_xt<8, 112><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
+        } else {
+            if (n_act + 1 <= 5) k_mlp_update_xt<5, 96><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
+            else k_mlp_update_xt<8, 96><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
+        }
     } else {
         if (n_act + 1 <= 5) k_mlp_update_fused<5, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
         else k_mlp_update_fused<8, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);

@@ -173,6 +173,10 @@ def timing():
 
 
 def main():
+    if '--variant' in sys.argv:
+        variant = int(sys.argv[sys.argv.index('--variant') + 1])
+        _native.check(lib.pb_mlp_update_set_variant(variant))
+        print('update kernel variant', variant, flush=True)
     ok = True
     for args in ((128, 1, 128, 4, 1), (1000, 1, 1000, 4, 2), (148 * 128 * 2 + 77, 1, 148 * 128 * 2 + 77, 7, 3),
                  (300, 2, 1000, 1, 4), (4096, 4, 16384, 4, 5)):
