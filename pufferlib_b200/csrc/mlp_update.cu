@@ -711,25 +711,25 @@ __device__ __forceinline__ uint32_t g_off(int n, int l) {
     return (uint32_t)(n * 128 + ((((l >> 2) ^ (n & 7))) << 4) + ((l & 3) << 2));
 }
 
-// pass 1 / pass 2 bodies with the column quarter as a template parameter: every c_wh / c_benc operand is a constant-bank
-// immediate
-template <int NH, int C>
-__device__ __forceinline__ void x2_heads(const float (&v)[32], float (&out)[NO]) {
+// pass 1 / pass 2 bodies; the column quarter is a warp-uniform RUNTIME offset into the constant bank (uniform-register
+// addressing), so all 16 epilogue warps run the same instructions (one copy in the instruction caches)
+template <int NH>
+__device__ __forceinline__ void x2_heads(const float (&v)[32], float (&out)[NO], int col0) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-        const float rh = fmaxf(v[k] + c_benc[32 * C + k], 0.f);
+        const float rh = fmaxf(v[k] + c_benc[col0 + k], 0.f);
 #pragma unroll
-        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * C + k], out[a]);
+        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + col0 + k], out[a]);
     }
 }
-template <int NH, int C>
-__device__ __forceinline__ void x2_dpre(float (&v)[32], float (&dp)[32], const float (&dO)[NO]) {
+template <int NH>
+__device__ __forceinline__ void x2_dpre(float (&v)[32], float (&dp)[32], const float (&dO)[NO], int col0) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-        const float pre = v[k] + c_benc[32 * C + k];
+        const float pre = v[k] + c_benc[col0 + k];
         float gk = 0.f;
 #pragma unroll
-        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * C + k], gk);
+        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + col0 + k], gk);
         dp[k] = pre > 0.f ? gk : 0.f;
         v[k] = fmaxf(pre, 0.f);
     }
@@ -866,24 +866,39 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         uint8_t* mine = gq + 32 * c * 128;                      // its hidden units 32c..32c+31: private until published
         float* xch = reinterpret_cast<float*>(smem + X2_XCH) + (q * 4 * 32 + lane) * 8;   // + c' * 256 floats
         float z0 = 0.f, z1 = 0.f;
-        for (int it = 0; it < n_my; ++it) {
+        // per-row scalars: loaded one tile ahead (their HBM latency would otherwise sit at the head of every tile)
+        struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; int64_t i; };
+        const float adv_mean = p.adv_norm ? p.adv_norm[0] : 0.f, adv_rstd = p.adv_norm ? p.adv_norm[1] : 1.f;
+        auto load_row = [&](int it) {
+            RowIn r;
+            r.act = 0; r.old_lp = 0.f; r.adv = 0.f; r.ret = 0.f; r.old_v = 0.f; r.valid = false; r.i = 0;
+            if (it >= n_my) return r;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            const int s = it & 1, ph = (it >> 1) & 1;
             const int slab = tile / p.tiles_per_slab;
             const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
-            const bool valid = lrow < p.slab_rows;
-            const int64_t i = (int64_t)slab * p.slab_rows + lrow;
-            const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;
-            int act = 0;
-            float old_lp = 0.f, adv = 0.f, ret = 0.f, old_v = 0.f;
-            if (valid) {
-                act = (int)p.actions[ri];
-                old_lp = p.old_logprobs[ri];
-                adv = p.adv[ri];
-                old_v = (p.clip_vloss || !p.returns) ? p.old_values[ri] : 0.f;
-                ret = p.returns ? p.returns[ri] : adv + old_v;
-                if (p.adv_norm) adv = (adv - p.adv_norm[0]) * p.adv_norm[1];
+            r.valid = lrow < p.slab_rows;
+            r.i = (int64_t)slab * p.slab_rows + lrow;                        // slab-major position (debug rows)
+            const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;     // position in the per-row arrays
+            if (r.valid) {
+                r.act = (int)p.actions[ri];
+                r.old_lp = p.old_logprobs[ri];
+                r.adv = p.adv[ri];
+                r.old_v = (p.clip_vloss || !p.returns) ? p.old_values[ri] : 0.f;
+                r.ret = p.returns ? p.returns[ri] : 0.f;
             }
+            return r;
+        };
+        RowIn nxt = load_row(0);
+        for (int it = 0; it < n_my; ++it) {
+            const int s = it & 1, ph = (it >> 1) & 1;
+            const RowIn cur = nxt;
+            nxt = load_row(it + 1);
+            const bool valid = cur.valid;
+            const int64_t i = cur.i;
+            const int act = cur.act;
+            const float old_lp = cur.old_lp, old_v = cur.old_v;
+            const float ret = p.returns ? cur.ret : cur.adv + cur.old_v;     // returns = raw advantages + old values (:476-481)
+            const float adv = (cur.adv - adv_mean) * adv_rstd;
             mbar_wait(&h_full[s], ph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * HID + 32 * c);
@@ -893,12 +908,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
             for (int a = 0; a < NO; ++a) out[a] = 0.f;
             tmem_ld32(taddr, v);
-            switch (c) {
-                case 0: x2_heads<NH, 0>(v, out); break;
-                case 1: x2_heads<NH, 1>(v, out); break;
-                case 2: x2_heads<NH, 2>(v, out); break;
-                default: x2_heads<NH, 3>(v, out); break;
-            }
+            x2_heads<NH>(v, out, 32 * c);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // everybody has read the previous tile's partials
             *reinterpret_cast<float4*>(xch + c * 256) = make_float4(out[0], out[1], out[2], out[3]);
             *reinterpret_cast<float4*>(xch + c * 256 + 4) = make_float4(out[4], out[5], out[6], out[7]);
@@ -951,12 +961,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             // ---- pass 2: dPre, dW_heads, db_enc of this quarter
             float dp[32];
             tmem_ld32(taddr, v);
-            switch (c) {
-                case 0: x2_dpre<NH, 0>(v, dp, dO); break;
-                case 1: x2_dpre<NH, 1>(v, dp, dO); break;
-                case 2: x2_dpre<NH, 2>(v, dp, dO); break;
-                default: x2_dpre<NH, 3>(v, dp, dO); break;
-            }
+            x2_dpre<NH>(v, dp, dO, 32 * c);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_empty[s]);                          // the accumulator stage is free
