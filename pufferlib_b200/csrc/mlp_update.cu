@@ -692,7 +692,8 @@ constexpr int X2_THREADS = 576;                          // warp 0 TMA, warp 1 M
 constexpr int X2_W = 0, X2_XK = TILE_BYTES, X2_G = 2 * TILE_BYTES;     // W_enc | x tile | 4 dPre blocks of 16 KiB
 constexpr int X2_XCH = 3 * TILE_BYTES;                   // [4 q][4 c][32 rows][8 floats] partial head sums
 constexpr int X2_ID = X2_XCH + 16384;                    // sliding identity: 2 strips of 32 core matrices
-constexpr int X2_BAR = X2_ID + 8192;
+constexpr int X2_ACC = X2_ID + 8192;                     // [128 rows][16 floats]: 6 loss statistics | 2 pad | 8 db_heads sums
+constexpr int X2_BAR = X2_ACC + 8192;
 constexpr int X2_TOTAL = X2_BAR + 256;
 constexpr int X2_TMEM_XT = 256, X2_TMEM_DW = 384;
 constexpr int X2_ID_GROUP = 128, X2_ID_STRIP = 32 * X2_ID_GROUP;
@@ -711,27 +712,30 @@ __device__ __forceinline__ uint32_t g_off(int n, int l) {
     return (uint32_t)(n * 128 + ((((l >> 2) ^ (n & 7))) << 4) + ((l & 3) << 2));
 }
 
-// pass 1 / pass 2 bodies; the column quarter is a warp-uniform RUNTIME offset into the constant bank (uniform-register
-// addressing), so all 16 epilogue warps run the same instructions (one copy in the instruction caches)
-template <int NH>
-__device__ __forceinline__ void x2_heads(const float (&v)[32], float (&out)[NO], int col0) {
+// pass 1 / pass 2 bodies with the column quarter as a template parameter: the c_wh / c_benc operands then come through
+// uniform registers (LDCU + FFMA ... UR); a runtime offset compiles to one per-thread LDC in front of every FFMA, 1.8x slower
+template <int NH, int C>
+__device__ __forceinline__ void x2_heads(const float (&v)[32], float (&out)[NO]) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-        const float rh = fmaxf(v[k] + c_benc[col0 + k], 0.f);
+        const float rh = fmaxf(v[k] + c_benc[32 * C + k], 0.f);
 #pragma unroll
-        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + col0 + k], out[a]);
+        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * C + k], out[a]);
     }
 }
-template <int NH>
-__device__ __forceinline__ void x2_dpre(float (&v)[32], float (&dp)[32], const float (&dO)[NO], int col0) {
+// v: pre-activations of the row -> dPre in place; relu(h) (TF32-rounded) goes straight to the warp's part of the dPre block
+template <int NH, int C>
+__device__ __forceinline__ void x2_dpre(float (&v)[32], const float (&dO)[NO], uint8_t* mine, int lane, float* dbg_h) {
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-        const float pre = v[k] + c_benc[col0 + k];
+        const float pre = v[k] + c_benc[32 * C + k];
         float gk = 0.f;
 #pragma unroll
-        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + col0 + k], gk);
-        dp[k] = pre > 0.f ? gk : 0.f;
-        v[k] = fmaxf(pre, 0.f);
+        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * C + k], gk);
+        const float rh = fmaxf(pre, 0.f);
+        *reinterpret_cast<uint32_t*>(mine + g_off(k, lane)) = to_tf32(rh);
+        if (dbg_h) dbg_h[k] = rh;
+        v[k] = pre > 0.f ? gk : 0.f;
     }
 }
 
@@ -769,7 +773,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // sliding identity: strip s (features 4s..4s+3 of a K = 8 slice) is 32 core matrices of 8 rows x 16 B, all zero except
     // number 15, whose row r holds a 1 at column r - 4s.  MMA k reads from (15 - k) core matrices in: row group k of A sees
     // the identity block, every other row group zeros.
-    for (int i = threadIdx.x; i < 8192 / 16; i += X2_THREADS) reinterpret_cast<uint4*>(smem + X2_ID)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 16384 / 16; i += X2_THREADS) reinterpret_cast<uint4*>(smem + X2_ID)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (threadIdx.x < 8) {
         const int r = threadIdx.x;
@@ -791,12 +795,8 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // epilogue warp (q, c): TMEM lane quadrant q (tile rows 32q..32q+31), hidden units 32c..32c+31
     float acc_wh[4][2];                  // dW_heads[a = lane>>2][32c + 8nb + 2(lane&3) + {0,1}] (this warp's rows)
     float acc_benc = 0.f;                // db_enc[32c + lane]
-    float acc_bh[NO];                    // db_heads (c == 0)
-    float st[6] = {0, 0, 0, 0, 0, 0};    // per-thread statistics of <= 28 tiles: fp32 here, fp64 across threads
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) acc_wh[nb][0] = acc_wh[nb][1] = 0.f;
-#pragma unroll
-    for (int k = 0; k < NO; ++k) acc_bh[k] = 0.f;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -867,17 +867,16 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         float* xch = reinterpret_cast<float*>(smem + X2_XCH) + (q * 4 * 32 + lane) * 8;   // + c' * 256 floats
         float z0 = 0.f, z1 = 0.f;
         // per-row scalars: loaded one tile ahead (their HBM latency would otherwise sit at the head of every tile)
-        struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; int64_t i; };
+        struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; };
         const float adv_mean = p.adv_norm ? p.adv_norm[0] : 0.f, adv_rstd = p.adv_norm ? p.adv_norm[1] : 1.f;
         auto load_row = [&](int it) {
             RowIn r;
-            r.act = 0; r.old_lp = 0.f; r.adv = 0.f; r.ret = 0.f; r.old_v = 0.f; r.valid = false; r.i = 0;
+            r.act = 0; r.old_lp = 0.f; r.adv = 0.f; r.ret = 0.f; r.old_v = 0.f; r.valid = false;
             if (it >= n_my) return r;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int slab = tile / p.tiles_per_slab;
             const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
             r.valid = lrow < p.slab_rows;
-            r.i = (int64_t)slab * p.slab_rows + lrow;                        // slab-major position (debug rows)
             const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;     // position in the per-row arrays
             if (r.valid) {
                 r.act = (int)p.actions[ri];
@@ -894,7 +893,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const RowIn cur = nxt;
             nxt = load_row(it + 1);
             const bool valid = cur.valid;
-            const int64_t i = cur.i;
+            int64_t dbg_i = 0;
             const int act = cur.act;
             const float old_lp = cur.old_lp, old_v = cur.old_v;
             const float ret = p.returns ? cur.ret : cur.adv + cur.old_v;     // returns = raw advantages + old values (:476-481)
@@ -908,7 +907,12 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
             for (int a = 0; a < NO; ++a) out[a] = 0.f;
             tmem_ld32(taddr, v);
-            x2_heads<NH>(v, out, 32 * c);
+            switch (c) {
+                case 0: x2_heads<NH, 0>(v, out); break;
+                case 1: x2_heads<NH, 1>(v, out); break;
+                case 2: x2_heads<NH, 2>(v, out); break;
+                default: x2_heads<NH, 3>(v, out); break;
+            }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // everybody has read the previous tile's partials
             *reinterpret_cast<float4*>(xch + c * 256) = make_float4(out[0], out[1], out[2], out[3]);
             *reinterpret_cast<float4*>(xch + c * 256 + 4) = make_float4(out[4], out[5], out[6], out[7]);
@@ -931,17 +935,21 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int a = 0; a < NO; ++a) dO[a] = 0.f;
             if (valid) {
                 const RowStats rs = ppo_row(out, p, act, old_lp, adv, ret, old_v, dO);
-                if (c == 0) {
-                    st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
+                if (c == 0) {      // statistics and db_heads of the row: fp32 running sums of this thread in shared memory
+                    float4* a4 = reinterpret_cast<float4*>(smem + X2_ACC) + rloc * 4;
+                    float4 s0 = a4[0], s1 = a4[1], s2 = a4[2], s3 = a4[3];
+                    s0.x += rs.pg; s0.y += rs.v; s0.z += rs.ent; s0.w += rs.okl;
+                    s1.x += rs.kl; s1.y += rs.clipped;
+                    s2.x += dO[0]; s2.y += dO[1]; s2.z += dO[2]; s2.w += dO[3];
+                    s3.x += dO[4]; s3.y += dO[5]; s3.z += dO[6]; s3.w += dO[7];
+                    a4[0] = s0; a4[1] = s1; a4[2] = s2; a4[3] = s3;
                     if (p.dbg_dout) {
-                        *reinterpret_cast<float4*>(p.dbg_dout + i * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-                        *reinterpret_cast<float4*>(p.dbg_dout + i * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                        float* dd = p.dbg_dout + ((int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc) * 8;
+                        *reinterpret_cast<float4*>(dd) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+                        *reinterpret_cast<float4*>(dd + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
                     }
                 }
-            }
-            if (c == 0) {
-#pragma unroll
-                for (int a = 0; a < NO; ++a) acc_bh[a] += dO[a];
             }
 
             // ---- A fragments of the dW_heads mma (A[m = head a][k = row]) through this warp's part of the dPre block
@@ -959,22 +967,29 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             __syncwarp();
 
             // ---- pass 2: dPre, dW_heads, db_enc of this quarter
-            float dp[32];
             tmem_ld32(taddr, v);
-            x2_dpre<NH>(v, dp, dO, 32 * c);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_empty[s]);                          // the accumulator stage is free
-            if (valid && p.dbg_hidden) {
+            {
+                float* dbg_h = nullptr;
+                if (valid && p.dbg_hidden) {
+                    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                    dbg_i = ((int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc) * HID + 32 * c;
+                    dbg_h = p.dbg_hidden + dbg_i;
+                }
+                switch (c) {
+                    case 0: x2_dpre<NH, 0>(v, dO, mine, lane, dbg_h); break;
+                    case 1: x2_dpre<NH, 1>(v, dO, mine, lane, dbg_h); break;
+                    case 2: x2_dpre<NH, 2>(v, dO, mine, lane, dbg_h); break;
+                    default: x2_dpre<NH, 3>(v, dO, mine, lane, dbg_h); break;
+                }
+                if (dbg_h) {
 #pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    *reinterpret_cast<float4*>(p.dbg_hidden + i * HID + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-                    *reinterpret_cast<float4*>(p.dbg_dpre + i * HID + 32 * c + k) = make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]);
+                    for (int k = 0; k < 32; k += 4)
+                        *reinterpret_cast<float4*>(p.dbg_dpre + dbg_i + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
                 }
             }
-            // relu(h) of the warp's 32 rows x 32 hidden units (TF32-rounded), K-major like the dPre that replaces it
-#pragma unroll
-            for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(mine + g_off(k, lane)) = to_tf32(v[k]);
             __syncwarp();
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -987,7 +1002,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             }
             __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(mine + g_off(k, lane)) = dp[k];
+            for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(mine + g_off(k, lane)) = v[k];
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dp_full[q]);
@@ -1011,9 +1026,10 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(pd + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
         if (c == 0) {
+            const float* acc = reinterpret_cast<const float*>(smem + X2_ACC) + rloc * 16;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                double x = (double)st[k];
+                double x = (double)acc[k];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
                 if (lane == 0) atomicAdd(p.stats + k, x);
@@ -1035,9 +1051,10 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         mine[NO * HID + 32 * c + lane] = acc_benc;
         if (c == 0) {
+            const float* acc = reinterpret_cast<const float*>(smem + X2_ACC) + (32 * q + lane) * 16 + 8;
 #pragma unroll
             for (int k = 0; k < NO; ++k) {
-                float x = acc_bh[k];
+                float x = acc[k];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
                 if (lane == 0) mine[NO * HID + HID + k] = x;
