@@ -690,10 +690,11 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
 // TMEM: [0,256) two forward accumulators, [256,384) x^T, [384,512) dW^T (lives across all tiles of the CTA).
 constexpr int X2_THREADS = 576;                          // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int X2_W = 0, X2_XK = TILE_BYTES, X2_G = 2 * TILE_BYTES;     // W_enc | x tile | 4 dPre blocks of 16 KiB
-constexpr int X2_XCH = 3 * TILE_BYTES;                   // [4 q][4 c][32 rows][8 floats] partial head sums
+constexpr int X2_XCH = 3 * TILE_BYTES;                   // [4 q][4 c][32 rows][8 heads] partial head sums
 constexpr int X2_ID = X2_XCH + 16384;                    // sliding identity: 2 strips of 32 core matrices
-constexpr int X2_ACC = X2_ID + 8192;                     // [128 rows][16 floats]: 6 loss statistics | 2 pad | 8 db_heads sums
-constexpr int X2_BAR = X2_ACC + 8192;
+constexpr int X2_DO = X2_ID + 8192;                      // [4 q][32 rows][8 heads] dOut of the tile
+constexpr int X2_BE = X2_DO + 4096;                      // b_enc [128]
+constexpr int X2_BAR = X2_BE + 512;
 constexpr int X2_TOTAL = X2_BAR + 256;
 constexpr int X2_TMEM_XT = 256, X2_TMEM_DW = 384;
 constexpr int X2_ID_GROUP = 128, X2_ID_STRIP = 32 * X2_ID_GROUP;
@@ -706,40 +707,21 @@ __device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo_bytes
            (1ull << 46);
 }
 
-// byte offset of element (hidden unit n, tile row r) inside dPre block r >> 5: K-major SWIZZLE_128B, n = MN row of 128 B,
-// the 32 rows of the quadrant along K
+// byte offset of element (hidden unit n, tile row l of the quadrant) inside a warp's part of dPre block q: K-major
+// SWIZZLE_128B, n = MN row of 128 B, the 32 rows of the quadrant along K
 __device__ __forceinline__ uint32_t g_off(int n, int l) {
     return (uint32_t)(n * 128 + ((((l >> 2) ^ (n & 7))) << 4) + ((l & 3) << 2));
 }
 
-// pass 1 / pass 2 bodies with the column quarter as a template parameter: the c_wh / c_benc operands then come through
-// uniform registers (LDCU + FFMA ... UR); a runtime offset compiles to one per-thread LDC in front of every FFMA, 1.8x slower
-template <int NH, int C>
-__device__ __forceinline__ void x2_heads(const float (&v)[32], float (&out)[NO]) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        const float rh = fmaxf(v[k] + c_benc[32 * C + k], 0.f);
-#pragma unroll
-        for (int a = 0; a < NH; ++a) out[a] = fmaf(rh, c_wh[a * HID + 32 * C + k], out[a]);
-    }
-}
-// v: pre-activations of the row -> dPre in place; relu(h) (TF32-rounded) goes straight to the warp's part of the dPre block
-template <int NH, int C>
-__device__ __forceinline__ void x2_dpre(float (&v)[32], const float (&dO)[NO], uint8_t* mine, int lane, float* dbg_h) {
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-        const float pre = v[k] + c_benc[32 * C + k];
-        float gk = 0.f;
-#pragma unroll
-        for (int a = 0; a < NH; ++a) gk = fmaf(dO[a], c_wh[a * HID + 32 * C + k], gk);
-        const float rh = fmaxf(pre, 0.f);
-        *reinterpret_cast<uint32_t*>(mine + g_off(k, lane)) = to_tf32(rh);
-        if (dbg_h) dbg_h[k] = rh;
-        v[k] = pre > 0.f ? gk : 0.f;
-    }
+// mma.sync m16n8k8 TF32 with all four A registers: a0 (g, t)  a1 (g + 8, t)  a2 (g, t + 4)  a3 (g + 8, t + 4);
+// b0 (k = t, n = g)  b1 (k = t + 4, n = g);  c0 c1 (g, 2t + {0,1})  c2 c3 (g + 8, 2t + {0,1})      [g = lane >> 2, t = lane & 3]
+__device__ __forceinline__ void mma_tf32_full(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int NH, int REGS>
+template <int REGS>
 __global__ void __maxnreg__(REGS)
 k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -748,7 +730,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint64_t* xk_full = bars + 1;         // x tile landed
     uint64_t* xk_empty = bars + 2;        // ... read by the forward AND the transposing MMAs
     uint64_t* h_full = bars + 3;          // [2] forward accumulator complete
-    uint64_t* h_empty = bars + 5;         // [2] drained by the 16 epilogue warps
+    uint64_t* h_empty = bars + 5;         // [2] read by the 16 epilogue warps
     uint64_t* dp_full = bars + 7;         // [4] dPre block of row quadrant q written (4 warps)
     uint64_t* dp_empty = bars + 11;       // [4] ... consumed by its dW MMAs
     uint64_t* dw_done = bars + 15;
@@ -773,7 +755,8 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // sliding identity: strip s (features 4s..4s+3 of a K = 8 slice) is 32 core matrices of 8 rows x 16 B, all zero except
     // number 15, whose row r holds a 1 at column r - 4s.  MMA k reads from (15 - k) core matrices in: row group k of A sees
     // the identity block, every other row group zeros.
-    for (int i = threadIdx.x; i < 16384 / 16; i += X2_THREADS) reinterpret_cast<uint4*>(smem + X2_ID)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 8192 / 16; i += X2_THREADS) reinterpret_cast<uint4*>(smem + X2_ID)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < HID) reinterpret_cast<float*>(smem + X2_BE)[threadIdx.x] = c_benc[threadIdx.x];
     __syncthreads();
     if (threadIdx.x < 8) {
         const int r = threadIdx.x;
@@ -795,8 +778,12 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // epilogue warp (q, c): TMEM lane quadrant q (tile rows 32q..32q+31), hidden units 32c..32c+31
     float acc_wh[4][2];                  // dW_heads[a = lane>>2][32c + 8nb + 2(lane&3) + {0,1}] (this warp's rows)
     float acc_benc = 0.f;                // db_enc[32c + lane]
+    float acc_bh[NO];                    // db_heads (c == 0: the warp that evaluates the loss)
+    float st[6] = {0, 0, 0, 0, 0, 0};    // per-thread statistics of <= 28 tiles: fp32 here, fp64 across threads
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) acc_wh[nb][0] = acc_wh[nb][1] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NO; ++k) acc_bh[k] = 0.f;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -859,20 +846,42 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             umma_commit(dw_done);
         }
     } else {
+        // ================= epilogue: all per-element products on the warp-level tensor core path (mma.sync, TF32 operands,
+        // fp32 accumulation -- the precision class of torch.set_float32_matmul_precision('high'), clean_pufferl.py:22).
+        // Thread = row only for the TMEM read, the ReLU and the loss; everything else works on mma fragments of the warp's
+        // [32 rows][32 hidden units] block staged in its part of the dPre block.
         const int q = warp & 3, c = (warp - 2) >> 2;
         const int g = lane >> 2, t = lane & 3;
         const int rloc = 32 * q + lane;
-        uint8_t* gq = smem + X2_G + q * KBLK_BYTES;             // dPre block of this row quadrant
-        uint8_t* mine = gq + 32 * c * 128;                      // its hidden units 32c..32c+31: private until published
-        float* xch = reinterpret_cast<float*>(smem + X2_XCH) + (q * 4 * 32 + lane) * 8;   // + c' * 256 floats
+        uint8_t* mine = smem + X2_G + q * KBLK_BYTES + 32 * c * 128;   // hidden units 32c..32c+31 x the quadrant's 32 rows
+        float* xch = reinterpret_cast<float*>(smem + X2_XCH) + q * 1024;                  // [4 c][32 rows][8 heads]
+        float* dos = reinterpret_cast<float*>(smem + X2_DO) + q * 256;                    // [32 rows][8 heads]
+        const float4* be4 = reinterpret_cast<const float4*>(smem + X2_BE) + 8 * c;
+        // W_heads fragments of this column quarter (TF32), resident in registers:
+        //   heads product  out[row][a] = sum_j rh[row][j] W[a][j]:   B[k = j][n = a]
+        //   g^T product    g[j][row]   = sum_a W[a][j] dO[row][a]:   A[m = j][k = a]
+        uint32_t hb[4][2], ga[2][4];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            hb[kb][0] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + t]);
+            hb[kb][1] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + t + 4]);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            ga[mb][0] = to_tf32(c_wh[t * HID + 32 * c + 16 * mb + g]);
+            ga[mb][1] = to_tf32(c_wh[t * HID + 32 * c + 16 * mb + g + 8]);
+            ga[mb][2] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g]);
+            ga[mb][3] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g + 8]);
+        }
         float z0 = 0.f, z1 = 0.f;
-        // per-row scalars: loaded one tile ahead (their HBM latency would otherwise sit at the head of every tile)
+
+        // per-row scalars of the warp that evaluates the loss (c == 0): loaded one tile ahead
         struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; };
         const float adv_mean = p.adv_norm ? p.adv_norm[0] : 0.f, adv_rstd = p.adv_norm ? p.adv_norm[1] : 1.f;
         auto load_row = [&](int it) {
             RowIn r;
             r.act = 0; r.old_lp = 0.f; r.adv = 0.f; r.ret = 0.f; r.old_v = 0.f; r.valid = false;
-            if (it >= n_my) return r;
+            if (c != 0 || it >= n_my) return r;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int slab = tile / p.tiles_per_slab;
             const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
@@ -887,126 +896,153 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             }
             return r;
         };
-        RowIn nxt = load_row(0);
+        RowIn row = load_row(0);
         for (int it = 0; it < n_my; ++it) {
             const int s = it & 1, ph = (it >> 1) & 1;
-            const RowIn cur = nxt;
-            nxt = load_row(it + 1);
-            const bool valid = cur.valid;
-            int64_t dbg_i = 0;
-            const int act = cur.act;
-            const float old_lp = cur.old_lp, old_v = cur.old_v;
-            const float ret = p.returns ? cur.ret : cur.adv + cur.old_v;     // returns = raw advantages + old values (:476-481)
-            const float adv = (cur.adv - adv_mean) * adv_rstd;
+            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+            // slab-major position of this thread's row (debug dumps)
+            const int64_t dbg_row = (int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
+            const bool dbg_ok = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc < p.slab_rows;
+
+            // ---- 1. h -> relu(h + b_enc), TF32-rounded, into the warp's part of the dPre block (K-major: [hidden unit][row])
             mbar_wait(&h_full[s], ph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * HID + 32 * c);
-
-            // ---- pass 1: this quarter's share of the head products; the four warps of the quadrant exchange them
-            float out[NO], v[32];
-#pragma unroll
-            for (int a = 0; a < NO; ++a) out[a] = 0.f;
-            tmem_ld32(taddr, v);
-            switch (c) {
-                case 0: x2_heads<NH, 0>(v, out); break;
-                case 1: x2_heads<NH, 1>(v, out); break;
-                case 2: x2_heads<NH, 2>(v, out); break;
-                default: x2_heads<NH, 3>(v, out); break;
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");      // everybody has read the previous tile's partials
-            *reinterpret_cast<float4*>(xch + c * 256) = make_float4(out[0], out[1], out[2], out[3]);
-            *reinterpret_cast<float4*>(xch + c * 256 + 4) = make_float4(out[4], out[5], out[6], out[7]);
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
-#pragma unroll
-            for (int a = 0; a < NO; ++a) out[a] = 0.f;
-#pragma unroll
-            for (int cq = 0; cq < 4; ++cq) {                                 // same order in all four warps
-                const float4 lo = *reinterpret_cast<const float4*>(xch + cq * 256);
-                const float4 hi = *reinterpret_cast<const float4*>(xch + cq * 256 + 4);
-                out[0] += lo.x; out[1] += lo.y; out[2] += lo.z; out[3] += lo.w;
-                out[4] += hi.x; out[5] += hi.y; out[6] += hi.z; out[7] += hi.w;
-            }
-#pragma unroll
-            for (int a = 0; a < NO; ++a) out[a] += c_bh[a];
-
-            // ---- loss row math -> dOut (all four warps; statistics and db_heads by c == 0)
-            float dO[NO];
-#pragma unroll
-            for (int a = 0; a < NO; ++a) dO[a] = 0.f;
-            if (valid) {
-                const RowStats rs = ppo_row(out, p, act, old_lp, adv, ret, old_v, dO);
-                if (c == 0) {      // statistics and db_heads of the row: fp32 running sums of this thread in shared memory
-                    float4* a4 = reinterpret_cast<float4*>(smem + X2_ACC) + rloc * 4;
-                    float4 s0 = a4[0], s1 = a4[1], s2 = a4[2], s3 = a4[3];
-                    s0.x += rs.pg; s0.y += rs.v; s0.z += rs.ent; s0.w += rs.okl;
-                    s1.x += rs.kl; s1.y += rs.clipped;
-                    s2.x += dO[0]; s2.y += dO[1]; s2.z += dO[2]; s2.w += dO[3];
-                    s3.x += dO[4]; s3.y += dO[5]; s3.z += dO[6]; s3.w += dO[7];
-                    a4[0] = s0; a4[1] = s1; a4[2] = s2; a4[3] = s3;
-                    if (p.dbg_dout) {
-                        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-                        float* dd = p.dbg_dout + ((int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc) * 8;
-                        *reinterpret_cast<float4*>(dd) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-                        *reinterpret_cast<float4*>(dd + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
-                    }
-                }
-            }
-
-            // ---- A fragments of the dW_heads mma (A[m = head a][k = row]) through this warp's part of the dPre block
-            //      (row r of the warp at byte r * 128 + (r & 3) * 32: conflict-free fragment loads)
-            mbar_wait(&dp_empty[q], (uint32_t)((it & 1) ^ 1));               // the dW MMAs of the previous tile have read the block
-            uint32_t afr[4][2];
-            *reinterpret_cast<float4*>(mine + lane * 128 + (lane & 3) * 32) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-            *reinterpret_cast<float4*>(mine + lane * 128 + (lane & 3) * 32 + 16) = make_float4(dO[4], dO[5], dO[6], dO[7]);
-            __syncwarp();
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                afr[ks][0] = to_tf32(*reinterpret_cast<const float*>(mine + (8 * ks + t) * 128 + t * 32 + g * 4));
-                afr[ks][1] = to_tf32(*reinterpret_cast<const float*>(mine + (8 * ks + t + 4) * 128 + t * 32 + g * 4));
-            }
-            __syncwarp();
-
-            // ---- pass 2: dPre, dW_heads, db_enc of this quarter
-            tmem_ld32(taddr, v);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_empty[s]);                          // the accumulator stage is free
             {
-                float* dbg_h = nullptr;
-                if (valid && p.dbg_hidden) {
-                    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-                    dbg_i = ((int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc) * HID + 32 * c;
-                    dbg_h = p.dbg_hidden + dbg_i;
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(s * HID + 32 * c), v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&h_empty[s]);                      // the accumulator stage is free already
+                mbar_wait(&dp_empty[q], (uint32_t)((it & 1) ^ 1));            // the dW MMAs of the previous tile have read the block
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 b = be4[k4];
+                    v[4 * k4] = fmaxf(v[4 * k4] + b.x, 0.f);
+                    v[4 * k4 + 1] = fmaxf(v[4 * k4 + 1] + b.y, 0.f);
+                    v[4 * k4 + 2] = fmaxf(v[4 * k4 + 2] + b.z, 0.f);
+                    v[4 * k4 + 3] = fmaxf(v[4 * k4 + 3] + b.w, 0.f);
                 }
-                switch (c) {
-                    case 0: x2_dpre<NH, 0>(v, dO, mine, lane, dbg_h); break;
-                    case 1: x2_dpre<NH, 1>(v, dO, mine, lane, dbg_h); break;
-                    case 2: x2_dpre<NH, 2>(v, dO, mine, lane, dbg_h); break;
-                    default: x2_dpre<NH, 3>(v, dO, mine, lane, dbg_h); break;
-                }
-                if (dbg_h) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(mine + g_off(k, lane)) = to_tf32(v[k]);
+                if (p.dbg_hidden && dbg_ok) {
 #pragma unroll
                     for (int k = 0; k < 32; k += 4)
-                        *reinterpret_cast<float4*>(p.dbg_dpre + dbg_i + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                        *reinterpret_cast<float4*>(p.dbg_hidden + dbg_row * HID + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
                 }
             }
             __syncwarp();
+
+            // ---- 2. this quarter's share of the head products: out[32 rows][8] = rh[32][32] . W^T
+            {
+                float hp[2][4];
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    hp[mb][0] = hp[mb][1] = hp[mb][2] = hp[mb][3] = 0.f;
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        uint32_t a[4];
+                        a[0] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t, 16 * mb + g));
+                        a[1] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t, 16 * mb + g + 8));
+                        a[2] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t + 4, 16 * mb + g));
+                        a[3] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t + 4, 16 * mb + g + 8));
+                        mma_tf32_full(hp[mb], a, hb[kb][0], hb[kb][1]);
+                    }
+                    *reinterpret_cast<float2*>(xch + (c * 32 + 16 * mb + g) * 8 + 2 * t) = make_float2(hp[mb][0], hp[mb][1]);
+                    *reinterpret_cast<float2*>(xch + (c * 32 + 16 * mb + g + 8) * 8 + 2 * t) = make_float2(hp[mb][2], hp[mb][3]);
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+
+            // ---- 3. the loss row math on the summed head outputs (warp c == 0 of the quadrant, thread = row) -> dOut
+            if (c == 0) {
+                float out[NO], dO[NO];
+#pragma unroll
+                for (int a = 0; a < NO; ++a) { out[a] = c_bh[a]; dO[a] = 0.f; }
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) {
+                    const float4 lo = *reinterpret_cast<const float4*>(xch + (cq * 32 + lane) * 8);
+                    const float4 hi = *reinterpret_cast<const float4*>(xch + (cq * 32 + lane) * 8 + 4);
+                    out[0] += lo.x; out[1] += lo.y; out[2] += lo.z; out[3] += lo.w;
+                    out[4] += hi.x; out[5] += hi.y; out[6] += hi.z; out[7] += hi.w;
+                }
+                if (row.valid) {
+                    const float ret = p.returns ? row.ret : row.adv + row.old_v;      // returns = raw advantages + old values (:476-481)
+                    const float adv = (row.adv - adv_mean) * adv_rstd;
+                    const RowStats rs = ppo_row(out, p, row.act, row.old_lp, adv, ret, row.old_v, dO);
+                    st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
+                    if (p.dbg_dout) {
+                        *reinterpret_cast<float4*>(p.dbg_dout + dbg_row * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+                        *reinterpret_cast<float4*>(p.dbg_dout + dbg_row * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < NO; ++a) acc_bh[a] += dO[a];
+                *reinterpret_cast<float4*>(dos + lane * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
+                *reinterpret_cast<float4*>(dos + lane * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                row = load_row(it + 1);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+
+            // ---- 4. dW_heads += dO^T . rh   (A[m = head][k = row] from the dOut tile, B[k = row][n = hidden unit] from rh)
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
+                uint32_t afr[2];
+                afr[0] = to_tf32(dos[(8 * ks + t) * 8 + g]);
+                afr[1] = to_tf32(dos[(8 * ks + t + 4) * 8 + g]);
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
                     const uint32_t b0 = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * nb + g, 8 * ks + t));
                     const uint32_t b1 = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * nb + g, 8 * ks + t + 4));
-                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[ks], b0, b1);
+                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr, b0, b1);
                 }
             }
-            __syncwarp();
+
+            // ---- 5. g^T[hidden unit][row] = W^T . dO^T, masked by rh > 0 -> dPre, in place over rh
+            {
+                float gt[2][4][4];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(mine + g_off(k, lane)) = v[k];
+                for (int nb = 0; nb < 4; ++nb) {
+                    const uint32_t b0 = to_tf32(dos[(8 * nb + g) * 8 + t]);
+                    const uint32_t b1 = to_tf32(dos[(8 * nb + g) * 8 + t + 4]);
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) {
+                        gt[mb][nb][0] = gt[mb][nb][1] = gt[mb][nb][2] = gt[mb][nb][3] = 0.f;
+                        mma_tf32_full(gt[mb][nb], ga[mb], b0, b1);
+                    }
+                }
+                // c0 c1: hidden unit 16mb + g, rows 8nb + 2t + {0,1};  c2 c3: hidden unit 16mb + g + 8, the same rows
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float2 r2 = *reinterpret_cast<const float2*>(mine + g_off(16 * mb + g + 8 * h, 8 * nb + 2 * t));
+                            gt[mb][nb][2 * h] = r2.x > 0.f ? gt[mb][nb][2 * h] : 0.f;
+                            gt[mb][nb][2 * h + 1] = r2.y > 0.f ? gt[mb][nb][2 * h + 1] : 0.f;
+                        }
+                __syncwarp();        // every lane has taken its rh fragments (steps 4 and 5) before dPre replaces them
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            *reinterpret_cast<float2*>(mine + g_off(16 * mb + g + 8 * h, 8 * nb + 2 * t)) =
+                                make_float2(gt[mb][nb][2 * h], gt[mb][nb][2 * h + 1]);
+                            if (p.dbg_dpre) {
+                                const int64_t r0 = dbg_row - lane + 8 * nb + 2 * t;        // slab-major row of tile row 32q + 8nb + 2t
+                                const bool ok0 = (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q + 8 * nb + 2 * t < p.slab_rows;
+                                const bool ok1 = (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q + 8 * nb + 2 * t + 1 < p.slab_rows;
+                                if (ok0) p.dbg_dpre[r0 * HID + 32 * c + 16 * mb + g + 8 * h] = gt[mb][nb][2 * h];
+                                if (ok1) p.dbg_dpre[(r0 + 1) * HID + 32 * c + 16 * mb + g + 8 * h] = gt[mb][nb][2 * h + 1];
+                            }
+                        }
+            }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dp_full[q]);
-            // db_enc: lane n sums hidden unit 32c + n over the warp's 32 rows (the UMMA only reads the block)
+            // ---- 6. db_enc: lane n sums hidden unit 32c + n over the warp's 32 rows (the UMMA only reads the block)
             float cs = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -1026,10 +1062,9 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(pd + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
         if (c == 0) {
-            const float* acc = reinterpret_cast<const float*>(smem + X2_ACC) + rloc * 16;
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
-                double x = (double)acc[k];
+                double x = (double)st[k];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
                 if (lane == 0) atomicAdd(p.stats + k, x);
@@ -1051,10 +1086,9 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         mine[NO * HID + 32 * c + lane] = acc_benc;
         if (c == 0) {
-            const float* acc = reinterpret_cast<const float*>(smem + X2_ACC) + (32 * q + lane) * 16 + 8;
 #pragma unroll
             for (int k = 0; k < NO; ++k) {
-                float x = acc[k];
+                float x = acc_bh[k];
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
                 if (lane == 0) mine[NO * HID + HID + k] = x;
@@ -1113,7 +1147,6 @@ int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t row
 
 int num_sms() { return pb_num_sms(); }
 
-int g_xt_regs = 96;
 int g_update_variant = 1;     // 1 = two x layouts (k_mlp_update_fused), 2 = one x layout + transposing MMA (k_mlp_update_xt)
 
 }  // namespace
@@ -1186,26 +1219,15 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<5, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<8, 112>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<5, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<8, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
-        int blocks = 0;      // 576 threads x 112 registers only fit if the register file is allocated at warp granularity
-        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_mlp_update_xt<5, 112>, X2_THREADS, X2_TOTAL));
-        g_xt_regs = blocks >= 1 ? 112 : 96;
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
         attr_set = true;
     }
     if (dpre_out) {
         if (n_act + 1 <= 5) k_mlp_update_fused<5, false><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
         else k_mlp_update_fused<8, false><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
     } else if (g_update_variant == 2) {
-        if (g_xt_regs == 112) {
-            if (n_act + 1 <= 5) k_mlp_update_xt<5, 112><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
-            else k_mlp_update_xt<8, 112><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
-        } else {
-            if (n_act + 1 <= 5) k_mlp_update_xt<5, 96><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
-            else k_mlp_update_xt<8, 96><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
-        }
+        // 18 warps = 5 on two of the four schedulers: 16384 registers / (5 x 32) caps the kernel at 96 per thread
+        k_mlp_update_xt<96><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
     } else {
         if (n_act + 1 <= 5) k_mlp_update_fused<5, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
         else k_mlp_update_fused<8, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);

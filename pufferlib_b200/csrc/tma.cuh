@@ -20,6 +20,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // attempts (seconds) something is broken (bad address, wrong byte count) -- trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
         uint32_t ok;
         asm volatile(

@@ -19,6 +19,7 @@ from pufferlib_b200 import _native  # noqa: E402
 
 lib = _native.lib()
 CFG = (0.1, 1, 0.1, 0.5, 0.01)      # clip, clip_vloss, vclip, vf_coef, ent_coef
+TF32_EPILOGUE = False               # variant 2: heads / dOut . W_heads products take TF32 operands (like torch 'high')
 
 
 def ptr(t):
@@ -101,11 +102,11 @@ def case(slab_rows, n_slabs, slab_stride, n_act, seed):
     # stage 2: heads + loss from the kernel's own hidden
     out = (dh.double() @ w_cat.double().t() + b_cat.double()).float()
     dout_ref, stats_ref = ppo_loss(out, act, olp, adv, ret, oval, n_act)
-    ok &= check('dOut (heads + PPO loss)', do, dout_ref, 2e-4)
-    ok &= check('loss statistics', stats[:6], stats_ref[:6], 1e-5)
+    ok &= check('dOut (heads + PPO loss)', do, dout_ref, 5e-3 if TF32_EPILOGUE else 2e-4)
+    ok &= check('loss statistics', stats[:6], stats_ref[:6], 2e-3 if TF32_EPILOGUE else 1e-5)
     # stage 3: dPre from the kernel's own dOut and hidden
     dpre_ref = (do.double() @ w_cat.double()) * (dh > 0)
-    ok &= check('dPre', dp, dpre_ref, 1e-5)
+    ok &= check('dPre', dp, dpre_ref, 3e-3 if TF32_EPILOGUE else 1e-5)
     # stage 4: gradients from the kernel's own dPre / dOut / hidden
     dw_enc = gflat[:128 * 128].view(128, 128)
     tail = gflat[128 * 128:]
@@ -126,10 +127,10 @@ def case(slab_rows, n_slabs, slab_stride, n_act, seed):
     g3, s3, _, _, _ = fused(xbuf, 128, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval,
                             n_act, debug=False, dpre_out=dpre_hbm)
     torch.cuda.synchronize()
-    ok &= check('dPre written to HBM', dpre_hbm, dp, 2e-6)       # (variant 2 sums the head products in four quarters)
-    ok &= check('small gradients (HBM mode)', g3[128 * 128:], gflat[128 * 128:], 1e-6)
+    ok &= check('dPre written to HBM', dpre_hbm, dp, 1e-2 if TF32_EPILOGUE else 2e-6)       # (variant 2 sums the head products in four quarters)
+    ok &= check('small gradients (HBM mode)', g3[128 * 128:], gflat[128 * 128:], 1e-2 if TF32_EPILOGUE else 1e-6)
     ok &= bool(torch.isnan(g3[:128 * 128]).all())
-    ok &= check('loss statistics (HBM mode)', s3[:6], stats[:6], 1e-7)
+    ok &= check('loss statistics (HBM mode)', s3[:6], stats[:6], 2e-3 if TF32_EPILOGUE else 1e-7)
     # the same launch without the debug dumps must give the same gradients
     g2, s2, _, _, _ = fused(xbuf, 128, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval,
                             n_act, debug=False)
@@ -177,6 +178,8 @@ def main():
         variant = int(sys.argv[sys.argv.index('--variant') + 1])
         _native.check(lib.pb_mlp_update_set_variant(variant))
         print('update kernel variant', variant, flush=True)
+        global TF32_EPILOGUE
+        TF32_EPILOGUE = variant == 2
     ok = True
     for args in ((128, 1, 128, 4, 1), (1000, 1, 1000, 4, 2), (148 * 128 * 2 + 77, 1, 148 * 128 * 2 + 77, 7, 3),
                  (300, 2, 1000, 1, 4), (4096, 4, 16384, 4, 5)):
