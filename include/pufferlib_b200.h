@@ -285,6 +285,8 @@ int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_
 size_t pb_mlp_update_workspace_bytes(void);
 /* 1 = two x layouts per tile (K-major + MN-major TMA loads), 2 = one x layout, x^T formed on the tensor core */
 int pb_mlp_update_set_variant(int32_t variant);
+/* profiling hook (variant 2): SM-clock stamps of tiles 8..11, [grid][18 warps][4][8] int64; NULL switches it off */
+int pb_mlp_update_debug_clock(long long* buf);
 int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
                         const float* w_enc, const float* b_enc, const float* w_heads, const float* b_heads,
                         const int64_t* actions, const float* old_logprobs, const float* advantages, const float* returns,

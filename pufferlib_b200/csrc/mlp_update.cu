@@ -83,6 +83,7 @@ struct FusedParams {
     float* dbg_hidden;         // nullable [m][128]
     float* dbg_dpre;           // nullable [m][128]
     float* dbg_dout;           // nullable [m][8]
+    long long* dbg_clk;        // profiling only: [grid][18 warps][4 tiles][8 events] SM clock stamps of tiles 8..11 (variant 2)
     int skip;                  // profiling only (env PB_MUF_SKIP): bit 0 head FFMAs, 1 loss math, 2 dPre FFMAs, 3 mma.sync + staging,
                                // 4 dPre stores / chunk hand-off, 5 column sums, 6 partner exchange
 };
@@ -774,6 +775,9 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto stamp = [&](int it, int ev) {
+        if (p.dbg_clk && lane == 0 && it >= 8 && it < 12) p.dbg_clk[(((int64_t)blockIdx.x * 18 + warp) * 4 + (it - 8)) * 8 + ev] = clock64();
+    };
 
     // epilogue warp (q, c): TMEM lane quadrant q (tile rows 32q..32q+31), hidden units 32c..32c+31
     float acc_wh[4][2];                  // dW_heads[a = lane>>2][32c + 8nb + 2(lane&3) + {0,1}] (this warp's rows)
@@ -793,7 +797,9 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const int tile = (int)blockIdx.x + it * (int)gridDim.x;
                 const int64_t row0 = (int64_t)(tile / p.tiles_per_slab) * p.slab_stride_rows +
                                      (int64_t)(tile % p.tiles_per_slab) * TILE_M;
+                stamp(it, 0);
                 mbar_wait(xk_empty, (uint32_t)((it & 1) ^ 1));
+                stamp(it, 1);
                 mbar_expect_tx(xk_full, TILE_BYTES);
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(smem + X2_XK + kb * KBLK_BYTES, &map_x, kb * KBLK, (int)row0, xk_full);
             }
@@ -804,8 +810,11 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint32_t g_addr = smem_u32(smem + X2_G), id_addr = smem_u32(smem + X2_ID);
             auto forward = [&](int it) {
                 const int s = it & 1, ph = (it >> 1) & 1;
+                stamp(it, 0);
                 mbar_wait(&h_empty[s], ph ^ 1);
+                stamp(it, 1);
                 mbar_wait(xk_full, (uint32_t)(it & 1));
+                stamp(it, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(s * HID);
 #pragma unroll
@@ -834,6 +843,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
                     mbar_wait(&dp_full[q], (uint32_t)(it & 1));
+                    stamp(it, 3 + q);
                     tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // K = 8 tile rows per MMA
@@ -842,6 +852,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     umma_commit(&dp_empty[q]);
                 }
                 if (it + 1 < n_my) transpose();
+                stamp(it, 7);
             }
             umma_commit(dw_done);
         }
@@ -905,7 +916,9 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const bool dbg_ok = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc < p.slab_rows;
 
             // ---- 1. h -> relu(h + b_enc), TF32-rounded, into the warp's part of the dPre block (K-major: [hidden unit][row])
+            stamp(it, 0);
             mbar_wait(&h_full[s], ph);
+            stamp(it, 1);
             tc_fence_after();
             {
                 float v[32];
@@ -914,6 +927,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&h_empty[s]);                      // the accumulator stage is free already
                 mbar_wait(&dp_empty[q], (uint32_t)((it & 1) ^ 1));            // the dW MMAs of the previous tile have read the block
+                stamp(it, 2);
 #pragma unroll
                 for (int k4 = 0; k4 < 8; ++k4) {
                     const float4 b = be4[k4];
@@ -951,7 +965,9 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     *reinterpret_cast<float2*>(xch + (c * 32 + 16 * mb + g + 8) * 8 + 2 * t) = make_float2(hp[mb][2], hp[mb][3]);
                 }
             }
+            stamp(it, 3);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+            stamp(it, 4);
 
             // ---- 3. the loss row math on the summed head outputs (warp c == 0 of the quadrant, thread = row) -> dOut
             if (c == 0) {
@@ -981,7 +997,9 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 *reinterpret_cast<float4*>(dos + lane * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
                 row = load_row(it + 1);
             }
+            stamp(it, 5);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+            stamp(it, 6);
 
             // ---- 4. dW_heads += dO^T . rh   (A[m = head][k = row] from the dOut tile, B[k = row][n = hidden unit] from rh)
 #pragma unroll
@@ -1042,6 +1060,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dp_full[q]);
+            stamp(it, 7);
             // ---- 6. db_enc: lane n sums hidden unit 32c + n over the warp's 32 rows (the UMMA only reads the block)
             float cs = 0.f;
 #pragma unroll
@@ -1147,6 +1166,7 @@ int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t row
 
 int num_sms() { return pb_num_sms(); }
 
+long long* g_dbg_clk = nullptr;
 int g_update_variant = 1;     // 1 = two x layouts (k_mlp_update_fused), 2 = one x layout + transposing MMA (k_mlp_update_xt)
 
 }  // namespace
@@ -1154,6 +1174,11 @@ int g_update_variant = 1;     // 1 = two x layouts (k_mlp_update_fused), 2 = one
 extern "C" int pb_mlp_update_set_variant(int32_t variant) {
     PB_REQUIRE(variant == 1 || variant == 2, PB_ERR_INVALID, "pb_mlp_update_set_variant: 1 or 2");
     g_update_variant = variant;
+    return PB_OK;
+}
+
+extern "C" int pb_mlp_update_debug_clock(long long* buf) {     // profiling hook: see FusedParams::dbg_clk; nullptr = off
+    g_dbg_clk = buf;
     return PB_OK;
 }
 
@@ -1207,6 +1232,7 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
         const char* sk = getenv("PB_MUF_SKIP");      // profiling only: skip phases of the epilogue (results are then wrong)
         p.skip = sk ? atoi(sk) : 0;
     }
+    p.dbg_clk = g_dbg_clk;
     p.stats = stats8; p.dpre_out = dpre_out; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
     PB_CUDA(cudaMemsetAsync(stats8, 0, 8 * sizeof(double), s));
     PB_CUDA(cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s));
