@@ -885,6 +885,18 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             ga[mb][3] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g + 8]);
         }
         float z0 = 0.f, z1 = 0.f;
+        // addresses inside the warp's part of the dPre block (see g_off), hoisted out of the tile loop
+        uint8_t* st_base[8];                                    // element (hidden unit k, row lane): + k * 128, index k & 7
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_base[j] = mine + ((((lane >> 2) ^ j)) << 4) + ((lane & 3) << 2);
+        uint8_t* ha_base[2];                                    // heads A fragments: hidden unit 8kb + t (+4), row 16mb + g (+8)
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8)
+            ha_base[h8] = mine + t * 128 + ((g & 3) << 2) + ((((g >> 2) ^ (t & 1)) | ((h8 ^ (t >> 1)) << 1)) << 4);
+        uint8_t* wb_base = mine + g * 128 + t * 4;              // dW_heads B fragments: hidden unit 8nb + g, row 8ks + t (+4)
+        uint8_t* mk_base[4];                                    // g^T fragments: hidden unit 16mb + g + 8h, rows 8nb + 2t + {0,1}
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) mk_base[nb] = mine + g * 128 + ((((2 * nb + (t >> 1)) ^ g)) << 4) + ((t & 1) << 3);
 
         // per-row scalars of the warp that evaluates the loss (c == 0): loaded one tile ahead
         struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; };
@@ -937,7 +949,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     v[4 * k4 + 3] = fmaxf(v[4 * k4 + 3] + b.w, 0.f);
                 }
 #pragma unroll
-                for (int k = 0; k < 32; ++k) *reinterpret_cast<uint32_t*>(mine + g_off(k, lane)) = to_tf32(v[k]);
+                for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(st_base[k & 7] + k * 128) = v[k];
                 if (p.dbg_hidden && dbg_ok) {
 #pragma unroll
                     for (int k = 0; k < 32; k += 4)
@@ -955,10 +967,11 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
                         uint32_t a[4];
-                        a[0] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t, 16 * mb + g));
-                        a[1] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t, 16 * mb + g + 8));
-                        a[2] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t + 4, 16 * mb + g));
-                        a[3] = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * kb + t + 4, 16 * mb + g + 8));
+                        // g_off(8kb + t + 4h4, 16mb + g + 8h8): the 16-byte piece index is (gh ^ t0) | ((h8 ^ t1) << 1) | ((mb ^ h4) << 2)
+                        a[0] = *reinterpret_cast<const uint32_t*>(ha_base[0] + kb * 1024 + mb * 64);
+                        a[1] = *reinterpret_cast<const uint32_t*>(ha_base[1] + kb * 1024 + mb * 64);
+                        a[2] = *reinterpret_cast<const uint32_t*>(ha_base[0] + kb * 1024 + 512 + (mb ^ 1) * 64);
+                        a[3] = *reinterpret_cast<const uint32_t*>(ha_base[1] + kb * 1024 + 512 + (mb ^ 1) * 64);
                         mma_tf32_full(hp[mb], a, hb[kb][0], hb[kb][1]);
                     }
                     *reinterpret_cast<float2*>(xch + (c * 32 + 16 * mb + g) * 8 + 2 * t) = make_float2(hp[mb][0], hp[mb][1]);
@@ -1005,12 +1018,12 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
                 uint32_t afr[2];
-                afr[0] = to_tf32(dos[(8 * ks + t) * 8 + g]);
-                afr[1] = to_tf32(dos[(8 * ks + t + 4) * 8 + g]);
+                afr[0] = __float_as_uint(dos[(8 * ks + t) * 8 + g]);
+                afr[1] = __float_as_uint(dos[(8 * ks + t + 4) * 8 + g]);
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * nb + g, 8 * ks + t));
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(mine + g_off(8 * nb + g, 8 * ks + t + 4));
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wb_base + (((2 * ks) ^ g) << 4) + nb * 1024);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wb_base + (((2 * ks + 1) ^ g) << 4) + nb * 1024);
                     mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr, b0, b1);
                 }
             }
@@ -1020,8 +1033,8 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 float gt[2][4][4];
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
-                    const uint32_t b0 = to_tf32(dos[(8 * nb + g) * 8 + t]);
-                    const uint32_t b1 = to_tf32(dos[(8 * nb + g) * 8 + t + 4]);
+                    const uint32_t b0 = __float_as_uint(dos[(8 * nb + g) * 8 + t]);
+                    const uint32_t b1 = __float_as_uint(dos[(8 * nb + g) * 8 + t + 4]);
 #pragma unroll
                     for (int mb = 0; mb < 2; ++mb) {
                         gt[mb][nb][0] = gt[mb][nb][1] = gt[mb][nb][2] = gt[mb][nb][3] = 0.f;
@@ -1035,7 +1048,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            const float2 r2 = *reinterpret_cast<const float2*>(mine + g_off(16 * mb + g + 8 * h, 8 * nb + 2 * t));
+                            const float2 r2 = *reinterpret_cast<const float2*>(mk_base[nb] + (16 * mb + 8 * h) * 128);
                             gt[mb][nb][2 * h] = r2.x > 0.f ? gt[mb][nb][2 * h] : 0.f;
                             gt[mb][nb][2 * h + 1] = r2.y > 0.f ? gt[mb][nb][2 * h + 1] : 0.f;
                         }
@@ -1046,7 +1059,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            *reinterpret_cast<float2*>(mine + g_off(16 * mb + g + 8 * h, 8 * nb + 2 * t)) =
+                            *reinterpret_cast<float2*>(mk_base[nb] + (16 * mb + 8 * h) * 128) =
                                 make_float2(gt[mb][nb][2 * h], gt[mb][nb][2 * h + 1]);
                             if (p.dbg_dpre) {
                                 const int64_t r0 = dbg_row - lane + 8 * nb + 2 * t;        // slab-major row of tile row 32q + 8nb + 2t
