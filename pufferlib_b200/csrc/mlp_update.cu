@@ -677,6 +677,70 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                      : "memory");
 }
 
+// ppo_row with FOUR lanes per row: lane `sub` (0..3) of the row owns outputs sub and sub + 4 (logits below n_act, the value at
+// index n_act); row-wide maxima / sums go through width-4 shuffles.  Same arithmetic as ppo_row, which remains the
+// statement of the math; every lane of the warp must call it (shuffles).  Returns dOut of the two owned outputs.
+__device__ __forceinline__ RowStats ppo_row_sub(float z_lo, float z_hi, int sub, int lane, const FusedParams& p, int act,
+                                                float old_lp, float adv, float ret, float old_v, float& g_lo, float& g_hi) {
+    const unsigned full = 0xffffffffu;
+    const int n = p.n_act;
+    const bool lo_ok = sub < n, hi_ok = sub + 4 < n;
+    float mx = fmaxf(lo_ok ? z_lo : -INFINITY, hi_ok ? z_hi : -INFINITY);
+    mx = fmaxf(mx, __shfl_xor_sync(full, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(full, mx, 2));
+    float sum = (lo_ok ? expf(z_lo - mx) : 0.f) + (hi_ok ? expf(z_hi - mx) : 0.f);
+    sum += __shfl_xor_sync(full, sum, 1);
+    sum += __shfl_xor_sync(full, sum, 2);
+    const float lse = mx + logf(sum);
+    const float nl_lo = z_lo - lse, nl_hi = z_hi - lse;
+    const float pk_lo = lo_ok ? expf(nl_lo) : 0.f, pk_hi = hi_ok ? expf(nl_hi) : 0.f;
+    float ent = -(lo_ok ? pk_lo * nl_lo : 0.f) - (hi_ok ? pk_hi * nl_hi : 0.f);
+    ent += __shfl_xor_sync(full, ent, 1);
+    ent += __shfl_xor_sync(full, ent, 2);
+    const int a = act < 0 ? 0 : (act >= n ? n - 1 : act);
+    const int base = lane & ~3;
+    const float nl_a = __shfl_sync(full, (a >> 2) ? nl_hi : nl_lo, base | (a & 3));
+    const float v_new = __shfl_sync(full, (n >> 2) ? z_hi : z_lo, base | (n & 3));
+    const float logratio = nl_a - old_lp;
+    const float ratio = expf(logratio);
+    const float pg1 = -adv * ratio;
+    const float rc = fminf(fmaxf(ratio, 1.f - p.clip), 1.f + p.clip);
+    const float pg2 = -adv * rc;
+    const float pg = fmaxf(pg1, pg2);
+    const float in_range = (ratio >= 1.f - p.clip && ratio <= 1.f + p.clip) ? 1.f : 0.f;
+    float g_ratio;
+    if (pg1 > pg2) g_ratio = -adv;
+    else if (pg1 < pg2) g_ratio = -adv * in_range;
+    else g_ratio = 0.5f * (-adv) + 0.5f * (-adv * in_range);
+    const float inv_m = 1.0f / (float)p.m;
+    const float g_nlp = g_ratio * ratio * inv_m;
+    const float dv = v_new - ret;
+    float vl, g_v;
+    if (p.clip_vloss) {
+        const float d = v_new - old_v;
+        const float dc = fminf(fmaxf(d, -p.vclip), p.vclip);
+        const float vc = old_v + dc;
+        const float vu = dv * dv, vcl = (vc - ret) * (vc - ret);
+        vl = fmaxf(vu, vcl);
+        const float v_in = (d >= -p.vclip && d <= p.vclip) ? 1.f : 0.f;
+        const float gu = 2.f * dv, gc = 2.f * (vc - ret) * v_in;
+        g_v = vu > vcl ? gu : (vu < vcl ? gc : 0.5f * (gu + gc));
+    } else {
+        vl = dv * dv;
+        g_v = 2.f * dv;
+    }
+    const float gv_out = 0.5f * p.vf_coef * g_v * inv_m;
+    const float g_ent = p.ent_coef * inv_m;
+    g_lo = lo_ok ? g_nlp * ((sub == a ? 1.f : 0.f) - pk_lo) + g_ent * pk_lo * (nl_lo + ent) : 0.f;
+    g_hi = hi_ok ? g_nlp * ((sub + 4 == a ? 1.f : 0.f) - pk_hi) + g_ent * pk_hi * (nl_hi + ent) : 0.f;
+    if (sub == n) g_lo = gv_out;
+    if (sub + 4 == n) g_hi = gv_out;
+    RowStats s;
+    s.pg = pg; s.v = vl; s.ent = ent; s.okl = -logratio; s.kl = (ratio - 1.f) - logratio;
+    s.clipped = fabsf(ratio - 1.f) > p.clip ? 1.f : 0.f;
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Variant 2: ONE x layout.  The tensor core only takes MN-major 32-bit operands in the BASE32B layout, so variant 1 loads
 // every x tile twice (K-major for the forward product, MN-major for dW) and has no shared memory left to overlap anything.
@@ -691,10 +755,12 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
 // TMEM: [0,256) two forward accumulators, [256,384) x^T, [384,512) dW^T (lives across all tiles of the CTA).
 constexpr int X2_THREADS = 576;                          // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int X2_W = 0, X2_XK = TILE_BYTES, X2_G = 2 * TILE_BYTES;     // W_enc | x tile | 4 dPre blocks of 16 KiB
-constexpr int X2_XCH = 3 * TILE_BYTES;                   // [4 q][4 c][32 rows][8 heads] partial head sums
-constexpr int X2_ID = X2_XCH + 16384;                    // sliding identity: 2 strips of 32 core matrices
-constexpr int X2_DO = X2_ID + 8192;                      // [4 q][32 rows][8 heads] dOut of the tile
-constexpr int X2_BE = X2_DO + 4096;                      // b_enc [128]
+constexpr int X2_XCH = 3 * TILE_BYTES;                   // [4 q][4 c][32 rows][10]: partial head sums (8 used; 10 = bank spread)
+constexpr int X2_XCH_ROW = 10, X2_XCH_Q = 4 * 32 * X2_XCH_ROW;
+constexpr int X2_ID = X2_XCH + 4 * X2_XCH_Q * 4;         // sliding identity: 2 strips of 32 core matrices
+constexpr int X2_DO = X2_ID + 8192;                      // [4 q][32 rows][9]: dOut of the tile (8 used)
+constexpr int X2_DO_ROW = 9, X2_DO_Q = 320;
+constexpr int X2_BE = X2_DO + 4 * X2_DO_Q * 4;           // b_enc [128]
 constexpr int X2_BAR = X2_BE + 512;
 constexpr int X2_TOTAL = X2_BAR + 256;
 constexpr int X2_TMEM_XT = 256, X2_TMEM_DW = 384;
@@ -781,13 +847,11 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
     // epilogue warp (q, c): TMEM lane quadrant q (tile rows 32q..32q+31), hidden units 32c..32c+31
     float acc_wh[4][2];                  // dW_heads[a = lane>>2][32c + 8nb + 2(lane&3) + {0,1}] (this warp's rows)
-    float acc_benc = 0.f;                // db_enc[32c + lane]
-    float acc_bh[NO];                    // db_heads (c == 0: the warp that evaluates the loss)
     float st[6] = {0, 0, 0, 0, 0, 0};    // per-thread statistics of <= 28 tiles: fp32 here, fp64 across threads
+    float acc_be[4] = {0.f, 0.f, 0.f, 0.f};   // db_enc[32c + 8nb + (lane >> 2)], this lane's 8 rows of every tile
+    float acc_bh2[2] = {0.f, 0.f};       // db_heads[lane & 3], [(lane & 3) + 4] over this lane's rows
 #pragma unroll
     for (int nb = 0; nb < 4; ++nb) acc_wh[nb][0] = acc_wh[nb][1] = 0.f;
-#pragma unroll
-    for (int k = 0; k < NO; ++k) acc_bh[k] = 0.f;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -857,25 +921,27 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             umma_commit(dw_done);
         }
     } else {
-        // ================= epilogue: all per-element products on the warp-level tensor core path (mma.sync, TF32 operands,
-        // fp32 accumulation -- the precision class of torch.set_float32_matmul_precision('high'), clean_pufferl.py:22).
-        // Thread = row only for the TMEM read, the ReLU and the loss; everything else works on mma fragments of the warp's
-        // [32 rows][32 hidden units] block staged in its part of the dPre block.
+        // ================= epilogue: all per-element products on the warp-level tensor core path (mma.sync, TF32 operands
+        // = the raw fp32 bits, low mantissa bits ignored like the UMMA products; fp32 accumulation -- the precision class of
+        // torch.set_float32_matmul_precision('high'), clean_pufferl.py:22).  Thread = row only for the TMEM read and the ReLU;
+        // everything else works on mma fragments of the warp's [32 rows][32 hidden units] block staged in its part of the
+        // dPre block.  The m / n / k indices of the three products are PERMUTED so that every fragment a lane needs is a run
+        // of 4 or 8 consecutive rows of one hidden unit (one or two 16-byte pieces of the K-major block: LDS.128 / STS.128),
+        // and so that the relu(h) fragments of the dW_heads product sit exactly where the g^T accumulators need their mask.
         const int q = warp & 3, c = (warp - 2) >> 2;
         const int g = lane >> 2, t = lane & 3;
-        const int rloc = 32 * q + lane;
         uint8_t* mine = smem + X2_G + q * KBLK_BYTES + 32 * c * 128;   // hidden units 32c..32c+31 x the quadrant's 32 rows
-        float* xch = reinterpret_cast<float*>(smem + X2_XCH) + q * 1024;                  // [4 c][32 rows][8 heads]
-        float* dos = reinterpret_cast<float*>(smem + X2_DO) + q * 256;                    // [32 rows][8 heads]
+        float* xch = reinterpret_cast<float*>(smem + X2_XCH) + q * X2_XCH_Q;              // [4 c][32 rows][10]
+        float* dos = reinterpret_cast<float*>(smem + X2_DO) + q * X2_DO_Q;                // [32 rows][9]
         const float4* be4 = reinterpret_cast<const float4*>(smem + X2_BE) + 8 * c;
         // W_heads fragments of this column quarter (TF32), resident in registers:
-        //   heads product  out[row][a] = sum_j rh[row][j] W[a][j]:   B[k = j][n = a]
-        //   g^T product    g[j][row]   = sum_a W[a][j] dO[row][a]:   A[m = j][k = a]
+        //   heads   out[row][a] = sum_j rh[row][j] W[a][j]:  B[k][n = a], k = t + 4h <-> hidden unit 8kb + 2t + h
+        //   g^T     g[j][row]   = sum_a W[a][j] dO[row][a]:  A[m][k = a], m = g + 8h <-> hidden unit 16mb + 8h + g
         uint32_t hb[4][2], ga[2][4];
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-            hb[kb][0] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + t]);
-            hb[kb][1] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + t + 4]);
+            hb[kb][0] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + 2 * t]);
+            hb[kb][1] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + 2 * t + 1]);
         }
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
@@ -886,28 +952,28 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         float z0 = 0.f, z1 = 0.f;
         // addresses inside the warp's part of the dPre block (see g_off), hoisted out of the tile loop
-        uint8_t* st_base[8];                                    // element (hidden unit k, row lane): + k * 128, index k & 7
+        uint8_t* st_base[8];                                    // thread = row: element (hidden unit k, row lane) at + k * 128, index k & 7
 #pragma unroll
         for (int j = 0; j < 8; ++j) st_base[j] = mine + ((((lane >> 2) ^ j)) << 4) + ((lane & 3) << 2);
-        uint8_t* ha_base[2];                                    // heads A fragments: hidden unit 8kb + t (+4), row 16mb + g (+8)
+        uint8_t* ha_base[2];                                    // heads A: hidden unit 8kb + 2t + h, rows 4g..4g+3 (one piece)
 #pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8)
-            ha_base[h8] = mine + t * 128 + ((g & 3) << 2) + ((((g >> 2) ^ (t & 1)) | ((h8 ^ (t >> 1)) << 1)) << 4);
-        uint8_t* wb_base = mine + g * 128 + t * 4;              // dW_heads B fragments: hidden unit 8nb + g, row 8ks + t (+4)
-        uint8_t* mk_base[4];                                    // g^T fragments: hidden unit 16mb + g + 8h, rows 8nb + 2t + {0,1}
+        for (int h = 0; h < 2; ++h) ha_base[h] = mine + (2 * t + h) * 128 + ((g ^ (2 * t + h)) << 4);
+        uint8_t* wb_base[2];                                    // dW_heads B / g^T C: hidden unit 8nb + g, rows 8t..8t+3 | 8t+4..8t+7
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) mk_base[nb] = mine + g * 128 + ((((2 * nb + (t >> 1)) ^ g)) << 4) + ((t & 1) << 3);
+        for (int e = 0; e < 2; ++e) wb_base[e] = mine + g * 128 + ((((2 * t + e) ^ g)) << 4);
 
-        // per-row scalars of the warp that evaluates the loss (c == 0): loaded one tile ahead
+        // the loss: warp c evaluates rows 8c..8c+7 of the quadrant, four lanes per row (ppo_row_sub)
+        const int lr = 8 * c + (lane >> 2), sub = lane & 3;
+        const float bh_lo = c_bh[sub], bh_hi = c_bh[sub + 4];
         struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; };
         const float adv_mean = p.adv_norm ? p.adv_norm[0] : 0.f, adv_rstd = p.adv_norm ? p.adv_norm[1] : 1.f;
         auto load_row = [&](int it) {
             RowIn r;
             r.act = 0; r.old_lp = 0.f; r.adv = 0.f; r.ret = 0.f; r.old_v = 0.f; r.valid = false;
-            if (c != 0 || it >= n_my) return r;
+            if (it >= n_my) return r;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
             const int slab = tile / p.tiles_per_slab;
-            const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
+            const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q + lr;
             r.valid = lrow < p.slab_rows;
             const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;     // position in the per-row arrays
             if (r.valid) {
@@ -923,11 +989,11 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int it = 0; it < n_my; ++it) {
             const int s = it & 1, ph = (it >> 1) & 1;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            // slab-major position of this thread's row (debug dumps)
-            const int64_t dbg_row = (int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc;
-            const bool dbg_ok = (int64_t)(tile % p.tiles_per_slab) * TILE_M + rloc < p.slab_rows;
+            // slab-major position of tile row 0 of this quadrant (debug dumps), rows of the slab left in the tile
+            const int64_t dbg_row0 = (int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q;
+            const int64_t rows_left = p.slab_rows - ((int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q);
 
-            // ---- 1. h -> relu(h + b_enc), TF32-rounded, into the warp's part of the dPre block (K-major: [hidden unit][row])
+            // ---- 1. h -> relu(h + b_enc) into the warp's part of the dPre block (K-major: [hidden unit][row])
             stamp(it, 0);
             mbar_wait(&h_full[s], ph);
             stamp(it, 1);
@@ -950,186 +1016,193 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 }
 #pragma unroll
                 for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(st_base[k & 7] + k * 128) = v[k];
-                if (p.dbg_hidden && dbg_ok) {
+                if (p.dbg_hidden && lane < rows_left) {
 #pragma unroll
                     for (int k = 0; k < 32; k += 4)
-                        *reinterpret_cast<float4*>(p.dbg_hidden + dbg_row * HID + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+                        *reinterpret_cast<float4*>(p.dbg_hidden + (dbg_row0 + lane) * HID + 32 * c + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
                 }
             }
             __syncwarp();
 
-            // ---- 2. this quarter's share of the head products: out[32 rows][8] = rh[32][32] . W^T
+            // ---- 2. this quarter's share of the head products.  m = g + 8h of block mb <-> row 4g + 2mb + h
             {
                 float hp[2][4];
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
-                    hp[mb][0] = hp[mb][1] = hp[mb][2] = hp[mb][3] = 0.f;
+                for (int mb = 0; mb < 2; ++mb) hp[mb][0] = hp[mb][1] = hp[mb][2] = hp[mb][3] = 0.f;
 #pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) {
-                        uint32_t a[4];
-                        // g_off(8kb + t + 4h4, 16mb + g + 8h8): the 16-byte piece index is (gh ^ t0) | ((h8 ^ t1) << 1) | ((mb ^ h4) << 2)
-                        a[0] = *reinterpret_cast<const uint32_t*>(ha_base[0] + kb * 1024 + mb * 64);
-                        a[1] = *reinterpret_cast<const uint32_t*>(ha_base[1] + kb * 1024 + mb * 64);
-                        a[2] = *reinterpret_cast<const uint32_t*>(ha_base[0] + kb * 1024 + 512 + (mb ^ 1) * 64);
-                        a[3] = *reinterpret_cast<const uint32_t*>(ha_base[1] + kb * 1024 + 512 + (mb ^ 1) * 64);
-                        mma_tf32_full(hp[mb], a, hb[kb][0], hb[kb][1]);
-                    }
-                    *reinterpret_cast<float2*>(xch + (c * 32 + 16 * mb + g) * 8 + 2 * t) = make_float2(hp[mb][0], hp[mb][1]);
-                    *reinterpret_cast<float2*>(xch + (c * 32 + 16 * mb + g + 8) * 8 + 2 * t) = make_float2(hp[mb][2], hp[mb][3]);
+                for (int kb = 0; kb < 4; ++kb) {
+                    const float4 lo = *reinterpret_cast<const float4*>(ha_base[0] + kb * 1024);   // hidden unit 8kb + 2t
+                    const float4 hi = *reinterpret_cast<const float4*>(ha_base[1] + kb * 1024);   // hidden unit 8kb + 2t + 1
+                    const uint32_t a0[4] = {__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(hi.x), __float_as_uint(hi.y)};
+                    const uint32_t a1[4] = {__float_as_uint(lo.z), __float_as_uint(lo.w), __float_as_uint(hi.z), __float_as_uint(hi.w)};
+                    mma_tf32_full(hp[0], a0, hb[kb][0], hb[kb][1]);
+                    mma_tf32_full(hp[1], a1, hb[kb][0], hb[kb][1]);
+                }
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    *reinterpret_cast<float2*>(xch + (c * 32 + 4 * g + 2 * mb) * X2_XCH_ROW + 2 * t) = make_float2(hp[mb][0], hp[mb][1]);
+                    *reinterpret_cast<float2*>(xch + (c * 32 + 4 * g + 2 * mb + 1) * X2_XCH_ROW + 2 * t) = make_float2(hp[mb][2], hp[mb][3]);
                 }
             }
             stamp(it, 3);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
             stamp(it, 4);
 
-            // ---- 3. the loss row math on the summed head outputs (warp c == 0 of the quadrant, thread = row) -> dOut
-            if (c == 0) {
-                float out[NO], dO[NO];
+            // ---- 3. the loss row math on the summed head outputs -> dOut tile of the quadrant
+            {
+                float z_lo = bh_lo, z_hi = bh_hi;
 #pragma unroll
-                for (int a = 0; a < NO; ++a) { out[a] = c_bh[a]; dO[a] = 0.f; }
-#pragma unroll
-                for (int cq = 0; cq < 4; ++cq) {
-                    const float4 lo = *reinterpret_cast<const float4*>(xch + (cq * 32 + lane) * 8);
-                    const float4 hi = *reinterpret_cast<const float4*>(xch + (cq * 32 + lane) * 8 + 4);
-                    out[0] += lo.x; out[1] += lo.y; out[2] += lo.z; out[3] += lo.w;
-                    out[4] += hi.x; out[5] += hi.y; out[6] += hi.z; out[7] += hi.w;
+                for (int cq = 0; cq < 4; ++cq) {                                    // fixed order
+                    z_lo += xch[(cq * 32 + lr) * X2_XCH_ROW + sub];
+                    z_hi += xch[(cq * 32 + lr) * X2_XCH_ROW + sub + 4];
                 }
-                if (row.valid) {
-                    const float ret = p.returns ? row.ret : row.adv + row.old_v;      // returns = raw advantages + old values (:476-481)
-                    const float adv = (row.adv - adv_mean) * adv_rstd;
-                    const RowStats rs = ppo_row(out, p, row.act, row.old_lp, adv, ret, row.old_v, dO);
+                const float ret = p.returns ? row.ret : row.adv + row.old_v;       // returns = raw advantages + old values (:476-481)
+                const float adv = (row.adv - adv_mean) * adv_rstd;
+                float g_lo, g_hi;
+                const RowStats rs = ppo_row_sub(z_lo, z_hi, sub, lane, p, row.act, row.old_lp, adv, ret, row.old_v, g_lo, g_hi);
+                if (!row.valid) g_lo = g_hi = 0.f;
+                if (row.valid && sub == 0) {
                     st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
-                    if (p.dbg_dout) {
-                        *reinterpret_cast<float4*>(p.dbg_dout + dbg_row * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-                        *reinterpret_cast<float4*>(p.dbg_dout + dbg_row * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
-                    }
                 }
-#pragma unroll
-                for (int a = 0; a < NO; ++a) acc_bh[a] += dO[a];
-                *reinterpret_cast<float4*>(dos + lane * 8) = make_float4(dO[0], dO[1], dO[2], dO[3]);
-                *reinterpret_cast<float4*>(dos + lane * 8 + 4) = make_float4(dO[4], dO[5], dO[6], dO[7]);
+                acc_bh2[0] += g_lo;
+                acc_bh2[1] += g_hi;
+                dos[lr * X2_DO_ROW + sub] = g_lo;
+                dos[lr * X2_DO_ROW + sub + 4] = g_hi;
+                if (p.dbg_dout && row.valid) {
+                    p.dbg_dout[(dbg_row0 + lr) * 8 + sub] = g_lo;
+                    p.dbg_dout[(dbg_row0 + lr) * 8 + sub + 4] = g_hi;
+                }
                 row = load_row(it + 1);
             }
             stamp(it, 5);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
             stamp(it, 6);
 
-            // ---- 4. dW_heads += dO^T . rh   (A[m = head][k = row] from the dOut tile, B[k = row][n = hidden unit] from rh)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t afr[2];
-                afr[0] = __float_as_uint(dos[(8 * ks + t) * 8 + g]);
-                afr[1] = __float_as_uint(dos[(8 * ks + t + 4) * 8 + g]);
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(wb_base + (((2 * ks) ^ g) << 4) + nb * 1024);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(wb_base + (((2 * ks + 1) ^ g) << 4) + nb * 1024);
-                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr, b0, b1);
-                }
-            }
-
-            // ---- 5. g^T[hidden unit][row] = W^T . dO^T, masked by rh > 0 -> dPre, in place over rh
+            // ---- 4. g^T[hidden unit][row] = W^T . dO^T        n = 2t' + j of block nb' <-> row 8t' + 2nb' + j
+            //         dW_heads += dO^T . rh                      k = t + 4j of block ks  <-> row 8t + 2ks + j
+            //      the rh fragments of the second product are the mask of the first one's accumulators
             {
                 float gt[2][4][4];
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
-                    const uint32_t b0 = __float_as_uint(dos[(8 * nb + g) * 8 + t]);
-                    const uint32_t b1 = __float_as_uint(dos[(8 * nb + g) * 8 + t + 4]);
+                    const int rn = 8 * (g >> 1) + 2 * nb + (g & 1);
+                    const uint32_t b0 = __float_as_uint(dos[rn * X2_DO_ROW + t]);
+                    const uint32_t b1 = __float_as_uint(dos[rn * X2_DO_ROW + t + 4]);
 #pragma unroll
                     for (int mb = 0; mb < 2; ++mb) {
                         gt[mb][nb][0] = gt[mb][nb][1] = gt[mb][nb][2] = gt[mb][nb][3] = 0.f;
                         mma_tf32_full(gt[mb][nb], ga[mb], b0, b1);
                     }
                 }
-                // c0 c1: hidden unit 16mb + g, rows 8nb + 2t + {0,1};  c2 c3: hidden unit 16mb + g + 8, the same rows
+                uint32_t afr[4][2];
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb)
+                for (int ks = 0; ks < 4; ++ks) {
+                    afr[ks][0] = __float_as_uint(dos[(8 * t + 2 * ks) * X2_DO_ROW + g]);
+                    afr[ks][1] = __float_as_uint(dos[(8 * t + 2 * ks + 1) * X2_DO_ROW + g]);
+                }
 #pragma unroll
-                    for (int nb = 0; nb < 4; ++nb)
+                for (int nb = 0; nb < 4; ++nb) {                 // hidden unit 8nb + g = 16mb + 8h + g
+                    const int mb = nb >> 1, h = nb & 1;
+                    const float4 lo = *reinterpret_cast<const float4*>(wb_base[0] + nb * 1024);   // rows 8t .. 8t+3
+                    const float4 hi = *reinterpret_cast<const float4*>(wb_base[1] + nb * 1024);   // rows 8t+4 .. 8t+7
+                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[0], __float_as_uint(lo.x), __float_as_uint(lo.y));
+                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[1], __float_as_uint(lo.z), __float_as_uint(lo.w));
+                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[2], __float_as_uint(hi.x), __float_as_uint(hi.y));
+                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[3], __float_as_uint(hi.z), __float_as_uint(hi.w));
+                    gt[mb][0][2 * h] = lo.x > 0.f ? gt[mb][0][2 * h] : 0.f;
+                    gt[mb][0][2 * h + 1] = lo.y > 0.f ? gt[mb][0][2 * h + 1] : 0.f;
+                    gt[mb][1][2 * h] = lo.z > 0.f ? gt[mb][1][2 * h] : 0.f;
+                    gt[mb][1][2 * h + 1] = lo.w > 0.f ? gt[mb][1][2 * h + 1] : 0.f;
+                    gt[mb][2][2 * h] = hi.x > 0.f ? gt[mb][2][2 * h] : 0.f;
+                    gt[mb][2][2 * h + 1] = hi.y > 0.f ? gt[mb][2][2 * h + 1] : 0.f;
+                    gt[mb][3][2 * h] = hi.z > 0.f ? gt[mb][3][2 * h] : 0.f;
+                    gt[mb][3][2 * h + 1] = hi.w > 0.f ? gt[mb][3][2 * h + 1] : 0.f;
+                    acc_be[nb] += ((gt[mb][0][2 * h] + gt[mb][0][2 * h + 1]) + (gt[mb][1][2 * h] + gt[mb][1][2 * h + 1])) +
+                                  ((gt[mb][2][2 * h] + gt[mb][2][2 * h + 1]) + (gt[mb][3][2 * h] + gt[mb][3][2 * h + 1]));
+                }
+                __syncwarp();        // every lane has taken its rh fragments before dPre replaces them
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const float2 r2 = *reinterpret_cast<const float2*>(mk_base[nb] + (16 * mb + 8 * h) * 128);
-                            gt[mb][nb][2 * h] = r2.x > 0.f ? gt[mb][nb][2 * h] : 0.f;
-                            gt[mb][nb][2 * h + 1] = r2.y > 0.f ? gt[mb][nb][2 * h + 1] : 0.f;
-                        }
-                __syncwarp();        // every lane has taken its rh fragments (steps 4 and 5) before dPre replaces them
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int mb = nb >> 1, h = nb & 1;
+                    *reinterpret_cast<float4*>(wb_base[0] + nb * 1024) =
+                        make_float4(gt[mb][0][2 * h], gt[mb][0][2 * h + 1], gt[mb][1][2 * h], gt[mb][1][2 * h + 1]);
+                    *reinterpret_cast<float4*>(wb_base[1] + nb * 1024) =
+                        make_float4(gt[mb][2][2 * h], gt[mb][2][2 * h + 1], gt[mb][3][2 * h], gt[mb][3][2 * h + 1]);
+                    if (p.dbg_dpre) {
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb)
-#pragma unroll
-                    for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            *reinterpret_cast<float2*>(mk_base[nb] + (16 * mb + 8 * h) * 128) =
-                                make_float2(gt[mb][nb][2 * h], gt[mb][nb][2 * h + 1]);
-                            if (p.dbg_dpre) {
-                                const int64_t r0 = dbg_row - lane + 8 * nb + 2 * t;        // slab-major row of tile row 32q + 8nb + 2t
-                                const bool ok0 = (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q + 8 * nb + 2 * t < p.slab_rows;
-                                const bool ok1 = (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q + 8 * nb + 2 * t + 1 < p.slab_rows;
-                                if (ok0) p.dbg_dpre[r0 * HID + 32 * c + 16 * mb + g + 8 * h] = gt[mb][nb][2 * h];
-                                if (ok1) p.dbg_dpre[(r0 + 1) * HID + 32 * c + 16 * mb + g + 8 * h] = gt[mb][nb][2 * h + 1];
-                            }
-                        }
+                        for (int r8 = 0; r8 < 8; ++r8)
+                            if (8 * t + r8 < rows_left)
+                                p.dbg_dpre[(dbg_row0 + 8 * t + r8) * HID + 32 * c + 8 * nb + g] = gt[mb][r8 >> 1][2 * h + (r8 & 1)];
+                    }
+                }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dp_full[q]);
             stamp(it, 7);
-            // ---- 6. db_enc: lane n sums hidden unit 32c + n over the warp's 32 rows (the UMMA only reads the block)
-            float cs = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 x4 = *reinterpret_cast<const float4*>(mine + lane * 128 + ((j ^ (lane & 7)) << 4));
-                cs += (x4.x + x4.y) + (x4.z + x4.w);
-            }
-            acc_benc += cs;
         }
         // ---- the dW^T accumulator: TMEM lane = feature, column = hidden unit
         mbar_wait(dw_done, 0);
         tc_fence_after();
         {
             float v[32];
-            float* pd = p.part_dw + ((int64_t)blockIdx.x * FEAT + rloc) * HID + 32 * c;
+            float* pd = p.part_dw + ((int64_t)blockIdx.x * FEAT + 32 * q + lane) * HID + 32 * c;
             tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(X2_TMEM_DW + 32 * c), v);
 #pragma unroll
             for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(pd + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
         }
-        if (c == 0) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                double x = (double)st[k];
+        for (int k = 0; k < 6; ++k) {          // statistics: the sub == 0 lanes hold this warp's rows
+            double x = (double)st[k];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-                if (lane == 0) atomicAdd(p.stats + k, x);
-            }
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            if (lane == 0) atomicAdd(p.stats + k, x);
         }
+        // db_enc: the four lanes of a hidden unit (t = 0..3) hold its 4 x 8 rows; db_heads: the eight lanes with the same sub
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            acc_be[nb] += __shfl_xor_sync(0xffffffffu, acc_be[nb], 1);
+            acc_be[nb] += __shfl_xor_sync(0xffffffffu, acc_be[nb], 2);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) acc_bh2[j] += __shfl_xor_sync(0xffffffffu, acc_bh2[j], off);
     }
 
     // ================= CTA reduction of the small gradients =================
     tc_fence_before();
-    __syncthreads();
-    float* red = reinterpret_cast<float*>(smem + X2_XK);           // [4 quadrants][TAIL] scratch in the idle x tile
+    __syncthreads();                           // every role is done: all MMAs retired, the x tile is scratch now
     if (warp >= 2) {
         const int q = warp & 3, c = (warp - 2) >> 2, g = lane >> 2, t = lane & 3;
-        float* mine = red + q * TAIL;
+        float* red = reinterpret_cast<float*>(smem + X2_XK);
+        float* mine_r = red + q * TAIL;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
-            mine[g * HID + 32 * c + 8 * nb + 2 * t] = acc_wh[nb][0];
-            mine[g * HID + 32 * c + 8 * nb + 2 * t + 1] = acc_wh[nb][1];
+            mine_r[g * HID + 32 * c + 8 * nb + 2 * t] = acc_wh[nb][0];
+            mine_r[g * HID + 32 * c + 8 * nb + 2 * t + 1] = acc_wh[nb][1];
+            if (t == 0) mine_r[NO * HID + 32 * c + 8 * nb + g] = acc_be[nb];
         }
-        mine[NO * HID + 32 * c + lane] = acc_benc;
-        if (c == 0) {
-#pragma unroll
-            for (int k = 0; k < NO; ++k) {
-                float x = acc_bh[k];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-                if (lane == 0) mine[NO * HID + HID + k] = x;
-            }
+        if (lane < 4) {                        // db_heads partial of this warp's rows: [16 warps][8] behind the four TAIL rows
+            red[4 * TAIL + (warp - 2) * NO + lane] = acc_bh2[0];
+            red[4 * TAIL + (warp - 2) * NO + lane + 4] = acc_bh2[1];
         }
     }
     __syncthreads();
-    float* pt = p.part_tail + (int64_t)blockIdx.x * TAIL;
-    for (int j = threadIdx.x; j < TAIL; j += X2_THREADS) pt[j] = red[j] + red[TAIL + j] + red[2 * TAIL + j] + red[3 * TAIL + j];
+    {
+        const float* red = reinterpret_cast<const float*>(smem + X2_XK);   // [4 quadrants][TAIL] | [16 warps][8] db_heads partials
+        float* pt = p.part_tail + (int64_t)blockIdx.x * TAIL;
+        for (int j = threadIdx.x; j < TAIL; j += X2_THREADS) {
+            float v;
+            if (j < NO * HID + HID) {
+                v = red[j] + red[TAIL + j] + red[2 * TAIL + j] + red[3 * TAIL + j];
+            } else {
+                v = 0.f;
+                for (int w = 0; w < 16; ++w) v += red[4 * TAIL + w * NO + (j - NO * HID - HID)];
+            }
+            pt[j] = v;
+        }
+    }
     if (warp == 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");

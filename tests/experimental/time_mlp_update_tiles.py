@@ -47,7 +47,7 @@ for cta in (0, 73, 147):
 per = c[:, 2:, 1:, 0] - c[:, 2:, :-1, 0]
 print('mean tile period (clocks) over all CTAs / epilogue warps:', per.mean(), ' min', per.min(), ' max', per.max())
 seg = np.diff(c[:, 2:, :, :], axis=-1)
-names = ['wait h_full', 'tmem ld + wait dp_empty', 'relu + stage + heads mma', 'bar 1', 'loss (c==0) / idle', 'bar 2', 'dW_heads + g^T + mask + store']
+names = ['wait h_full', 'tmem ld + wait dp_empty', 'relu + stage + heads mma', 'bar 1', 'loss (4 lanes per row)', 'bar 2', 'g^T + dW_heads + mask + store']
 for i, n in enumerate(names):
     print(f'{n:34s} mean {seg[..., i].mean():8.0f}   c==0 warps {seg[:, [2, 3, 0, 1], :, i].mean():8.0f}   others {seg[:, 4:, :, i].mean():8.0f}')
 print('tail: arrive -> next tile enter', (c[:, 2:, 1:, 0] - c[:, 2:, :-1, 7]).mean())
