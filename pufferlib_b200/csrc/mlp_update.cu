@@ -788,7 +788,7 @@ __device__ __forceinline__ void mma_tf32_full(float (&c)[4], const uint32_t (&a)
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int REGS>
+template <int REGS, bool CLK>
 __global__ void __maxnreg__(REGS)
 k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -842,16 +842,16 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
     const int n_my = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     auto stamp = [&](int it, int ev) {
-        if (p.dbg_clk && lane == 0 && it >= 8 && it < 12) p.dbg_clk[(((int64_t)blockIdx.x * 18 + warp) * 4 + (it - 8)) * 8 + ev] = clock64();
+        if (CLK && p.dbg_clk && lane == 0 && it >= 8 && it < 12) p.dbg_clk[(((int64_t)blockIdx.x * 18 + warp) * 4 + (it - 8)) * 8 + ev] = clock64();
     };
 
     // epilogue warp (q, c): TMEM lane quadrant q (tile rows 32q..32q+31), hidden units 32c..32c+31
-    float acc_wh[4][2];                  // dW_heads[a = lane>>2][32c + 8nb + 2(lane&3) + {0,1}] (this warp's rows)
+    float acc_wh[2][4];                  // dW_heads[head 2t + (i & 1)][32c + 16mb + 8(i >> 1) + g] (this warp's rows)
     float st[6] = {0, 0, 0, 0, 0, 0};    // per-thread statistics of <= 28 tiles: fp32 here, fp64 across threads
     float acc_be[4] = {0.f, 0.f, 0.f, 0.f};   // db_enc[32c + 8nb + (lane >> 2)], this lane's 8 rows of every tile
     float acc_bh2[2] = {0.f, 0.f};       // db_heads[lane & 3], [(lane & 3) + 4] over this lane's rows
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) acc_wh[nb][0] = acc_wh[nb][1] = 0.f;
+    for (int mb = 0; mb < 2; ++mb) acc_wh[mb][0] = acc_wh[mb][1] = acc_wh[mb][2] = acc_wh[mb][3] = 0.f;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -950,7 +950,6 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             ga[mb][2] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g]);
             ga[mb][3] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g + 8]);
         }
-        float z0 = 0.f, z1 = 0.f;
         // addresses inside the warp's part of the dPre block (see g_off), hoisted out of the tile loop
         uint8_t* st_base[8];                                    // thread = row: element (hidden unit k, row lane) at + k * 128, index k & 7
 #pragma unroll
@@ -965,33 +964,41 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // the loss: warp c evaluates rows 8c..8c+7 of the quadrant, four lanes per row (ppo_row_sub)
         const int lr = 8 * c + (lane >> 2), sub = lane & 3;
         const float bh_lo = c_bh[sub], bh_hi = c_bh[sub + 4];
+        // per-row scalars of the loss rows, loaded ONE TILE AHEAD with volatile loads issued right after the second barrier
+        // (plain loads get sunk to their first use by the compiler, which puts their HBM latency back on the critical path)
         struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; };
         const float adv_mean = p.adv_norm ? p.adv_norm[0] : 0.f, adv_rstd = p.adv_norm ? p.adv_norm[1] : 1.f;
+        const bool need_old_v = p.clip_vloss || !p.returns;
+        auto ldg_f32 = [](const float* ptr) { float v; asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(ptr)); return v; };
+        auto ldg_s64 = [](const int64_t* ptr) { long long v; asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(ptr)); return v; };
         auto load_row = [&](int it) {
             RowIn r;
             r.act = 0; r.old_lp = 0.f; r.adv = 0.f; r.ret = 0.f; r.old_v = 0.f; r.valid = false;
             if (it >= n_my) return r;
             const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            const int slab = tile / p.tiles_per_slab;
-            const int64_t lrow = (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q + lr;
+            const int slab = tile / p.tiles_per_slab, tis = tile - slab * p.tiles_per_slab;
+            const int64_t lrow = (int64_t)tis * TILE_M + 32 * q + lr;
             r.valid = lrow < p.slab_rows;
             const int64_t ri = (int64_t)slab * p.row_slab_stride + lrow;     // position in the per-row arrays
             if (r.valid) {
-                r.act = (int)p.actions[ri];
-                r.old_lp = p.old_logprobs[ri];
-                r.adv = p.adv[ri];
-                r.old_v = (p.clip_vloss || !p.returns) ? p.old_values[ri] : 0.f;
-                r.ret = p.returns ? p.returns[ri] : 0.f;
+                r.act = (int)ldg_s64(p.actions + ri);
+                r.old_lp = ldg_f32(p.old_logprobs + ri);
+                r.adv = ldg_f32(p.adv + ri);
+                if (need_old_v) r.old_v = ldg_f32(p.old_values + ri);
+                if (p.returns) r.ret = ldg_f32(p.returns + ri);
             }
             return r;
         };
         RowIn row = load_row(0);
         for (int it = 0; it < n_my; ++it) {
             const int s = it & 1, ph = (it >> 1) & 1;
-            const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-            // slab-major position of tile row 0 of this quadrant (debug dumps), rows of the slab left in the tile
-            const int64_t dbg_row0 = (int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q;
-            const int64_t rows_left = p.slab_rows - ((int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q);
+            // debug dumps only: slab-major position of tile row 0 of this quadrant, rows of the slab left in the tile
+            int64_t dbg_row0 = 0, rows_left = 32;
+            if (p.dbg_hidden || p.dbg_dout || p.dbg_dpre) {
+                const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+                dbg_row0 = (int64_t)(tile / p.tiles_per_slab) * p.slab_rows + (int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q;
+                rows_left = p.slab_rows - ((int64_t)(tile % p.tiles_per_slab) * TILE_M + 32 * q);
+            }
 
             // ---- 1. h -> relu(h + b_enc) into the warp's part of the dPre block (K-major: [hidden unit][row])
             stamp(it, 0);
@@ -1072,11 +1079,11 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     p.dbg_dout[(dbg_row0 + lr) * 8 + sub] = g_lo;
                     p.dbg_dout[(dbg_row0 + lr) * 8 + sub + 4] = g_hi;
                 }
-                row = load_row(it + 1);
             }
             stamp(it, 5);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
             stamp(it, 6);
+            row = load_row(it + 1);
 
             // ---- 4. g^T[hidden unit][row] = W^T . dO^T        n = 2t' + j of block nb' <-> row 8t' + 2nb' + j
             //         dW_heads += dO^T . rh                      k = t + 4j of block ks  <-> row 8t + 2ks + j
@@ -1094,31 +1101,42 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         mma_tf32_full(gt[mb][nb], ga[mb], b0, b1);
                     }
                 }
-                uint32_t afr[4][2];
+                uint32_t bfr[4][2];                              // dO as B[k = row][n = head]: rows 8t + 2ks + {0,1}, head g
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
-                    afr[ks][0] = __float_as_uint(dos[(8 * t + 2 * ks) * X2_DO_ROW + g]);
-                    afr[ks][1] = __float_as_uint(dos[(8 * t + 2 * ks + 1) * X2_DO_ROW + g]);
+                    bfr[ks][0] = __float_as_uint(dos[(8 * t + 2 * ks) * X2_DO_ROW + g]);
+                    bfr[ks][1] = __float_as_uint(dos[(8 * t + 2 * ks + 1) * X2_DO_ROW + g]);
                 }
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {                 // hidden unit 8nb + g = 16mb + 8h + g
-                    const int mb = nb >> 1, h = nb & 1;
-                    const float4 lo = *reinterpret_cast<const float4*>(wb_base[0] + nb * 1024);   // rows 8t .. 8t+3
-                    const float4 hi = *reinterpret_cast<const float4*>(wb_base[1] + nb * 1024);   // rows 8t+4 .. 8t+7
-                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[0], __float_as_uint(lo.x), __float_as_uint(lo.y));
-                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[1], __float_as_uint(lo.z), __float_as_uint(lo.w));
-                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[2], __float_as_uint(hi.x), __float_as_uint(hi.y));
-                    mma_tf32(acc_wh[nb][0], acc_wh[nb][1], z0, z1, afr[3], __float_as_uint(hi.z), __float_as_uint(hi.w));
-                    gt[mb][0][2 * h] = lo.x > 0.f ? gt[mb][0][2 * h] : 0.f;
-                    gt[mb][0][2 * h + 1] = lo.y > 0.f ? gt[mb][0][2 * h + 1] : 0.f;
-                    gt[mb][1][2 * h] = lo.z > 0.f ? gt[mb][1][2 * h] : 0.f;
-                    gt[mb][1][2 * h + 1] = lo.w > 0.f ? gt[mb][1][2 * h + 1] : 0.f;
-                    gt[mb][2][2 * h] = hi.x > 0.f ? gt[mb][2][2 * h] : 0.f;
-                    gt[mb][2][2 * h + 1] = hi.y > 0.f ? gt[mb][2][2 * h + 1] : 0.f;
-                    gt[mb][3][2 * h] = hi.z > 0.f ? gt[mb][3][2 * h] : 0.f;
-                    gt[mb][3][2 * h + 1] = hi.w > 0.f ? gt[mb][3][2 * h + 1] : 0.f;
-                    acc_be[nb] += ((gt[mb][0][2 * h] + gt[mb][0][2 * h + 1]) + (gt[mb][1][2 * h] + gt[mb][1][2 * h + 1])) +
-                                  ((gt[mb][2][2 * h] + gt[mb][2][2 * h + 1]) + (gt[mb][3][2 * h] + gt[mb][3][2 * h + 1]));
+                for (int mb = 0; mb < 2; ++mb) {                 // hidden units 16mb + g (h = 0) and 16mb + 8 + g (h = 1)
+                    float4 lo[2], hi[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        lo[h] = *reinterpret_cast<const float4*>(wb_base[0] + (2 * mb + h) * 1024);   // rows 8t .. 8t+3
+                        hi[h] = *reinterpret_cast<const float4*>(wb_base[1] + (2 * mb + h) * 1024);   // rows 8t+4 .. 8t+7
+                    }
+                    // A[m = g + 8h][k = t + 4j] = rh[row 8t + 2ks + j][hidden unit 16mb + 8h + g]
+                    const uint32_t a0[4] = {__float_as_uint(lo[0].x), __float_as_uint(lo[1].x), __float_as_uint(lo[0].y), __float_as_uint(lo[1].y)};
+                    const uint32_t a1[4] = {__float_as_uint(lo[0].z), __float_as_uint(lo[1].z), __float_as_uint(lo[0].w), __float_as_uint(lo[1].w)};
+                    const uint32_t a2[4] = {__float_as_uint(hi[0].x), __float_as_uint(hi[1].x), __float_as_uint(hi[0].y), __float_as_uint(hi[1].y)};
+                    const uint32_t a3[4] = {__float_as_uint(hi[0].z), __float_as_uint(hi[1].z), __float_as_uint(hi[0].w), __float_as_uint(hi[1].w)};
+                    mma_tf32_full(acc_wh[mb], a0, bfr[0][0], bfr[0][1]);
+                    mma_tf32_full(acc_wh[mb], a1, bfr[1][0], bfr[1][1]);
+                    mma_tf32_full(acc_wh[mb], a2, bfr[2][0], bfr[2][1]);
+                    mma_tf32_full(acc_wh[mb], a3, bfr[3][0], bfr[3][1]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        gt[mb][0][2 * h] = lo[h].x > 0.f ? gt[mb][0][2 * h] : 0.f;
+                        gt[mb][0][2 * h + 1] = lo[h].y > 0.f ? gt[mb][0][2 * h + 1] : 0.f;
+                        gt[mb][1][2 * h] = lo[h].z > 0.f ? gt[mb][1][2 * h] : 0.f;
+                        gt[mb][1][2 * h + 1] = lo[h].w > 0.f ? gt[mb][1][2 * h + 1] : 0.f;
+                        gt[mb][2][2 * h] = hi[h].x > 0.f ? gt[mb][2][2 * h] : 0.f;
+                        gt[mb][2][2 * h + 1] = hi[h].y > 0.f ? gt[mb][2][2 * h + 1] : 0.f;
+                        gt[mb][3][2 * h] = hi[h].z > 0.f ? gt[mb][3][2 * h] : 0.f;
+                        gt[mb][3][2 * h + 1] = hi[h].w > 0.f ? gt[mb][3][2 * h + 1] : 0.f;
+                        acc_be[2 * mb + h] += ((gt[mb][0][2 * h] + gt[mb][0][2 * h + 1]) + (gt[mb][1][2 * h] + gt[mb][1][2 * h + 1])) +
+                                              ((gt[mb][2][2 * h] + gt[mb][2][2 * h + 1]) + (gt[mb][3][2 * h] + gt[mb][3][2 * h + 1]));
+                    }
                 }
                 __syncwarp();        // every lane has taken its rh fragments before dPre replaces them
 #pragma unroll
@@ -1179,8 +1197,8 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         float* mine_r = red + q * TAIL;
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
-            mine_r[g * HID + 32 * c + 8 * nb + 2 * t] = acc_wh[nb][0];
-            mine_r[g * HID + 32 * c + 8 * nb + 2 * t + 1] = acc_wh[nb][1];
+            mine_r[(2 * t) * HID + 32 * c + 8 * nb + g] = acc_wh[nb >> 1][2 * (nb & 1)];
+            mine_r[(2 * t + 1) * HID + 32 * c + 8 * nb + g] = acc_wh[nb >> 1][2 * (nb & 1) + 1];
             if (t == 0) mine_r[NO * HID + 32 * c + 8 * nb + g] = acc_be[nb];
         }
         if (lane < 4) {                        // db_heads partial of this warp's rows: [16 warps][8] behind the four TAIL rows
@@ -1331,7 +1349,8 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
         PB_CUDA(cudaFuncSetAttribute(k_mlp_update_fused<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_mlp_update_xt<96, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, X2_TOTAL));
         attr_set = true;
     }
     if (dpre_out) {
@@ -1339,7 +1358,8 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
         else k_mlp_update_fused<8, false><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
     } else if (g_update_variant == 2) {
         // 18 warps = 5 on two of the four schedulers: 16384 registers / (5 x 32) caps the kernel at 96 per thread
-        k_mlp_update_xt<96><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
+        if (p.dbg_clk) k_mlp_update_xt<96, true><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
+        else k_mlp_update_xt<96, false><<<grid, X2_THREADS, X2_TOTAL, s>>>(map_x, map_w, p);
     } else {
         if (n_act + 1 <= 5) k_mlp_update_fused<5, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
         else k_mlp_update_fused<8, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
