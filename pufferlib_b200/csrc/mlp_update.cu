@@ -951,9 +951,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             ga[mb][3] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g + 8]);
         }
         // addresses inside the warp's part of the dPre block (see g_off), hoisted out of the tile loop
-        uint8_t* st_base[8];                                    // thread = row: element (hidden unit k, row lane) at + k * 128, index k & 7
-#pragma unroll
-        for (int j = 0; j < 8; ++j) st_base[j] = mine + ((((lane >> 2) ^ j)) << 4) + ((lane & 3) << 2);
+        uint8_t* const st_row = mine + ((lane & 3) << 2);       // thread = row: element (hidden unit k, row lane) at k * 128 + piece ((lane >> 2) ^ (k & 7))
         uint8_t* ha_base[2];                                    // heads A: hidden unit 8kb + 2t + h, rows 4g..4g+3 (one piece)
 #pragma unroll
         for (int h = 0; h < 2; ++h) ha_base[h] = mine + (2 * t + h) * 128 + ((g ^ (2 * t + h)) << 4);
@@ -1022,7 +1020,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     v[4 * k4 + 3] = fmaxf(v[4 * k4 + 3] + b.w, 0.f);
                 }
 #pragma unroll
-                for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(st_base[k & 7] + k * 128) = v[k];
+                for (int k = 0; k < 32; ++k) *reinterpret_cast<float*>(st_row + ((((lane >> 2) ^ (k & 7))) << 4) + k * 128) = v[k];
                 if (p.dbg_hidden && lane < rows_left) {
 #pragma unroll
                     for (int k = 0; k < 32; k += 4)
@@ -1083,32 +1081,30 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             stamp(it, 5);
             asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
             stamp(it, 6);
-            row = load_row(it + 1);
 
-            // ---- 4. g^T[hidden unit][row] = W^T . dO^T        n = 2t' + j of block nb' <-> row 8t' + 2nb' + j
-            //         dW_heads += dO^T . rh                      k = t + 4j of block ks  <-> row 8t + 2ks + j
-            //      the rh fragments of the second product are the mask of the first one's accumulators
+            // ---- 4. per 16 hidden units (block mb):
+            //         g^T[hidden unit][row] = W^T . dO^T        n = 2t' + j of block nb' <-> row 8t' + 2nb' + j
+            //         dW_heads^T += rh^T . dO                   k = t + 4j of block ks  <-> row 8t + 2ks + j,  m = g + 8h <-> unit 16mb + 8h + g
+            //      the rh fragments of the second product sit exactly where the first one's accumulators need their mask, and
+            //      dPre goes back to the same places: no lane touches another lane's elements in this step
             {
-                float gt[2][4][4];
+                uint32_t gb[4][2], bfr[4][2];
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
+                for (int nb = 0; nb < 4; ++nb) {                 // dO as B[k = head][n = row] (g^T) and as B[k = row][n = head] (dW_heads^T)
                     const int rn = 8 * (g >> 1) + 2 * nb + (g & 1);
-                    const uint32_t b0 = __float_as_uint(dos[rn * X2_DO_ROW + t]);
-                    const uint32_t b1 = __float_as_uint(dos[rn * X2_DO_ROW + t + 4]);
+                    gb[nb][0] = __float_as_uint(dos[rn * X2_DO_ROW + t]);
+                    gb[nb][1] = __float_as_uint(dos[rn * X2_DO_ROW + t + 4]);
+                    bfr[nb][0] = __float_as_uint(dos[(8 * t + 2 * nb) * X2_DO_ROW + g]);
+                    bfr[nb][1] = __float_as_uint(dos[(8 * t + 2 * nb + 1) * X2_DO_ROW + g]);
+                }
 #pragma unroll
-                    for (int mb = 0; mb < 2; ++mb) {
-                        gt[mb][nb][0] = gt[mb][nb][1] = gt[mb][nb][2] = gt[mb][nb][3] = 0.f;
-                        mma_tf32_full(gt[mb][nb], ga[mb], b0, b1);
+                for (int mb = 0; mb < 2; ++mb) {
+                    float gt[4][4];                              // [nb'][2h + j]: hidden unit 16mb + 8h + g, row 8t + 2nb' + j
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        gt[nb][0] = gt[nb][1] = gt[nb][2] = gt[nb][3] = 0.f;
+                        mma_tf32_full(gt[nb], ga[mb], gb[nb][0], gb[nb][1]);
                     }
-                }
-                uint32_t bfr[4][2];                              // dO as B[k = row][n = head]: rows 8t + 2ks + {0,1}, head g
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    bfr[ks][0] = __float_as_uint(dos[(8 * t + 2 * ks) * X2_DO_ROW + g]);
-                    bfr[ks][1] = __float_as_uint(dos[(8 * t + 2 * ks + 1) * X2_DO_ROW + g]);
-                }
-#pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {                 // hidden units 16mb + g (h = 0) and 16mb + 8 + g (h = 1)
                     float4 lo[2], hi[2];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -1126,34 +1122,23 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     mma_tf32_full(acc_wh[mb], a3, bfr[3][0], bfr[3][1]);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        gt[mb][0][2 * h] = lo[h].x > 0.f ? gt[mb][0][2 * h] : 0.f;
-                        gt[mb][0][2 * h + 1] = lo[h].y > 0.f ? gt[mb][0][2 * h + 1] : 0.f;
-                        gt[mb][1][2 * h] = lo[h].z > 0.f ? gt[mb][1][2 * h] : 0.f;
-                        gt[mb][1][2 * h + 1] = lo[h].w > 0.f ? gt[mb][1][2 * h + 1] : 0.f;
-                        gt[mb][2][2 * h] = hi[h].x > 0.f ? gt[mb][2][2 * h] : 0.f;
-                        gt[mb][2][2 * h + 1] = hi[h].y > 0.f ? gt[mb][2][2 * h + 1] : 0.f;
-                        gt[mb][3][2 * h] = hi[h].z > 0.f ? gt[mb][3][2 * h] : 0.f;
-                        gt[mb][3][2 * h + 1] = hi[h].w > 0.f ? gt[mb][3][2 * h + 1] : 0.f;
-                        acc_be[2 * mb + h] += ((gt[mb][0][2 * h] + gt[mb][0][2 * h + 1]) + (gt[mb][1][2 * h] + gt[mb][1][2 * h + 1])) +
-                                              ((gt[mb][2][2 * h] + gt[mb][2][2 * h + 1]) + (gt[mb][3][2 * h] + gt[mb][3][2 * h + 1]));
-                    }
-                }
-                __syncwarp();        // every lane has taken its rh fragments before dPre replaces them
+                        const float4 d0 = make_float4(lo[h].x > 0.f ? gt[0][2 * h] : 0.f, lo[h].y > 0.f ? gt[0][2 * h + 1] : 0.f,
+                                                      lo[h].z > 0.f ? gt[1][2 * h] : 0.f, lo[h].w > 0.f ? gt[1][2 * h + 1] : 0.f);
+                        const float4 d1 = make_float4(hi[h].x > 0.f ? gt[2][2 * h] : 0.f, hi[h].y > 0.f ? gt[2][2 * h + 1] : 0.f,
+                                                      hi[h].z > 0.f ? gt[3][2 * h] : 0.f, hi[h].w > 0.f ? gt[3][2 * h + 1] : 0.f);
+                        *reinterpret_cast<float4*>(wb_base[0] + (2 * mb + h) * 1024) = d0;
+                        *reinterpret_cast<float4*>(wb_base[1] + (2 * mb + h) * 1024) = d1;
+                        acc_be[2 * mb + h] += ((d0.x + d0.y) + (d0.z + d0.w)) + ((d1.x + d1.y) + (d1.z + d1.w));
+                        if (p.dbg_dpre) {
+                            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    const int mb = nb >> 1, h = nb & 1;
-                    *reinterpret_cast<float4*>(wb_base[0] + nb * 1024) =
-                        make_float4(gt[mb][0][2 * h], gt[mb][0][2 * h + 1], gt[mb][1][2 * h], gt[mb][1][2 * h + 1]);
-                    *reinterpret_cast<float4*>(wb_base[1] + nb * 1024) =
-                        make_float4(gt[mb][2][2 * h], gt[mb][2][2 * h + 1], gt[mb][3][2 * h], gt[mb][3][2 * h + 1]);
-                    if (p.dbg_dpre) {
-#pragma unroll
-                        for (int r8 = 0; r8 < 8; ++r8)
-                            if (8 * t + r8 < rows_left)
-                                p.dbg_dpre[(dbg_row0 + 8 * t + r8) * HID + 32 * c + 8 * nb + g] = gt[mb][r8 >> 1][2 * h + (r8 & 1)];
+                            for (int r8 = 0; r8 < 8; ++r8)
+                                if (8 * t + r8 < rows_left) p.dbg_dpre[(dbg_row0 + 8 * t + r8) * HID + 32 * c + 16 * mb + 8 * h + g] = dv[r8];
+                        }
                     }
                 }
             }
+            row = load_row(it + 1);          // (volatile loads: issued here, where few registers are live)
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&dp_full[q]);
