@@ -1256,7 +1256,7 @@ int make_map2(EncodeTiledFn fn, CUtensorMap* map, const float* base, int64_t row
 int num_sms() { return pb_num_sms(); }
 
 long long* g_dbg_clk = nullptr;
-int g_update_variant = 1;     // 1 = two x layouts (k_mlp_update_fused), 2 = one x layout + transposing MMA (k_mlp_update_xt)
+int g_update_variant = 2;     // 1 = two x layouts (k_mlp_update_fused), 2 = one x layout + transposing MMA (k_mlp_update_xt)
 
 }  // namespace
 

@@ -134,7 +134,13 @@ def case(slab_rows, n_slabs, slab_stride, n_act, seed):
     g3, s3, _, _, _ = fused(xbuf, 128, slab_rows, slab_stride, n_slabs, w_enc, b_enc, w_cat, b_cat, act, olp, adv, ret, oval,
                             n_act, debug=False, dpre_out=dpre_hbm)
     torch.cuda.synchronize()
-    ok &= check('dPre written to HBM', dpre_hbm, dp, 1e-2 if TF32_EPILOGUE else 2e-6)       # (variant 2 sums the head products in four quarters)
+    if TF32_EPILOGUE:    # the HBM mode runs the variant-1 kernel (fp32 head products): a TF32-sized change of a logit moves rows
+        # across the clipping boundaries of the loss, so compare row-wise and allow a few such rows
+        bad = ((dpre_hbm.double() - dp.double()).abs().amax(1) > 2e-2 * float(dp.abs().max())).float().mean().item()
+        print(f'    dPre written to HBM (variant 1)    rows off by more than 2 %: {100 * bad:.3f} %  {"ok" if bad < 2e-3 else "MISMATCH"}', flush=True)
+        ok &= bad < 2e-3
+    else:
+        ok &= check('dPre written to HBM', dpre_hbm, dp, 2e-6)
     ok &= check('small gradients (HBM mode)', g3[128 * 128:], gflat[128 * 128:], 1e-2 if TF32_EPILOGUE else 1e-6)
     ok &= bool(torch.isnan(g3[:128 * 128]).all())
     ok &= check('loss statistics (HBM mode)', s3[:6], stats[:6], 2e-3 if TF32_EPILOGUE else 1e-7)
