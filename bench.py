@@ -227,7 +227,7 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                                  C.c_float(0.99), C.c_float(0.95), _native.ptr(exp._gae_ws), exp._gae_ws.numel(),
                                  _native.stream_ptr()))
     t_gae = time_launches(gae, 16)
-    t_gae_v1 = t_gae_v3 = None
+    t_gae_v1 = t_gae_v3 = t_gae_v2 = None
     if h in (128, 256, 512) and n % 4 == 0:      # A/B: the other tile-kernel variants on the same inputs
         try:
             _native.check(lib.pb_gae_set_variant(1))
@@ -236,13 +236,21 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
             _native.check(lib.pb_gae_set_variant(3))
             gae(0)
             t_gae_v3 = time_launches(gae, 16)
+            _native.check(lib.pb_gae_set_variant(2))
+            gae(0)
+            t_gae_v2 = time_launches(gae, 16)
         finally:
-            lib.pb_gae_set_variant(2)
+            lib.pb_gae_set_variant(0)
     del sets
     # pb_gae's dispatch (csrc/gae.cu): the single-pass tile kernel for H in {128, 256, 512} and N % 4 == 0, else the general one
     gae_kernel = 'k_gae_fast' if (h in (128, 256, 512) and n % 4 == 0) else 'k_gae'
     gae_kernel = 'k_gae_tile' if gae_kernel == 'k_gae_fast' else gae_kernel
+    if gae_kernel == 'k_gae_tile':
+        gae_kernel += ' (double-buffered)' if h <= 128 else ' (single-buffered)'       # pb_gae's choice by horizon (csrc/gae.cu)
     out['gae'] = dict(kernel=gae_kernel, bytes_per_launch=n * h * 20, seconds=t_gae, launches_per_step=1)
+    if t_gae_v2 is not None:
+        out['gae_double_buffered'] = dict(kernel='k_gae_tile, NBUF = 2 (for comparison)', bytes_per_launch=n * h * 20,
+                                          seconds=t_gae_v2, launches_per_step=0)
     if t_gae_v3 is not None:
         out['gae_single_buffered'] = dict(kernel='k_gae_tile, NBUF = 1 (for comparison)', bytes_per_launch=n * h * 20,
                                           seconds=t_gae_v3, launches_per_step=0)
@@ -356,7 +364,8 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
                 with torch.no_grad():
                     upd(0)
                     t_upd = time_launches(upd, 8)
-                out['mlp_update'] = dict(kernel=f'k_mlp_update_fused (tcgen05, dW: {dw_mode}) + k_update_reduce', seconds=t_upd,
+                out['mlp_update'] = dict(kernel=('k_mlp_update_xt (tcgen05 forward / x^T / dW + mma.sync epilogue)' if dw_mode == 'kernel' else
+                                                 'k_mlp_update_fused (tcgen05, dPre to HBM, dW: cuBLAS)') + ' + k_update_reduce', seconds=t_upd,
                                          bytes_per_launch=mb * (512 + 28 + (512 if dpre_b is not None else 0)),
                                          launches_per_step=nm * args.epochs,
                                          tf32_tflops=round(2 * 2 * mb * 128 * 128 / t_upd / 1e12, 1))
@@ -369,7 +378,7 @@ def kernel_rooflines(data, args, peak_gbs, peak_src):
     # DRAM traffic per launch from the committed `ncu --set full` capture of this workload (profiles/), else null
     traffic = None
     try:
-        tr = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic_r01.json')))['bytes_per_launch']
+        tr = json.load(open(os.path.join(REPO, 'profiles', 'ncu_traffic_r02.json')))['bytes_per_launch']
         if args.env == 'breakout' and n == 16384 and h == 128:
             traffic = tr.get({'env_step': 'breakout', 'obs_gather': 'gather'}.get(dom, dom))
     except Exception:

@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(THREADS) k_gae_tile(GaeParams p) {
     }
 }
 
-int g_gae_variant = 2;   // 2: k_gae_tile (double-buffered, coalesced outputs); 1: k_gae_fast
+int g_gae_variant = 0;   // 0: by horizon (measured: 2 at H <= 128, 3 above); 2 / 3: k_gae_tile double- / single-buffered; 1: k_gae_fast
 
 struct GaePlan {
     int fastKC;   // > 0: k_gae_fast<fastKC, nbuf>
@@ -921,9 +921,10 @@ extern "C" int pb_gae_tm(const float* rewards, const float* values, const float*
         k_gae_tile<KC, NBUF, THREADS><<<grid, THREADS, smem2, s>>>(p);                                                \
     }
         const bool v2_ok = !(returns_sorted && advantages_time_major);   // v2 stages two outputs: adv + (ret | adv_tm)
-        if (g_gae_variant == 2 && v2_ok) {
+        const int variant = g_gae_variant ? g_gae_variant : (g.fastKC == 1 ? 2 : 3);   // C2 (H = 128): 17.8 us either way; C3 (H = 256): 95 vs 119 us
+        if (variant == 2 && v2_ok) {
             if (g.fastKC == 1) PB_GAE_TILE(1, 2, 256) else if (g.fastKC == 2) PB_GAE_TILE(1, 2, 512) else PB_GAE_TILE(2, 1, 512)
-        } else if (g_gae_variant == 3 && v2_ok) {   // single-buffered tiles (more CTAs per SM), coalesced outputs
+        } else if (variant == 3 && v2_ok) {   // single-buffered tiles (more CTAs per SM), coalesced outputs
             if (g.fastKC == 1) PB_GAE_TILE(1, 1, 256) else if (g.fastKC == 2) PB_GAE_TILE(2, 1, 256) else PB_GAE_TILE(2, 1, 512)
         } else {
             if (g.fastKC == 1) PB_GAE_FAST(1) else if (g.fastKC == 2) PB_GAE_FAST(2) else PB_GAE_FAST(4)
@@ -949,10 +950,10 @@ extern "C" int pb_gae_tm(const float* rewards, const float* values, const float*
     return PB_OK;
 }
 
-// 2 (default): k_gae_tile (double-buffered tiles, coalesced outputs); 3: k_gae_tile single-buffered; 1: the round-1
-// k_gae_fast.  For A/B measurements.
+// 0 (default): chosen by horizon; 2: k_gae_tile (double-buffered tiles, coalesced outputs); 3: k_gae_tile single-buffered;
+// 1: the round-1 k_gae_fast.  For A/B measurements.
 extern "C" int pb_gae_set_variant(int32_t variant) {
-    PB_REQUIRE(variant >= 1 && variant <= 3, PB_ERR_INVALID, "pb_gae_set_variant: 1, 2 or 3");
+    PB_REQUIRE(variant >= 0 && variant <= 3, PB_ERR_INVALID, "pb_gae_set_variant: 0 .. 3");
     g_gae_variant = variant;
     return PB_OK;
 }
