@@ -285,6 +285,10 @@ int pb_mlp_tail_backward(const float* dout, int64_t dout_stride, const float* w_
 size_t pb_mlp_update_workspace_bytes(void);
 /* 1 = two x layouts per tile (K-major + MN-major TMA loads), 2 = one x layout, x^T formed on the tensor core */
 int pb_mlp_update_set_variant(int32_t variant);
+/* the reduce step of pb_mlp_update_fused also leaves the sum of squares of the gradient it wrote as pb_mlp_update_sumsq_parts()
+ * doubles at byte pb_mlp_update_sumsq_offset() of the workspace (dW-in-kernel mode): input of pb_clip_adam_parts */
+size_t pb_mlp_update_sumsq_offset(void);
+int32_t pb_mlp_update_sumsq_parts(void);
 /* profiling hook (variant 2): SM-clock stamps of tiles 8..11, [grid][18 warps][4][8] int64; NULL switches it off */
 int pb_mlp_update_debug_clock(long long* buf);
 int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
@@ -343,6 +347,15 @@ int pb_peer_open(const void* handle64, void** ptr_out);
 int pb_peer_close(void* ptr);
 int pb_peer_free(void* ptr);
 int pb_peer_allreduce(const pb_peer_comm* comm, float* flat, int64_t n, void* stream);
+/* Multi-CTA forms (the single-CTA calls above stay for callers without partial sums of squares): pb_peer_allreduce_parts
+ * sums flat[0..n) over the ranks with pb_peer_slices() CTAs and writes that many partial sums of squares of the result;
+ * pb_clip_adam_parts is pb_clip_adam with the norm taken from n_parts partial sums of squares of the summed, unscaled
+ * gradient; it advances *peer_epoch (nullable: the communicator's counter) for the all-reduce that preceded it. */
+int pb_peer_allreduce_parts(const pb_peer_comm* comm, float* flat, int64_t n, double* sumsq_parts, void* stream);
+int32_t pb_peer_slices(void);
+int pb_clip_adam_parts(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
+                       const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
+                       const double* sumsq_parts, int32_t n_parts, unsigned long long* peer_epoch, void* stream);
 int pb_clip_adam_peer(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
                       const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
                       const pb_peer_comm* comm, float* grad_flat, int64_t grad_flat_numel, void* stream);

@@ -98,6 +98,12 @@ SIGNATURES = {
     'pb_clip_adam_peer': (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float,
                                     C.c_float, C.c_float, C.c_void_p, C.POINTER(PeerComm), C.c_void_p, C.c_int64,
                                     C.c_void_p]),
+    'pb_clip_adam_parts': (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float,
+                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    'pb_peer_allreduce_parts': (C.c_int, [C.POINTER(PeerComm), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'pb_peer_slices': (C.c_int32, []),
+    'pb_mlp_update_sumsq_offset': (C.c_size_t, []),
+    'pb_mlp_update_sumsq_parts': (C.c_int32, []),
     'pb_peer_buffer_bytes': (C.c_size_t, [C.c_int64]),
     'pb_peer_alloc': (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
     'pb_peer_open': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -269,6 +269,7 @@ class _DefaultMLPUpdate:
         # multi-GPU: the gradient sum is fused into pb_clip_adam_peer over NVLink peer memory (distributed.PeerComm); the
         # NCCL all-reduce is only the fallback when peer mapping is unavailable (config.peer_allreduce=False, or IPC failed)
         self.peer = None
+        self.peer_parts = None
         if self.world > 1 and bool(getattr(data.config, 'peer_allreduce', True)):
             from pufferlib_b200.distributed import PeerComm
             ok = torch.ones(1, device=dev)
@@ -411,11 +412,26 @@ class _DefaultMLPUpdate:
         lr = g['lr']
         lr_dev = _native.ptr(lr) if isinstance(lr, torch.Tensor) else None
         b1, b2 = g['betas']
-        _native.check(_native.lib().pb_clip_adam_peer(
-            self.tensors, len(self.tensors), C.c_float(float(config.max_grad_norm)), C.c_float(1.0 / self.world),
-            C.c_float(0.0 if lr_dev is not None else float(lr)), lr_dev, C.c_float(b1), C.c_float(b2),
-            C.c_float(g['eps']), None, C.byref(self.peer.struct) if self.peer is not None else None,
-            _native.ptr(self.gflat), self.gflat.numel(), _native.stream_ptr()))
+        lib = _native.lib()
+        hyper = (C.c_float(float(config.max_grad_norm)), C.c_float(1.0 / self.world),
+                 C.c_float(0.0 if lr_dev is not None else float(lr)), lr_dev, C.c_float(b1), C.c_float(b2), C.c_float(g['eps']), None)
+        in_kernel = str(getattr(config, 'fused_update_dw', FUSED_UPDATE_DW_DEFAULT)) == 'kernel'
+        if self.used_fused and in_kernel and (self.world == 1 or self.peer is not None) and bool(getattr(config, 'adam_parts', True)):
+            # the fused update's reduce step left the gradient's sum of squares as partial sums: multi-CTA clip + Adam without a
+            # norm pass; several ranks: sliced peer all-reduce first, which leaves its own partial sums of squares
+            parts = C.c_void_p(self.fused_ws.data_ptr() + lib.pb_mlp_update_sumsq_offset())
+            n_parts, epoch = lib.pb_mlp_update_sumsq_parts(), None
+            if self.peer is not None:
+                if self.peer_parts is None:
+                    self.peer_parts = torch.zeros(lib.pb_peer_slices(), dtype=torch.float64, device=self.gflat.device)
+                _native.check(lib.pb_peer_allreduce_parts(C.byref(self.peer.struct), _native.ptr(self.gflat), self.gflat.numel(),
+                                                          _native.ptr(self.peer_parts), _native.stream_ptr()))
+                parts, n_parts, epoch = _native.ptr(self.peer_parts), lib.pb_peer_slices(), _native.ptr(self.peer.epoch)
+            _native.check(lib.pb_clip_adam_parts(self.tensors, len(self.tensors), *hyper, parts, n_parts, epoch, _native.stream_ptr()))
+        else:
+            _native.check(lib.pb_clip_adam_peer(
+                self.tensors, len(self.tensors), *hyper, C.byref(self.peer.struct) if self.peer is not None else None,
+                _native.ptr(self.gflat), self.gflat.numel(), _native.stream_ptr()))
         self.pack_heads()
 
     def loss_means(self, n_mb):

@@ -1215,12 +1215,16 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 //   gflat = [ dW_enc[hid][feat] (transposed from the partials' [feat][hid]) | dW_heads 8 x hid | db_enc | db_heads ]
 // Block = 64 outputs x 4 partial groups; consecutive threads read consecutive partial elements (coalesced).
 __global__ void __launch_bounds__(256) k_update_reduce(const float* __restrict__ part_dw, const float* __restrict__ part_tail,
-                                                       int n_parts, float* __restrict__ gflat) {
+                                                       int n_parts, float* __restrict__ gflat, double* __restrict__ sumsq_part) {
     __shared__ float sh[4][64];
+    __shared__ double sq[2];
     const int e = blockIdx.x * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
     constexpr int NDW = FEAT * HID;
     float s = 0.f;
-    if (e < NDW && !part_dw) return;          // dW_enc is formed by the caller (dPre went to HBM); whole blocks: NDW % 64 == 0
+    if (e < NDW && !part_dw) {                // dW_enc is formed by the caller (dPre went to HBM); whole blocks: NDW % 64 == 0
+        if (threadIdx.x == 0) sumsq_part[blockIdx.x] = 0.0;
+        return;
+    }
     if (e < NDW + TAIL) {
         const float* src = e < NDW ? part_dw + e : part_tail + (e - NDW);
         const int64_t stride = e < NDW ? NDW : TAIL;
@@ -1229,11 +1233,22 @@ __global__ void __launch_bounds__(256) k_update_reduce(const float* __restrict__
     }
     sh[grp][threadIdx.x & 63] = s;
     __syncthreads();
-    if (grp == 0 && e < NDW + TAIL) {
-        const float tot = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
-        if (e < NDW) gflat[(e % HID) * FEAT + e / HID] = tot;      // partial element (f, j) -> dW_enc[j][f]
-        else gflat[e] = tot;
+    if (grp == 0) {                           // warps 0 and 1
+        float tot = 0.f;
+        if (e < NDW + TAIL) {
+            tot = sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x];
+            if (e < NDW) gflat[(e % HID) * FEAT + e / HID] = tot;      // partial element (f, j) -> dW_enc[j][f]
+            else gflat[e] = tot;
+        }
+        // sum of squares of this block's 64 gradient elements: the global-norm pass of the optimizer step becomes a sum of
+        // gridDim.x doubles (pb_clip_adam_parts), in a fixed order
+        double d = (double)tot * (double)tot;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+        if ((threadIdx.x & 31) == 0) sq[threadIdx.x >> 5] = d;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) sumsq_part[blockIdx.x] = sq[0] + sq[1];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1271,8 +1286,15 @@ extern "C" int pb_mlp_update_debug_clock(long long* buf) {     // profiling hook
     return PB_OK;
 }
 
+constexpr int REDUCE_BLOCKS = (FEAT * HID + TAIL + 63) / 64;
+
+// workspace: per-CTA partials [SMs][FEAT * HID + TAIL] floats | REDUCE_BLOCKS doubles (sums of squares of the gradient)
+extern "C" size_t pb_mlp_update_sumsq_offset(void) {
+    return (((size_t)num_sms() * (FEAT * HID + TAIL) * sizeof(float)) + 15) & ~(size_t)15;
+}
+extern "C" int32_t pb_mlp_update_sumsq_parts(void) { return REDUCE_BLOCKS; }
 extern "C" size_t pb_mlp_update_workspace_bytes(void) {
-    return (size_t)num_sms() * (FEAT * HID + TAIL) * sizeof(float);
+    return pb_mlp_update_sumsq_offset() + REDUCE_BLOCKS * sizeof(double);
 }
 
 extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_rows, int64_t slab_stride_rows, int32_t n_slabs,
@@ -1350,7 +1372,8 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
         else k_mlp_update_fused<8, true><<<grid, THREADS, SMEM_TOTAL, s>>>(map_x, map_x32, map_w, p);
     }
     PB_LAUNCH_CHECK();
-    k_update_reduce<<<(FEAT * HID + TAIL + 63) / 64, 256, 0, s>>>(dpre_out ? nullptr : p.part_dw, p.part_tail, grid, grad_flat);
+    k_update_reduce<<<REDUCE_BLOCKS, 256, 0, s>>>(dpre_out ? nullptr : p.part_dw, p.part_tail, grid, grad_flat,
+                                                  reinterpret_cast<double*>((char*)workspace + pb_mlp_update_sumsq_offset()));
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

@@ -97,6 +97,78 @@ __global__ void __launch_bounds__(CA_THREADS) k_clip_adam(AdamArgs a) {
     }
 }
 
+// Multi-CTA form for callers that already hold the gradient's sum of squares as partial sums (k_update_reduce of the fused
+// update, or the sliced peer all-reduce): no norm pass, every CTA sums the partials in the same fixed order, then updates
+// its share of the elements.  The step counters are advanced by the LAST CTA to finish (all others have read them).
+constexpr int CAP_THREADS = 256, CAP_BLOCKS = 32;
+__device__ unsigned int g_cap_ticket = 0;
+
+__global__ void __launch_bounds__(CAP_THREADS) k_clip_adam_parts(AdamArgs a, const double* __restrict__ parts, int n_parts,
+                                                                unsigned long long* peer_epoch) {
+    __shared__ double s_red[CAP_THREADS / 32];
+    __shared__ float s_coef;
+    __shared__ float s_step_size[CA_MAX_TENSORS], s_bc2_sqrt[CA_MAX_TENSORS], s_new_step[CA_MAX_TENSORS];
+    __shared__ int64_t s_first[CA_MAX_TENSORS + 1];
+    const int tid = threadIdx.x;
+    double d = 0.0;
+    for (int i = tid; i < n_parts; i += CAP_THREADS) d += parts[i];          // fixed assignment and order: same bits in every CTA
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+    if ((tid & 31) == 0) s_red[tid >> 5] = d;
+    if (tid == 0) {
+        int64_t acc = 0;
+        for (int k = 0; k < a.n; ++k) { s_first[k] = acc; acc += a.t[k].numel; }
+        s_first[a.n] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < CAP_THREADS / 32; ++w) tot += s_red[w];
+        const float norm = (float)sqrt(tot) * a.grad_scale;                   // partials are of the unscaled (summed) gradient
+        float coef = 1.f;
+        if (a.max_norm > 0.f) coef = fminf(a.max_norm / (norm + 1e-6f), 1.f);
+        s_coef = coef * a.grad_scale;
+        if (a.total_norm_out && blockIdx.x == 0) *a.total_norm_out = norm;
+    }
+    if (tid < a.n) {
+        const float step = *a.t[tid].step + 1.f;
+        const double lr = a.lr_dev ? (double)*a.lr_dev : (double)a.lr;
+        const double bc1 = 1.0 - pow((double)a.beta1, (double)step);
+        const double bc2 = 1.0 - pow((double)a.beta2, (double)step);
+        s_step_size[tid] = (float)(lr / bc1);
+        s_bc2_sqrt[tid] = (float)sqrt(bc2);
+        s_new_step[tid] = step;
+    }
+    __syncthreads();
+    const float coef = s_coef;
+    const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+    const int64_t total = s_first[a.n];
+    for (int64_t j = (int64_t)blockIdx.x * CAP_THREADS + tid; j < total; j += (int64_t)gridDim.x * CAP_THREADS) {
+        int k = 0;
+        while (j >= s_first[k + 1]) ++k;
+        const int64_t i = j - s_first[k];
+        const float x = a.t[k].grad[i] * coef;
+        float* m = a.t[k].exp_avg;
+        float* v = a.t[k].exp_avg_sq;
+        const float mi = m[i] + w1 * (x - m[i]);                  // lerp(exp_avg, grad, 1 - beta1)
+        const float vi = a.beta2 * v[i] + w2 * x * x;
+        const float denom = sqrtf(vi) / s_bc2_sqrt[k] + a.eps;
+        m[i] = mi;
+        v[i] = vi;
+        a.t[k].param[i] -= s_step_size[k] * mi / denom;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(&g_cap_ticket, 1u);
+        if (t == gridDim.x - 1) {        // every CTA has read the step counters (and the peer epoch is no longer in use)
+            for (int k = 0; k < a.n; ++k) *a.t[k].step = s_new_step[k];
+            if (peer_epoch) *peer_epoch += 1ull;
+            g_cap_ticket = 0;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_pack_heads(const float* __restrict__ w_dec, const float* __restrict__ b_dec,
                                                     const float* __restrict__ w_val, const float* __restrict__ b_val,
                                                     int n_act, int hid, float* __restrict__ w_cat,
@@ -166,6 +238,37 @@ extern "C" int pb_clip_adam_peer(const pb_adam_tensor* tensors, int32_t n_tensor
         a.flat_n = grad_flat_numel;
     }
     k_clip_adam<<<1, CA_THREADS, 0, (cudaStream_t)stream>>>(a);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+}
+
+// pb_clip_adam for callers that hold the sum of squares of the (already summed over ranks, unscaled) gradient as n_parts
+// partial sums: the reduce step of pb_mlp_update_fused (pb_mlp_update_sumsq_offset / _parts) or pb_peer_allreduce_parts.
+// peer_epoch (nullable): the communicator's epoch counter, advanced here after pb_peer_allreduce_parts.
+extern "C" int pb_clip_adam_parts(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale,
+                                  float lr, const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
+                                  const double* sumsq_parts, int32_t n_parts, unsigned long long* peer_epoch, void* stream) {
+    PB_REQUIRE(tensors && n_tensors >= 1 && n_tensors <= CA_MAX_TENSORS && sumsq_parts && n_parts >= 1, PB_ERR_INVALID,
+               "pb_clip_adam_parts: bad arguments");
+    AdamArgs a{};
+    for (int k = 0; k < n_tensors; ++k) {
+        const pb_adam_tensor& t = tensors[k];
+        PB_REQUIRE(t.param && t.exp_avg && t.exp_avg_sq && t.step && t.grad && t.numel >= 1, PB_ERR_INVALID,
+                   "pb_clip_adam_parts: tensor %d has a null pointer or no elements", k);
+        a.t[k] = t;
+    }
+    PB_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && grad_scale > 0.f,
+               PB_ERR_INVALID, "pb_clip_adam_parts: bad hyper-parameters");
+    a.n = n_tensors;
+    a.max_norm = max_grad_norm;
+    a.grad_scale = grad_scale;
+    a.lr = lr;
+    a.lr_dev = lr_dev;
+    a.beta1 = beta1;
+    a.beta2 = beta2;
+    a.eps = eps;
+    a.total_norm_out = total_norm_out;
+    k_clip_adam_parts<<<CAP_BLOCKS, CAP_THREADS, 0, (cudaStream_t)stream>>>(a, sumsq_parts, n_parts, peer_epoch);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

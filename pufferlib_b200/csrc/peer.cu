@@ -58,7 +58,25 @@ namespace {
 __global__ void __launch_bounds__(1024) k_peer_allreduce(pb_peer_comm c, float* flat, int64_t n) {
     pb_peer_allreduce_sum(c, flat, n);
 }
+__global__ void __launch_bounds__(512) k_peer_allreduce_slices(pb_peer_comm c, float* flat, int64_t n, double* sumsq) {
+    pb_peer_allreduce_slice(c, flat, n, sumsq);
+}
 }  // namespace
+
+// Sliced form: PB_PEER_SLICES CTAs, each sums one slice over all ranks and leaves the slice's sum of squares in
+// sumsq_parts[0..16).  The epoch counter is advanced by the pb_clip_adam_parts call that must follow in the same stream.
+extern "C" int pb_peer_allreduce_parts(const pb_peer_comm* comm, float* flat, int64_t n, double* sumsq_parts, void* stream) {
+    PB_REQUIRE(comm && flat && n >= 1 && sumsq_parts, PB_ERR_INVALID, "pb_peer_allreduce_parts: bad arguments");
+    PB_REQUIRE(comm->world >= 1 && comm->world <= PB_PEER_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world &&
+                   comm->epoch && n <= comm->capacity,
+               PB_ERR_INVALID, "pb_peer_allreduce_parts: bad communicator (world %d rank %d capacity %lld, n %lld)", comm->world,
+               comm->rank, (long long)comm->capacity, (long long)n);
+    for (int r = 0; r < comm->world; ++r) PB_REQUIRE(comm->base[r], PB_ERR_INVALID, "pb_peer_allreduce_parts: peer %d not mapped", r);
+    k_peer_allreduce_slices<<<PB_PEER_SLICES, 512, 0, (cudaStream_t)stream>>>(*comm, flat, n, sumsq_parts);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+}
+extern "C" int32_t pb_peer_slices(void) { return PB_PEER_SLICES; }
 
 // In-place sum of flat[0..n) over all ranks (every rank must call it the same number of times).  One CTA.
 extern "C" int pb_peer_allreduce(const pb_peer_comm* comm, float* flat, int64_t n, void* stream) {

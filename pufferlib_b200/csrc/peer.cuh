@@ -76,4 +76,58 @@ __device__ __forceinline__ void pb_peer_allreduce_sum(const pb_peer_comm& c, flo
     __syncthreads();
     if (tid == 0) *c.epoch = e;
 }
+
+constexpr int PB_PEER_SLICES = 16;           // flags of source rank r, slice b at byte 128 r + 8 b of the header
+
+// Multi-CTA form: CTA b (of PB_PEER_SLICES) sums slice b over all ranks.  Slices are independent (own flag per rank and
+// slice), so there is no grid-wide barrier; the epoch counter is NOT advanced here (every CTA reads it at its start): the
+// kernel that follows in the stream does it (pb_clip_adam_parts).  sumsq[b] = sum of squares of the summed slice.
+__device__ __forceinline__ void pb_peer_allreduce_slice(const pb_peer_comm& c, float* flat, int64_t n, double* sumsq) {
+    __shared__ uint64_t s_epoch;
+    __shared__ double s_sq[32];
+    const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x;
+    if (tid == 0) s_epoch = *c.epoch + 1;
+    __syncthreads();
+    const uint64_t e = s_epoch;
+    const int64_t chunk = ((n + PB_PEER_SLICES - 1) / PB_PEER_SLICES + 3) & ~(int64_t)3;
+    const int64_t lo = (int64_t)b * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    const int64_t slot_off = PB_PEER_HEADER_BYTES / 4 + (int64_t)(e & 1) * c.capacity;
+    float* mine = reinterpret_cast<float*>(c.base[c.rank]) + slot_off;
+    for (int64_t i = lo + tid; i < hi; i += nt) mine[i] = flat[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid < c.world) {
+        uint64_t* flag = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(c.base[tid]) + 128 * c.rank + 8 * b);
+        pb_st_release_sys_u64(flag, e);
+        const uint64_t* theirs = reinterpret_cast<const uint64_t*>(reinterpret_cast<const char*>(c.base[c.rank]) + 128 * tid + 8 * b);
+        const long long t0 = clock64();
+        while (pb_ld_acquire_sys_u64(theirs) < e) {
+            if (clock64() - t0 > 20000000000ll) __trap();
+            __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    double sq = 0.0;
+    for (int64_t i = lo + tid; i < hi; i += nt) {
+        float v[PB_PEER_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < PB_PEER_MAX_RANKS; ++r)
+            if (r < c.world) v[r] = pb_ld_relaxed_sys_f32(reinterpret_cast<const float*>(c.base[r]) + slot_off + i);
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < PB_PEER_MAX_RANKS; ++r)      // rank order: the same bits on every rank
+            if (r < c.world) s += v[r];
+        flat[i] = s;
+        sq += (double)s * (double)s;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+    if ((tid & 31) == 0) s_sq[tid >> 5] = sq;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (nt + 31) / 32; ++w) tot += s_sq[w];
+        sumsq[b] = tot;
+    }
+}
 #endif

@@ -50,6 +50,48 @@ def test_clip_adam_matches_torch_clip_and_adam(max_norm, world, lr_on_device):
             assert float((ours[k] - ref[k].detach()).abs().max()) <= 1e-3 * lr * (it + 1), (it, k)
 
 
+@pytest.mark.parametrize('world,n_parts', [(1, 275), (2, 16), (1, 1)])
+def test_clip_adam_parts_matches_single_cta_kernel(world, n_parts):
+    """pb_clip_adam_parts (multi-CTA, norm from partial sums of squares of the unscaled gradient) vs pb_clip_adam on the same
+    gradients, several steps with and without clipping: same step counters, moments and parameters."""
+    dev = torch.device('cuda')
+    torch.manual_seed(3)
+    shapes = [(128, 128), (128,), (4, 128), (4,), (1, 128), (1,)]
+    pa = [torch.randn(s, device=dev) * 0.1 for s in shapes]
+    pb = [p.clone() for p in pa]
+    mk = lambda ps: [dict(step=torch.zeros((), device=dev), m=torch.zeros_like(p), v=torch.zeros_like(p)) for p in ps]
+    sa, sb = mk(pa), mk(pb)
+    lib = _native.lib()
+    na, nb = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    for it in range(4):
+        flat = torch.randn(sum(int(np.prod(s)) for s in shapes), device=dev) * (10.0 if it == 1 else 0.05)
+        grads, off = [], 0
+        for s in shapes:
+            k = int(np.prod(s))
+            grads.append(flat[off:off + k])
+            off += k
+        chunks = torch.tensor_split(flat.double(), n_parts)
+        parts = torch.stack([(c * c).sum() for c in chunks])
+        for ps, st, norm, use_parts in ((pa, sa, na, False), (pb, sb, nb, True)):
+            arr = (_native.AdamTensor * 6)()
+            for k in range(6):
+                arr[k] = _native.AdamTensor(ps[k].data_ptr(), st[k]['m'].data_ptr(), st[k]['v'].data_ptr(),
+                                            st[k]['step'].data_ptr(), grads[k].data_ptr(), ps[k].numel())
+            hyper = (C.c_float(0.5), C.c_float(1.0 / world), C.c_float(2.5e-4), None, C.c_float(0.9), C.c_float(0.999),
+                     C.c_float(1e-5), _native.ptr(norm))
+            if use_parts:
+                _native.check(lib.pb_clip_adam_parts(arr, 6, *hyper, _native.ptr(parts), n_parts, None, _native.stream_ptr()))
+            else:
+                _native.check(lib.pb_clip_adam(arr, 6, *hyper, _native.stream_ptr()))
+        torch.cuda.synchronize()
+        assert abs(float(na) - float(nb)) <= 1e-6 * float(na)
+        for k in range(6):
+            assert float(sa[k]['step']) == float(sb[k]['step']) == it + 1
+            assert torch.allclose(sa[k]['m'], sb[k]['m'], rtol=1e-5, atol=1e-10)
+            assert torch.allclose(sa[k]['v'], sb[k]['v'], rtol=1e-5, atol=1e-12)
+            assert float((pa[k] - pb[k]).abs().max()) <= 1e-7
+
+
 @pytest.mark.parametrize('n_act,features', [(4, 128), (7, 49), (1, 300)])
 def test_pack_heads_matches_torch_construction(n_act, features):
     dev = torch.device('cuda')
