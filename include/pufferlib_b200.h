@@ -353,9 +353,20 @@ int pb_peer_allreduce(const pb_peer_comm* comm, float* flat, int64_t n, void* st
  * gradient; it advances *peer_epoch (nullable: the communicator's counter) for the all-reduce that preceded it. */
 int pb_peer_allreduce_parts(const pb_peer_comm* comm, float* flat, int64_t n, double* sumsq_parts, void* stream);
 int32_t pb_peer_slices(void);
+typedef struct pb_head_pack {   /* optional tail of pb_clip_adam_parts: pb_pack_heads (without the encoder copy) on the updated parameters */
+    const float* w_dec;
+    const float* b_dec;
+    const float* w_val;
+    const float* b_val;
+    float* w_cat;
+    float* b_cat;
+    int32_t n_act;
+    int32_t hid;
+} pb_head_pack;
 int pb_clip_adam_parts(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
                        const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
-                       const double* sumsq_parts, int32_t n_parts, unsigned long long* peer_epoch, void* stream);
+                       const double* sumsq_parts, int32_t n_parts, unsigned long long* peer_epoch, const pb_head_pack* pack,
+                       void* stream);
 int pb_clip_adam_peer(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
                       const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
                       const pb_peer_comm* comm, float* grad_flat, int64_t grad_flat_numel, void* stream);

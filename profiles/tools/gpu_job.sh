@@ -1,9 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
 run() { name=$1; t=$2; shift 2; ( timeout $t "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?" >> gpurun_out/$name.log ); echo "== $name: $(tail -1 gpurun_out/$name.log)"; }
-run t_all 900 python -m pytest tests -m gpu -x -q
-tail -5 gpurun_out/t_all.log
-run smoke 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
-tail -2 gpurun_out/smoke.log
-run launches 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 2 --warmup 1 --no-extra-configs --no-cpu-baseline
-tail -2 gpurun_out/launches.log | cut -c1-200
+run t_sel 600 python -m pytest tests/test_gpu_optim.py tests/test_gpu_rollout.py tests/test_gpu_experience.py -x -q
+tail -4 gpurun_out/t_sel.log
+run fused_v2 200 python tests/experimental/check_mlp_update_fused.py --variant 2
+grep -n "MISMATCH\|ALL OK\|SOME\|fused update\|rror" gpurun_out/fused_v2.log | head -20
+run bench 400 python bench.py --steps 10 --warmup 3 --no-extra-configs --no-cpu-baseline
+python - <<'PY'
+import json
+for line in open('gpurun_out/bench.log'):
+    if line.startswith('{"metric"'):
+        d=json.loads(line); rk=d['roofline_kernels']
+        print(d['value'], d['ms_per_step'], {k:rk[k]['avg_launch_us'] for k in ('rollout','mlp_update','gae') if k in rk}, d.get('e2e',{}).get('value'))
+PY

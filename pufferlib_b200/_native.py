@@ -32,6 +32,11 @@ class AdamTensor(C.Structure):
                 ('grad', C.c_void_p), ('numel', C.c_int64)]
 
 
+class HeadPack(C.Structure):
+    _fields_ = [('w_dec', C.c_void_p), ('b_dec', C.c_void_p), ('w_val', C.c_void_p), ('b_val', C.c_void_p),
+                ('w_cat', C.c_void_p), ('b_cat', C.c_void_p), ('n_act', C.c_int32), ('hid', C.c_int32)]
+
+
 class PeerComm(C.Structure):
     _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('base', C.c_void_p * 8), ('epoch', C.c_void_p),
                 ('capacity', C.c_int64)]
@@ -99,7 +104,8 @@ SIGNATURES = {
                                     C.c_float, C.c_float, C.c_void_p, C.POINTER(PeerComm), C.c_void_p, C.c_int64,
                                     C.c_void_p]),
     'pb_clip_adam_parts': (C.c_int, [C.POINTER(AdamTensor), C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_float,
-                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+                                     C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(HeadPack),
+                                     C.c_void_p]),
     'pb_peer_allreduce_parts': (C.c_int, [C.POINTER(PeerComm), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'pb_peer_slices': (C.c_int32, []),
     'pb_mlp_update_sumsq_offset': (C.c_size_t, []),

@@ -270,6 +270,7 @@ class _DefaultMLPUpdate:
         # NCCL all-reduce is only the fallback when peer mapping is unavailable (config.peer_allreduce=False, or IPC failed)
         self.peer = None
         self.peer_parts = None
+        self.head_pack = None
         if self.world > 1 and bool(getattr(data.config, 'peer_allreduce', True)):
             from pufferlib_b200.distributed import PeerComm
             ok = torch.ones(1, device=dev)
@@ -427,7 +428,14 @@ class _DefaultMLPUpdate:
                 _native.check(lib.pb_peer_allreduce_parts(C.byref(self.peer.struct), _native.ptr(self.gflat), self.gflat.numel(),
                                                           _native.ptr(self.peer_parts), _native.stream_ptr()))
                 parts, n_parts, epoch = _native.ptr(self.peer_parts), lib.pb_peer_slices(), _native.ptr(self.peer.epoch)
-            _native.check(lib.pb_clip_adam_parts(self.tensors, len(self.tensors), *hyper, parts, n_parts, epoch, _native.stream_ptr()))
+            m = self.model
+            if self.head_pack is None:      # the head matrix is rebuilt by the last CTA of the optimizer kernel
+                self.head_pack = _native.HeadPack(m.decoder.weight.data_ptr(), m.decoder.bias.data_ptr(), m.value_head.weight.data_ptr(),
+                                                  m.value_head.bias.data_ptr(), self.w_cat.data_ptr(), self.b_cat.data_ptr(),
+                                                  self.n_act, self.hid)
+            _native.check(lib.pb_clip_adam_parts(self.tensors, len(self.tensors), *hyper, parts, n_parts, epoch,
+                                                 C.byref(self.head_pack), _native.stream_ptr()))
+            return
         else:
             _native.check(lib.pb_clip_adam_peer(
                 self.tensors, len(self.tensors), *hyper, C.byref(self.peer.struct) if self.peer is not None else None,

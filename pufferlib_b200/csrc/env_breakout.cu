@@ -285,6 +285,7 @@ __device__ __forceinline__ void ro_write_obs(uint8_t* tile, int r, int px, int b
     }
 }
 
+template <bool DBG>      // DBG: step-0 dumps for the validation hook (pb_rollout_debug_buffers); compiled out of the product path
 __global__ void __launch_bounds__(RO_THREADS, 1)
 k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_constant__ CUtensorMap map_carry,
                    const __grid_constant__ CUtensorMap map_w, const RolloutParams p) {
@@ -396,13 +397,13 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
                     const float rh = fmaxf(v[k] + c_ro_benc[32 * c + k], 0.f);
-                    if (p.dbg_hidden && t == 0) p.dbg_hidden[(int64_t)e * 128 + 32 * c + k] = rh;
+                    if (DBG && p.dbg_hidden && t == 0) p.dbg_hidden[(int64_t)e * 128 + 32 * c + k] = rh;
 #pragma unroll
                     for (int a = 0; a < RO_HEADS; ++a) out[a] = fmaf(rh, c_ro_wh[a * 128 + 32 * c + k], out[a]);   // rows >= 5: zero padding
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (p.dbg_out && t == 0)
+            if (DBG && p.dbg_out && t == 0)
 #pragma unroll
                 for (int a = 0; a < 8; ++a) p.dbg_out[(int64_t)e * 8 + a] = out[a];
             // sample_logits (frameworks/cleanrl.py:25-47) by inverse CDF -- the arithmetic of k_policy_mlp_sample, with the
@@ -631,10 +632,12 @@ extern "C" int pb_rollout_breakout_mlp(pb_env* env, int32_t horizon, float* obs,
     PB_CUDA(cudaMemcpyToSymbolAsync(c_ro_bh, b_heads, sizeof(float) * 8, 0, cudaMemcpyDeviceToDevice, s));
     static bool attr_set = false;
     if (!attr_set) {
-        PB_CUDA(cudaFuncSetAttribute(k_breakout_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, RO_SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_breakout_rollout<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RO_SMEM_TOTAL));
+        PB_CUDA(cudaFuncSetAttribute(k_breakout_rollout<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RO_SMEM_TOTAL));
         attr_set = true;
     }
-    k_breakout_rollout<<<n / RO_ENVS, RO_THREADS, RO_SMEM_TOTAL, s>>>(map_obs, map_carry, map_w, p);
+    if (p.dbg_hidden || p.dbg_out) k_breakout_rollout<true><<<n / RO_ENVS, RO_THREADS, RO_SMEM_TOTAL, s>>>(map_obs, map_carry, map_w, p);
+    else k_breakout_rollout<false><<<n / RO_ENVS, RO_THREADS, RO_SMEM_TOTAL, s>>>(map_obs, map_carry, map_w, p);
     PB_LAUNCH_CHECK();
     k_counter_add<<<1, 1, 0, s>>>(counter_dev, (uint64_t)horizon);
     PB_LAUNCH_CHECK();

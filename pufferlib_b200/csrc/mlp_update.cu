@@ -83,6 +83,9 @@ struct FusedParams {
     float* dbg_hidden;         // nullable [m][128]
     float* dbg_dpre;           // nullable [m][128]
     float* dbg_dout;           // nullable [m][8]
+    const float* w_heads;      // [8][128], b_enc [128], b_heads [8] in global memory (variant 2 reads them directly)
+    const float* b_enc;
+    const float* b_heads;
     long long* dbg_clk;        // profiling only: [grid][18 warps][4 tiles][8 events] SM clock stamps of tiles 8..11 (variant 2)
     int skip;                  // profiling only (env PB_MUF_SKIP): bit 0 head FFMAs, 1 loss math, 2 dPre FFMAs, 3 mma.sync + staging,
                                // 4 dPre stores / chunk hand-off, 5 column sums, 6 partner exchange
@@ -823,7 +826,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     // number 15, whose row r holds a 1 at column r - 4s.  MMA k reads from (15 - k) core matrices in: row group k of A sees
     // the identity block, every other row group zeros.
     for (int i = threadIdx.x; i < 8192 / 16; i += X2_THREADS) reinterpret_cast<uint4*>(smem + X2_ID)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x < HID) reinterpret_cast<float*>(smem + X2_BE)[threadIdx.x] = c_benc[threadIdx.x];
+    if (threadIdx.x < HID) reinterpret_cast<float*>(smem + X2_BE)[threadIdx.x] = p.b_enc[threadIdx.x];
     __syncthreads();
     if (threadIdx.x < 8) {
         const int r = threadIdx.x;
@@ -940,15 +943,15 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         uint32_t hb[4][2], ga[2][4];
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
-            hb[kb][0] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + 2 * t]);
-            hb[kb][1] = to_tf32(c_wh[g * HID + 32 * c + 8 * kb + 2 * t + 1]);
+            hb[kb][0] = to_tf32(p.w_heads[g * HID + 32 * c + 8 * kb + 2 * t]);
+            hb[kb][1] = to_tf32(p.w_heads[g * HID + 32 * c + 8 * kb + 2 * t + 1]);
         }
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
-            ga[mb][0] = to_tf32(c_wh[t * HID + 32 * c + 16 * mb + g]);
-            ga[mb][1] = to_tf32(c_wh[t * HID + 32 * c + 16 * mb + g + 8]);
-            ga[mb][2] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g]);
-            ga[mb][3] = to_tf32(c_wh[(t + 4) * HID + 32 * c + 16 * mb + g + 8]);
+            ga[mb][0] = to_tf32(p.w_heads[t * HID + 32 * c + 16 * mb + g]);
+            ga[mb][1] = to_tf32(p.w_heads[t * HID + 32 * c + 16 * mb + g + 8]);
+            ga[mb][2] = to_tf32(p.w_heads[(t + 4) * HID + 32 * c + 16 * mb + g]);
+            ga[mb][3] = to_tf32(p.w_heads[(t + 4) * HID + 32 * c + 16 * mb + g + 8]);
         }
         // addresses inside the warp's part of the dPre block (see g_off), hoisted out of the tile loop
         uint8_t* const st_row = mine + ((lane & 3) << 2);       // thread = row: element (hidden unit k, row lane) at k * 128 + piece ((lane >> 2) ^ (k & 7))
@@ -961,7 +964,7 @@ k_mlp_update_xt(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 
         // the loss: warp c evaluates rows 8c..8c+7 of the quadrant, four lanes per row (ppo_row_sub)
         const int lr = 8 * c + (lane >> 2), sub = lane & 3;
-        const float bh_lo = c_bh[sub], bh_hi = c_bh[sub + 4];
+        const float bh_lo = p.b_heads[sub], bh_hi = p.b_heads[sub + 4];
         // per-row scalars of the loss rows, loaded ONE TILE AHEAD with volatile loads issued right after the second barrier
         // (plain loads get sunk to their first use by the compiler, which puts their HBM latency back on the critical path)
         struct RowIn { int act; float old_lp, adv, ret, old_v; bool valid; };
@@ -1344,11 +1347,14 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
         p.skip = sk ? atoi(sk) : 0;
     }
     p.dbg_clk = g_dbg_clk;
+    p.w_heads = w_heads; p.b_enc = b_enc; p.b_heads = b_heads;
     p.stats = stats8; p.dpre_out = dpre_out; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
     PB_CUDA(cudaMemsetAsync(stats8, 0, 8 * sizeof(double), s));
-    PB_CUDA(cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s));
-    PB_CUDA(cudaMemcpyToSymbolAsync(c_benc, b_enc, sizeof(float) * HID, 0, cudaMemcpyDeviceToDevice, s));
-    PB_CUDA(cudaMemcpyToSymbolAsync(c_bh, b_heads, sizeof(float) * NO, 0, cudaMemcpyDeviceToDevice, s));
+    if (dpre_out || g_update_variant != 2) {      // variant 1 takes the small operands from the constant bank
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_wh, w_heads, sizeof(float) * NO * HID, 0, cudaMemcpyDeviceToDevice, s));
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_benc, b_enc, sizeof(float) * HID, 0, cudaMemcpyDeviceToDevice, s));
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_bh, b_heads, sizeof(float) * NO, 0, cudaMemcpyDeviceToDevice, s));
+    }
     // dispatch on the live head rows (n_act + 1: 5 for the 4-action configs, 8 = generic) and on where dW_enc is formed
     static bool attr_set = false;
     if (!attr_set) {

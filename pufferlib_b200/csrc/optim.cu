@@ -104,7 +104,8 @@ constexpr int CAP_THREADS = 256, CAP_BLOCKS = 32;
 __device__ unsigned int g_cap_ticket = 0;
 
 __global__ void __launch_bounds__(CAP_THREADS) k_clip_adam_parts(AdamArgs a, const double* __restrict__ parts, int n_parts,
-                                                                unsigned long long* peer_epoch) {
+                                                                unsigned long long* peer_epoch, pb_head_pack pack) {
+    __shared__ int s_last;
     __shared__ double s_red[CAP_THREADS / 32];
     __shared__ float s_coef;
     __shared__ float s_step_size[CA_MAX_TENSORS], s_bc2_sqrt[CA_MAX_TENSORS], s_new_step[CA_MAX_TENSORS];
@@ -161,11 +162,21 @@ __global__ void __launch_bounds__(CAP_THREADS) k_clip_adam_parts(AdamArgs a, con
     if (tid == 0) {
         __threadfence();
         const unsigned int t = atomicAdd(&g_cap_ticket, 1u);
-        if (t == gridDim.x - 1) {        // every CTA has read the step counters (and the peer epoch is no longer in use)
+        s_last = t == gridDim.x - 1;
+        if (s_last) {                    // every CTA has read the step counters (and the peer epoch is no longer in use)
             for (int k = 0; k < a.n; ++k) *a.t[k].step = s_new_step[k];
             if (peer_epoch) *peer_epoch += 1ull;
             g_cap_ticket = 0;
         }
+    }
+    __syncthreads();
+    if (s_last && pack.w_cat) {          // the last CTA sees every CTA's parameter updates: rebuild the 8-row head matrix (pb_pack_heads)
+        __threadfence();
+        for (int j = tid; j < 8 * pack.hid; j += CAP_THREADS) {
+            const int r = j / pack.hid, c = j % pack.hid;
+            pack.w_cat[j] = r < pack.n_act ? pack.w_dec[(int64_t)r * pack.hid + c] : (r == pack.n_act ? pack.w_val[c] : 0.f);
+        }
+        if (tid < 8) pack.b_cat[tid] = tid < pack.n_act ? pack.b_dec[tid] : (tid == pack.n_act ? pack.b_val[0] : 0.f);
     }
 }
 
@@ -247,7 +258,8 @@ extern "C" int pb_clip_adam_peer(const pb_adam_tensor* tensors, int32_t n_tensor
 // peer_epoch (nullable): the communicator's epoch counter, advanced here after pb_peer_allreduce_parts.
 extern "C" int pb_clip_adam_parts(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale,
                                   float lr, const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
-                                  const double* sumsq_parts, int32_t n_parts, unsigned long long* peer_epoch, void* stream) {
+                                  const double* sumsq_parts, int32_t n_parts, unsigned long long* peer_epoch,
+                                  const pb_head_pack* pack, void* stream) {
     PB_REQUIRE(tensors && n_tensors >= 1 && n_tensors <= CA_MAX_TENSORS && sumsq_parts && n_parts >= 1, PB_ERR_INVALID,
                "pb_clip_adam_parts: bad arguments");
     AdamArgs a{};
@@ -268,7 +280,14 @@ extern "C" int pb_clip_adam_parts(const pb_adam_tensor* tensors, int32_t n_tenso
     a.beta2 = beta2;
     a.eps = eps;
     a.total_norm_out = total_norm_out;
-    k_clip_adam_parts<<<CAP_BLOCKS, CAP_THREADS, 0, (cudaStream_t)stream>>>(a, sumsq_parts, n_parts, peer_epoch);
+    pb_head_pack hp{};
+    if (pack) {
+        PB_REQUIRE(pack->w_dec && pack->b_dec && pack->w_val && pack->b_val && pack->w_cat && pack->b_cat && pack->n_act >= 1 &&
+                       pack->n_act <= 7 && pack->hid >= 1,
+                   PB_ERR_INVALID, "pb_clip_adam_parts: bad head-pack arguments");
+        hp = *pack;
+    }
+    k_clip_adam_parts<<<CAP_BLOCKS, CAP_THREADS, 0, (cudaStream_t)stream>>>(a, sumsq_parts, n_parts, peer_epoch, hp);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }

@@ -80,7 +80,7 @@ def test_clip_adam_parts_matches_single_cta_kernel(world, n_parts):
             hyper = (C.c_float(0.5), C.c_float(1.0 / world), C.c_float(2.5e-4), None, C.c_float(0.9), C.c_float(0.999),
                      C.c_float(1e-5), _native.ptr(norm))
             if use_parts:
-                _native.check(lib.pb_clip_adam_parts(arr, 6, *hyper, _native.ptr(parts), n_parts, None, _native.stream_ptr()))
+                _native.check(lib.pb_clip_adam_parts(arr, 6, *hyper, _native.ptr(parts), n_parts, None, None, _native.stream_ptr()))
             else:
                 _native.check(lib.pb_clip_adam(arr, 6, *hyper, _native.stream_ptr()))
         torch.cuda.synchronize()
