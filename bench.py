@@ -146,6 +146,8 @@ def timed_steps(data, cp, steps, world):
     for _ in range(steps):
         cp.evaluate(data)
         cp.train(data)
+    if getattr(data.vecenv, 'host_buffers', False):
+        data.vecenv.host_sync()      # e2e: every device->host copy of the timed steps has landed before the clock stops
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')

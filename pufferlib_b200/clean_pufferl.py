@@ -889,8 +889,11 @@ def _rollout_loop(data, infos):
                 a_host = actions.cpu().numpy()
                 io.d2h += a_host.nbytes
                 vecenv.send(a_host)
-    if device_feed:
-        vecenv.host_sync()       # every device->host copy of the rollout has landed (part of the e2e timed region)
+    if device_feed and not bool(getattr(config, 'host_copy_defer', True)):
+        vecenv.host_sync()       # every device->host copy of the rollout has landed
+    # (default: the observation blocks keep streaming to the pinned host arrays while train() runs -- it only reads the
+    #  rollout tensors; the next rollout's first write waits for them on the device, and any host-side reader (recv(),
+    #  host_sync(), close()) waits for them as before)
     if hasattr(vecenv, 'join'):
         vecenv.join()            # pool mode: side-stream env steps rejoin the caller's stream (and any graph capture)
 

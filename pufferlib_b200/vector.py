@@ -310,6 +310,10 @@ class B200:
                 lo, hi = t * n, (t + 1) * n
                 if self._pending_own:   # carry-over rows (reset, or the step that closed the previous rollout)
                     lib = _native.lib()
+                    if self.host_buffers and self._host_pending:
+                        # copies of the previous rollout's rows may still be streaming to the host (host_defer): the first
+                        # write into the rollout tensors waits for them on the device, the host does not block
+                        torch.cuda.current_stream().wait_event(self._ev_copy)
                     _native.check(lib.pb_copy_rows(_native.ptr(b.observations), self.obs_bytes,
                                                    C.c_void_p(x.obs.data_ptr() + lo * self.obs_bytes),
                                                    self.obs_bytes, self.obs_bytes, n, _native.stream_ptr()))
@@ -350,7 +354,14 @@ class B200:
 
     def actions_to_host(self, actions):
         """Device actions -> the pinned host action array (async, on the caller's stream); valid after host_sync()."""
-        self._host.actions.copy_(actions.reshape(-1), non_blocking=True)
+        # a kernel store into the pinned (UVA-mapped) host array, not a DMA copy: the copy engine is busy with the 8 MB
+        # observation blocks of this and earlier steps, and a 128 KB cudaMemcpyAsync would queue behind them (150 us per step)
+        a = actions.reshape(-1)
+        if a.dtype != torch.int64 or not a.is_contiguous():
+            a = a.to(torch.int64).contiguous()
+        nbytes = 8 * a.numel()
+        _native.check(_native.lib().pb_copy_rows(_native.ptr(a), nbytes, C.c_void_p(self._host.actions.data_ptr()), nbytes, nbytes, 1,
+                                                 _native.stream_ptr()))
         self._ev_act.record()
         self._act_pending = True
         self.d2h_bytes += 8 * self.num_agents
