@@ -871,6 +871,10 @@ def _rollout_loop(data, infos):
                 a_host = vecenv.actions_to_host(actions)
                 if getattr(vecenv, 'exact_infos', False) or vecenv._rollout is None:
                     info = vecenv.host_sync()[4]          # per-step info dicts need the terminal flags on the host
+                elif torch.cuda.is_current_stream_capturing():
+                    # captured rollout (host_graph): the action round trip device -> pinned host array -> device is stream-ordered
+                    # inside the graph (store kernel, then the H2D copy node of send()); the host is not in the loop
+                    info = []
                 else:
                     # nothing on the host side reads this step's observations: wait for the actions only and let the big
                     # copies stream behind (each reads its own rollout row); they are awaited when the rollout ends
@@ -889,7 +893,9 @@ def _rollout_loop(data, infos):
                 a_host = actions.cpu().numpy()
                 io.d2h += a_host.nbytes
                 vecenv.send(a_host)
-    if device_feed and not bool(getattr(config, 'host_copy_defer', True)):
+    if device_feed and torch.cuda.is_current_stream_capturing():
+        vecenv.join_copies()     # the copy stream rejoins the captured stream: the graph ends when every host copy has landed
+    elif device_feed and not bool(getattr(config, 'host_copy_defer', True)):
         vecenv.host_sync()       # every device->host copy of the rollout has landed
     # (default: the observation blocks keep streaming to the pinned host arrays while train() runs -- it only reads the
     #  rollout tensors; the next rollout's first write waits for them on the device, and any host-side reader (recv(),
@@ -913,8 +919,13 @@ def evaluate(data):
     vecenv = data.vecenv
     on_device = not getattr(vecenv, 'host_buffers', False)
     _invalidate_policy_cache(data)          # parameters may have changed since the last rollout
-    use_graph = bool(getattr(config, 'cuda_graph_rollout', getattr(config, 'cuda_graph', False))) and on_device and \
-        not getattr(vecenv, 'exact_infos', False)
+    # host_buffers mode: the loop is capturable when nothing on the host reads a step while it runs (no per-step info dicts,
+    # rollout rows bound): every env step still moves its observation block to the pinned host arrays and takes its actions
+    # from the pinned host action array, as copy nodes of the graph
+    host_graph = not on_device and hasattr(vecenv, 'recv_device') and getattr(vecenv, '_rollout', None) is not None and \
+        bool(getattr(config, 'cuda_graph_host_rollout', True))
+    use_graph = bool(getattr(config, 'cuda_graph_rollout', getattr(config, 'cuda_graph', False))) and \
+        (on_device or host_graph) and not getattr(vecenv, 'exact_infos', False)
 
     if not use_graph or data.graph_state == 0:
         _rollout_loop(data, infos)
@@ -924,11 +935,20 @@ def evaluate(data):
         if data.graph_state == 1:
             torch.cuda.synchronize()
             step0, launches0 = data.global_step, _native.lib().pb_launch_count()
+            io0 = (data.io.h2d + getattr(vecenv, 'h2d_bytes', 0), data.io.d2h + getattr(vecenv, 'd2h_bytes', 0))
             _invalidate_policy_cache(data)       # anything cached eagerly must be rebuilt inside the capture
+            if not on_device:
+                vecenv.host_sync()               # outstanding eager copies (their events are not part of the capture)
+                vecenv.graph_mode = True
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 _rollout_loop(data, infos)       # python-side state advances exactly as in an eager rollout
             data.rollout_graph = graph
+            # host <-> device bytes one replay moves (the byte counters only advance while Python runs the loop)
+            data.graph_io = (data.io.h2d + getattr(vecenv, 'h2d_bytes', 0) - io0[0], data.io.d2h + getattr(vecenv, 'd2h_bytes', 0) - io0[1])
+            if not on_device:
+                vecenv.h2d_bytes -= data.graph_io[0]     # capture executes nothing: the replay below adds them back
+                vecenv.d2h_bytes -= data.graph_io[1]
             data.graph_steps = data.global_step - step0
             data.graph_launches = _native.lib().pb_launch_count() - launches0
             data.graph_state = 2
@@ -937,6 +957,9 @@ def evaluate(data):
             data.rollout_graph.replay()
         data.global_step += data.graph_steps
         data.graph_replays += 1
+        if not on_device:
+            vecenv.h2d_bytes += data.graph_io[0]
+            vecenv.d2h_bytes += data.graph_io[1]
         experience.ptr = experience.batch_size    # what the captured loop leaves behind
         experience.step = experience.batch_size // experience.num_envs
 

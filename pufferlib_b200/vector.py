@@ -220,6 +220,7 @@ class B200:
                 self._copy_stream = torch.cuda.Stream()
                 self._ev_step, self._ev_copy, self._ev_act = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
             self._host_pending = False
+            self.graph_mode = False
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -310,7 +311,7 @@ class B200:
                 lo, hi = t * n, (t + 1) * n
                 if self._pending_own:   # carry-over rows (reset, or the step that closed the previous rollout)
                     lib = _native.lib()
-                    if self.host_buffers and self._host_pending:
+                    if self.host_buffers and self._host_pending and not self.graph_mode:
                         # copies of the previous rollout's rows may still be streaming to the host (host_defer): the first
                         # write into the rollout tensors waits for them on the device, the host does not block
                         torch.cuda.current_stream().wait_event(self._ev_copy)
@@ -367,22 +368,36 @@ class B200:
         self.d2h_bytes += 8 * self.num_agents
         return self._host_np.actions
 
+    def join_copies(self):
+        """Inside a stream capture: the copy stream's work becomes a predecessor of whatever the caller's stream does next
+        (the captured graph then ends only when every host copy has landed)."""
+        torch.cuda.current_stream().wait_event(self._ev_copy)
+
     def host_sync(self, actions_only=False):
         """Wait for the step's device->host copies (and an outstanding actions_to_host); returns what recv() returns in
         host_buffers mode: pinned numpy arrays + the info dicts.  actions_only: wait for the action copy alone -- the
         observation / reward / flag copies keep streaming on the copy stream (they are ordered among themselves, each reads
         its own rollout row) and are awaited by the next full host_sync(); for callers that do not read them every step."""
-        if actions_only:
+        if self.graph_mode:
+            # the rollout runs as a captured graph whose last node joins the copy stream: the caller's stream is the one
+            # thing to wait for (events recorded during a capture cannot be waited on from the host)
+            if not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream().synchronize()
+            self._host_pending = self._act_pending = False
+            if actions_only:
+                return None
+        elif actions_only:
             if getattr(self, '_act_pending', False):
                 self._ev_act.synchronize()
                 self._act_pending = False
             return None
-        if self._host_pending:
-            self._ev_copy.synchronize()
-            self._host_pending = False
-        if getattr(self, '_act_pending', False):
-            self._ev_act.synchronize()
-            self._act_pending = False
+        else:
+            if self._host_pending:
+                self._ev_copy.synchronize()
+                self._host_pending = False
+            if getattr(self, '_act_pending', False):
+                self._ev_act.synchronize()
+                self._act_pending = False
         hn = self._host_np
         # the terminal flags are on the host already: no second D2H for the info dicts
         infos = self._collect_infos(hn.terminals) if self.exact_infos else []

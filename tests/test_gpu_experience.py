@@ -183,12 +183,12 @@ def test_evaluate_train_loop_eager_graph_and_host_modes():
     from pufferlib_b200.frameworks import cleanrl
     from oracle.squared import SquaredSerial
     n, h = 64, 32
-    for mode in ('eager', 'graph', 'host'):
-        backend = pvec.B200.options(host_buffers=(mode == 'host'))
+    for mode in ('eager', 'graph', 'host', 'host_graph'):
+        backend = pvec.B200.options(host_buffers=mode.startswith('host'))
         vec = pvec.make(ocean.env_creator('squared'), num_envs=n, backend=backend)
         torch.manual_seed(0)
         pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=(mode != 'host'), seed=1).cuda()
-        data = clean_pufferl.create(make_config(n, h, cuda_graph=(mode == 'graph')), vec, pol)
+        data = clean_pufferl.create(make_config(n, h, cuda_graph=mode.endswith('graph')), vec, pol)
         ora = SquaredSerial(n)
         ora.async_reset(1)
         for it in range(3):                      # iteration 2 is the first graph replay
@@ -204,7 +204,14 @@ def test_evaluate_train_loop_eager_graph_and_host_modes():
             assert np.isfinite(data.losses.policy_loss) and np.isfinite(data.losses.value_loss)
             assert data.global_step == (it + 1) * n * h
             assert 'episode_return' in stats
-        if mode == 'graph':
+            if mode.startswith('host'):
+                # the pinned host arrays hold the step that closed the rollout, the action array the last actions sent
+                # (host_graph: every env step of the captured loop copies through them, no host code in between)
+                hobs = vec.host_sync()[0]
+                assert hobs.shape == (n, 7, 7) and np.isfinite(hobs).all()
+                assert np.array_equal(vec._host_np.actions, acts[-1])
+                assert vec.d2h_bytes >= (it + 1) * h * n * 49 and vec.h2d_bytes == (it + 1) * h * n * 8
+        if mode.endswith('graph'):
             assert data.graph_replays == 2 and data.graph_launches > 0
         clean_pufferl.close(data)
 
