@@ -185,7 +185,7 @@ def test_evaluate_train_loop_eager_graph_and_host_modes():
     n, h = 64, 32
     for mode in ('eager', 'graph', 'host', 'host_graph'):
         # (per-step info dicts need the host after every env step: the captured host loop runs with the device-side statistics)
-        backend = pvec.B200.options(host_buffers=mode.startswith('host'), exact_infos=(mode != 'host_graph'))
+        backend = pvec.B200.options(host_buffers=mode.startswith('host'), exact_infos=(False if mode == 'host_graph' else None))
         vec = pvec.make(ocean.env_creator('squared'), num_envs=n, backend=backend)
         torch.manual_seed(0)
         pol = cleanrl.Policy(models.Default(vec.driver_env), fused_sample=(mode != 'host'), seed=1).cuda()
