@@ -9,26 +9,22 @@
 //     pb_mlp_tail_backward(dOut, hidden) -> dPre, dW_heads, db_enc, db_heads      (csrc/mlp_tail.cu, reads hidden, writes dPre)
 //     dW_enc = dPre^T x                           (split-K cuBLAS GEMM, reads dPre and x)
 // which streams `hidden` / `dPre` through HBM five times (1.9 GB, ~350 us per minibatch).  Here the algorithmic traffic is
-// x once (268 MB) + 24 B of per-row scalars.
+// x once (268 MB) + 28 B of per-row scalars (ncu: 287 MB of DRAM traffic per launch).
 //
-// CTA = 192 threads, one per SM, persistent over 128-row tiles:
-//   warp 0      TMA producer: W_enc once, then x tiles (4 boxes of [128 rows][32 floats], SWIZZLE_128B) into a 2-stage ring
-//   warp 1      TMEM allocation + single-thread tcgen05.mma issue:
-//                 forward   h[128 rows][128 hid]  = x . W_enc^T       16 x (M128 N128 K8) kind::tf32, both operands K-major
-//                 backward  dW^T[128 feat][32 hid chunk] += x^T . dPre_chunk   16 x (M128 N32 K8), both operands MN-major:
-//                           A = the SAME x tile bytes the forward used (a K-major SW128 tile read as MN-major:
-//                           M = feature, K = row), B = the dPre chunk the epilogue warps wrote to shared memory
-//   warps 2..5  epilogue, thread = row (TMEM lane): tcgen05.ld h -> bias + ReLU -> heads (W_heads as constant-bank FFMA
-//               operands) -> the pb_ppo_loss row math -> dOut -> per 32-column chunk: dPre = (dOut . W_heads) * (h > 0)
-//               -> swizzled MN-major chunk in shared memory (generic stores + fence.proxy.async) for the dW UMMA;
-//               dW_heads by mma.sync on the warp's own rows (relu(h) chunk staged through the same buffer), db_enc by
-//               column sums of the staged dPre chunk, db_heads / statistics in registers.
-// TMEM: columns [0,256) two forward accumulators, [256,384) dW^T accumulator (lives across all tiles of the CTA).
-// Per-CTA partial results go to a workspace; k_update_reduce sums them deterministically into the flat gradient
-// buffer [dW_enc (hid x feat) | dW_heads (8 x hid) | db_enc | db_heads] of clean_pufferl._DefaultMLPUpdate.
+// Two kernels, the second one is the product path (pb_mlp_update_set_variant, default 2):
+//   k_mlp_update_fused (variant 1, and the dPre-to-HBM mode of both variants): every x tile is loaded twice, K-major for
+//       the forward product and MN-major (SWIZZLE_128B_BASE32B, the only MN-major layout the tensor core takes for 32-bit
+//       operands) for dW_enc^T = x^T dPre; thread-per-row epilogue with the head products as constant-bank FFMAs.  293 us.
+//   k_mlp_update_xt (variant 2): ONE x layout; x^T is formed on the tensor core by a "sliding identity" MMA into tensor
+//       memory and enters the dW product as a TS operand; the 64 KB that frees hold a whole tile of dPre; 16 epilogue warps
+//       do all per-element products on mma.sync fragments.  168-190 us.
+// Both: warp 0 TMA producer, warp 1 single-thread tcgen05.mma issue + TMEM allocation, the rest epilogue; the dW_enc^T
+// accumulator lives in TMEM across all tiles of a CTA; per-CTA partials go to a workspace and k_update_reduce sums them
+// deterministically into the flat gradient buffer [dW_enc (hid x feat) | dW_heads (8 x hid) | db_enc | db_heads] of
+// clean_pufferl._DefaultMLPUpdate, leaving per-block sums of squares for pb_clip_adam_parts.
 //
 // Descriptor encodings were validated on hardware with csrc/experimental/umma_probe.cu (tests/experimental/
-// check_umma_probe.py).  Every mbarrier wait is bounded (tma.cuh: __trap instead of a hang).
+// check_umma_probe.py, check_umma_transpose.py).  Every mbarrier wait is bounded (tma.cuh: __trap instead of a hang).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -87,8 +83,6 @@ struct FusedParams {
     const float* b_enc;
     const float* b_heads;
     long long* dbg_clk;        // profiling only: [grid][18 warps][4 tiles][8 events] SM clock stamps of tiles 8..11 (variant 2)
-    int skip;                  // profiling only (env PB_MUF_SKIP): bit 0 head FFMAs, 1 loss math, 2 dPre FFMAs, 3 mma.sync + staging,
-                               // 4 dPre stores / chunk hand-off, 5 column sums, 6 partner exchange
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -114,7 +108,6 @@ __device__ __forceinline__ uint64_t desc_mn32(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor: D fmt F32 (1<<4) | A TF32 (2<<7) | B TF32 (2<<10) | A major bit 15 | B major bit 16 | N>>3 <<17 | M>>4 <<24
 constexpr uint32_t IDESC_FWD = (1u << 4) | (2u << 7) | (2u << 10) | ((HID >> 3) << 17) | ((TILE_M >> 4) << 24);
-constexpr uint32_t IDESC_HEADS = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((TILE_M >> 4) << 24);
 constexpr uint32_t IDESC_DW = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((CHUNK_COLS >> 3) << 17) |
                               ((FEAT >> 4) << 24);
 
@@ -136,21 +129,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
-        "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])),
-        "r"(__float_as_uint(r[8])), "r"(__float_as_uint(r[9])), "r"(__float_as_uint(r[10])), "r"(__float_as_uint(r[11])),
-        "r"(__float_as_uint(r[12])), "r"(__float_as_uint(r[13])), "r"(__float_as_uint(r[14])), "r"(__float_as_uint(r[15])),
-        "r"(__float_as_uint(r[16])), "r"(__float_as_uint(r[17])), "r"(__float_as_uint(r[18])), "r"(__float_as_uint(r[19])),
-        "r"(__float_as_uint(r[20])), "r"(__float_as_uint(r[21])), "r"(__float_as_uint(r[22])), "r"(__float_as_uint(r[23])),
-        "r"(__float_as_uint(r[24])), "r"(__float_as_uint(r[25])), "r"(__float_as_uint(r[26])), "r"(__float_as_uint(r[27])),
-        "r"(__float_as_uint(r[28])), "r"(__float_as_uint(r[29])), "r"(__float_as_uint(r[30])), "r"(__float_as_uint(r[31]))
         : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&r)[8]) {
@@ -280,11 +258,6 @@ __device__ __forceinline__ RowStats ppo_row(const float (&zin)[8], const FusedPa
     s.pg = pg; s.v = vl; s.ent = ent; s.okl = -logratio; s.kl = (ratio - 1.f) - logratio;
     s.clipped = fabsf(ratio - 1.f) > p.clip ? 1.f : 0.f;
     return s;
-}
-
-// byte offset of element (row r, column j) of a [128 rows][32 floats] SWIZZLE_128B chunk
-__device__ __forceinline__ uint32_t chunk_off(int r, int j) {
-    return (uint32_t)(r * 128 + ((((j >> 2) ^ (r & 7))) << 4) + ((j & 3) << 2));
 }
 
 // NH = live rows of the 8-row head matrix (n_act logits + the value): rows >= NH are zero padding, their products are skipped
@@ -464,7 +437,6 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 float v[32];
                 if (hh == 0) {      // (compile-time column offsets: every c_wh / c_benc operand is a constant-bank immediate)
                     tmem_ld32(taddr + 32 * cc, v);
-                    if (!(p.skip & 1))
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const float rh = fmaxf(v[k] + c_benc[32 * cc + k], 0.f);
@@ -473,7 +445,6 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     }
                 } else {
                     tmem_ld32(taddr + 64 + 32 * cc, v);
-                    if (!(p.skip & 1))
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const float rh = fmaxf(v[k] + c_benc[64 + 32 * cc + k], 0.f);
@@ -482,14 +453,14 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                     }
                 }
             }
-            if (!(p.skip & 64)) {
+            {
             tmem_st8(xchg + 8 * hh, out);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // the two warps of quadrant q
             tc_fence_after();
             }
-            if (!(p.skip & 64)) {
+            {
                 float other[NO];
                 tmem_ld8(xchg + 8 * (hh ^ 1), other);
 #pragma unroll
@@ -501,7 +472,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
             float dO[NO];
 #pragma unroll
             for (int a = 0; a < NO; ++a) dO[a] = 0.f;
-            if (valid && !(p.skip & 2)) {
+            if (valid) {
                 const RowStats rs = ppo_row(out, p, act, old_lp, adv, ret, old_v, dO);
                 if (hh == 0) {
                     st[0] += rs.pg; st[1] += rs.v; st[2] += rs.ent; st[3] += rs.okl; st[4] += rs.kl; st[5] += rs.clipped;
@@ -538,10 +509,7 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 float v[32], dp[32];
                 const int col0 = 64 * hh + 32 * cc;           // first hidden unit of the chunk (hh is warp-uniform)
                 tmem_ld32(taddr + col0, v);
-                if (p.skip & 4) {
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) dp[k] = v[k];
-                } else if (hh == 0) {
+                if (hh == 0) {
 #pragma unroll
                     for (int k = 0; k < 32; ++k) {
                         const float pre = v[k] + c_benc[32 * cc + k];
@@ -569,14 +537,14 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                         *reinterpret_cast<float4*>(p.dbg_dpre + i * HID + col0 + k) = make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]);
                     }
                 }
-                if (!DW_KERNEL && valid && !(p.skip & 16)) {    // dPre row segment to HBM (128 contiguous bytes per thread)
+                if (!DW_KERNEL && valid) {    // dPre row segment to HBM (128 contiguous bytes per thread)
 #pragma unroll
                     for (int k = 0; k < 32; k += 4)
                         __stcs(reinterpret_cast<float4*>(p.dpre_out + i * HID + col0 + k), make_float4(dp[k], dp[k + 1], dp[k + 2], dp[k + 3]));
                 }
                 if (DW_KERNEL) mbar_wait(&dp_empty[hh], (uint32_t)(((it * 2 + cc) & 1) ^ 1));   // last use of the buffer consumed
                 // relu(h) chunk of this warp's 32 rows (TF32-rounded) -> B fragments of the dW_heads mma
-                if (!(p.skip & 8)) {
+                {
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                     uint8_t* dst = buf + rloc * 128 + ((j8 ^ (rloc & 3)) << 5);
@@ -608,14 +576,13 @@ k_mlp_update_fused(const __grid_constant__ CUtensorMap map_x, const __grid_const
                 if (DW_KERNEL && lane == 0) mbar_arrive(&dp_full[hh]);
                 // db_enc: column sums over this warp's rows (the UMMA only reads the buffer)
                 float cs = 0.f;
-                if (!(p.skip & 32))
 #pragma unroll 8
                 for (int r = 0; r < 32; ++r) cs += *reinterpret_cast<const float*>(buf + chunk32_off(32 * q + r, lane));
                 acc_benc[cc] += cs;
                 __syncwarp();                                    // (mode without UMMA: the next chunk overwrites the rows)
             }
             tc_fence_before();
-            if (!(p.skip & 64)) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both warps are done with the exchange columns
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");     // both warps are done with the exchange columns
             __syncwarp();
             if (lane == 0) mbar_arrive(&h_empty[s]);
         }
@@ -777,11 +744,9 @@ __device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo_bytes
            (1ull << 46);
 }
 
-// byte offset of element (hidden unit n, tile row l of the quadrant) inside a warp's part of dPre block q: K-major
-// SWIZZLE_128B, n = MN row of 128 B, the 32 rows of the quadrant along K
-__device__ __forceinline__ uint32_t g_off(int n, int l) {
-    return (uint32_t)(n * 128 + ((((l >> 2) ^ (n & 7))) << 4) + ((l & 3) << 2));
-}
+// Layout of a dPre block (K-major SWIZZLE_128B, [128 hidden units][32 rows of the quadrant]): element (hidden unit n, row l)
+// sits at byte  n * 128 + (((l >> 2) ^ (n & 7)) << 4) + ((l & 3) << 2)  -- hidden unit n = MN row of 128 B, the quadrant's rows
+// along K in 16-byte pieces XORed with n & 7.  The epilogue's addresses (st_row, ha_base, wb_base) are instances of it.
 
 // mma.sync m16n8k8 TF32 with all four A registers: a0 (g, t)  a1 (g + 8, t)  a2 (g, t + 4)  a3 (g + 8, t + 4);
 // b0 (k = t, n = g)  b1 (k = t + 4, n = g);  c0 c1 (g, 2t + {0,1})  c2 c3 (g + 8, 2t + {0,1})      [g = lane >> 2, t = lane & 3]
@@ -1342,10 +1307,6 @@ extern "C" int pb_mlp_update_fused(const float* x, int64_t ldx, int64_t slab_row
     p.tiles_per_slab = (int)tiles_per_slab; p.n_tiles = (int)n_tiles; p.n_act = n_act;
     p.clip = clip_coef; p.vclip = vf_clip_coef; p.vf_coef = vf_coef; p.ent_coef = ent_coef; p.clip_vloss = clip_vloss;
     p.part_dw = (float*)workspace; p.part_tail = (float*)workspace + (size_t)num_sms() * FEAT * HID;
-    {
-        const char* sk = getenv("PB_MUF_SKIP");      // profiling only: skip phases of the epilogue (results are then wrong)
-        p.skip = sk ? atoi(sk) : 0;
-    }
     p.dbg_clk = g_dbg_clk;
     p.w_heads = w_heads; p.b_enc = b_enc; p.b_heads = b_heads;
     p.stats = stats8; p.dpre_out = dpre_out; p.dbg_hidden = dbg_hidden; p.dbg_dpre = dbg_dpre; p.dbg_dout = dbg_dout;
