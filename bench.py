@@ -73,7 +73,9 @@ def ppo_config(num_envs, horizon, device, seed=1, cuda_graph=True, minibatches=4
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the start of the timed region; when that region is shorter
+    than ~0.6 s (K steps of 3.6 ms) the same steps keep running, untimed, until at least that long has been sampled under load
+    (`window` in the JSON says so)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -85,7 +87,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -98,7 +100,7 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.25)
+        time.sleep(0.06)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -430,7 +432,19 @@ def run_b200(args):
     launches = ((_native.lib().pb_launch_count() - launches0) + (data.graph_replays - replays0) * data.graph_launches
                 + (data.train_graph_replays - treplays0) * data.train_graph_launches
                 + (getattr(data.train_segments, 'replayed_launches', 0) - seg0))
+    # clocks under load: keep the same steps running (untimed) until the sampler has had 0.6 s of them
+    # (the count comes from the rank-maximum step time, so every rank runs the same number of exchanges)
+    extra = max(0, int(np.ceil((600.0 - ms) / max(ms / args.steps, 1e-3)))) if ms < 600.0 else 0
+    extra = min(extra, 2000)
+    for i in range(extra):
+        cp.evaluate(data)
+        cp.train(data)
+        if i % 8 == 7:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     clk = clocks.stop() if rank == 0 else None
+    if clk is not None:
+        clk['window'] = f'{args.steps} timed steps' + (f' + {extra} more of the same steps, untimed' if extra else '')
     value = world * n * h * args.steps / (ms * 1e-3)
     prof = {k: round(v, 4) for k, v in dict(data.profile).items() if k.endswith('_time')}
     stats = {k: float(v) for k, v in data.stats.items()}

@@ -1,5 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
 run() { name=$1; t=$2; shift 2; ( timeout $t "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?" >> gpurun_out/$name.log ); echo "== $name: $(tail -1 gpurun_out/$name.log)"; }
-run t_host 400 python -m pytest tests/test_gpu_experience.py -x -q
-tail -15 gpurun_out/t_host.log | cut -c1-200
+run t_all 1200 python -m pytest tests -m gpu -x -q
+tail -5 gpurun_out/t_all.log
+run smoke 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
+tail -2 gpurun_out/smoke.log
+run bench_full 600 python bench.py
+grep -h '"metric"' gpurun_out/bench_full.log | cut -c1-400
+run bench_ref 400 python bench.py --impl reference --steps 3 --warmup 1
+grep -h '"metric"\|"impl"' gpurun_out/bench_ref.log | cut -c1-400
