@@ -940,9 +940,6 @@ def evaluate(data):
             if not on_device:
                 vecenv.host_sync()               # outstanding eager copies (their events are not part of the capture)
                 vecenv.graph_mode = True
-                # the observation blocks of the last rows are copied after the graph, beside train() (vector.copy_tail_rows):
-                # default one eighth of the horizon ~ the time the update takes at the bench shape
-                vecenv.host_tail_rows = int(getattr(config, 'host_tail_rows', max(1, vecenv._horizon // 8)))
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 _rollout_loop(data, infos)       # python-side state advances exactly as in an eager rollout
@@ -957,11 +954,7 @@ def evaluate(data):
             data.graph_state = 2
             data.global_step = step0
         with profile.env:
-            if not on_device:
-                vecenv.wait_tail()               # the previous rollout's last observation blocks are still on their way to the host
             data.rollout_graph.replay()
-            if not on_device:
-                vecenv.copy_tail_rows()
         data.global_step += data.graph_steps
         data.graph_replays += 1
         if not on_device:

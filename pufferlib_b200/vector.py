@@ -219,9 +219,6 @@ class B200:
                 # device->host copies run on their own stream, behind the env kernel and beside the policy forward
                 self._copy_stream = torch.cuda.Stream()
                 self._ev_step, self._ev_copy, self._ev_act = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-                self._ev_tail = torch.cuda.Event()
-            self.host_tail_rows = 0      # set by clean_pufferl.evaluate for the captured host rollout
-            self._tail_pending = False
             self._host_pending = False
             self.graph_mode = False
         self.h2d_bytes = 0
@@ -333,19 +330,14 @@ class B200:
                 h, cs = self._host, self._copy_stream
                 self._ev_step.record()
                 cs.wait_event(self._ev_step)
-                # captured host rollout: the observation blocks of the last `host_tail_rows` steps are left to copy_tail_rows(),
-                # which streams them while train() runs (the graph itself has to end with the copy stream joined)
-                defer = self.graph_mode and self._rollout is not None and torch.cuda.is_current_stream_capturing() and \
-                    self._cursor >= self._horizon - self.host_tail_rows
                 with torch.cuda.stream(cs):
-                    if not defer:
-                        h.observations.copy_(obs, non_blocking=True)
+                    h.observations.copy_(obs, non_blocking=True)
                     h.rewards.copy_(rewards, non_blocking=True)
                     h.terminals.copy_(b.terminals, non_blocking=True)
                     h.truncations.copy_(b.truncations, non_blocking=True)
                     self._ev_copy.record(cs)
                 self._host_pending = True
-                self.d2h_bytes += ((0 if defer else h.observations.numel() * h.observations.element_size())
+                self.d2h_bytes += (h.observations.numel() * h.observations.element_size()
                                    + 4 * self.num_agents + 2 * self.num_agents)
                 self._device_view = (obs, rewards, b.terminals, b.truncations, [], self.agent_ids, b.masks)
                 return self.host_sync() if not _device else self._device_view
@@ -376,28 +368,6 @@ class B200:
         self.d2h_bytes += 8 * self.num_agents
         return self._host_np.actions
 
-    def copy_tail_rows(self):
-        """After a replay of the captured host rollout: the observation blocks of its last host_tail_rows steps go to the
-        pinned host array now, on the copy stream, behind the graph -- beside whatever the caller launches next (train()).
-        The next rollout (and any host-side reader) waits for them: wait_tail() / host_sync()."""
-        k = min(self.host_tail_rows, self._horizon)
-        if not (self.graph_mode and k > 0):
-            return
-        x, n, cs = self._rollout, self.num_agents, self._copy_stream
-        cs.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(cs):
-            for t in range(self._horizon - k, self._horizon):
-                self._host.observations.copy_(x.obs[t * n:(t + 1) * n], non_blocking=True)
-            self._ev_tail.record(cs)
-        self._tail_pending = True
-        self.d2h_bytes += k * self._host.observations.numel() * self._host.observations.element_size()
-
-    def wait_tail(self):
-        """Device-side: the caller's stream waits for copy_tail_rows() (before the next rollout overwrites those rows)."""
-        if getattr(self, '_tail_pending', False):
-            torch.cuda.current_stream().wait_event(self._ev_tail)
-            self._tail_pending = False
-
     def join_copies(self):
         """Inside a stream capture: the copy stream's work becomes a predecessor of whatever the caller's stream does next
         (the captured graph then ends only when every host copy has landed)."""
@@ -413,9 +383,6 @@ class B200:
             # thing to wait for (events recorded during a capture cannot be waited on from the host)
             if not torch.cuda.is_current_stream_capturing():
                 torch.cuda.current_stream().synchronize()
-                if getattr(self, '_tail_pending', False):
-                    self._ev_tail.synchronize()
-                    self._tail_pending = False
             self._host_pending = self._act_pending = False
             if actions_only:
                 return None
