@@ -62,8 +62,8 @@ EXP_SO = os.path.join(HERE, 'libpuffer_b200_exp.so')
 
 
 def build_experimental(force=False, verbose=False):
-    """csrc/experimental/*.cu -> libpuffer_b200_exp.so: round-2 groundwork (tcgen05 kernels not yet validated on
-    hardware).  Nothing in the product path loads it; tests/experimental/ holds the hardware checks."""
+    """csrc/experimental/*.cu -> libpuffer_b200_exp.so: the tcgen05 descriptor probe (umma_probe.cu) behind the layout facts
+    DESIGN.md section 7 lists.  Nothing in the product path loads it; tests/experimental/ holds the scripts that drive it."""
     srcs = sorted(glob.glob(os.path.join(CSRC, 'experimental', '*.cu')))
     deps = srcs + glob.glob(os.path.join(CSRC, '*.cuh'))
     if not force and os.path.exists(EXP_SO) and all(os.path.getmtime(EXP_SO) >= os.path.getmtime(d) for d in deps):
