@@ -285,6 +285,19 @@ __device__ __forceinline__ void ro_write_obs(uint8_t* tile, int r, int px, int b
     }
 }
 
+// mma.sync m16n8k8 TF32 (fp32 accumulate): a0 (g, t)  a1 (g + 8, t)  a2 (g, t + 4)  a3 (g + 8, t + 4);  b0 (k = t, n = g)  b1 (k = t + 4, n = g);
+// c0 c1 (g, 2t + {0,1})  c2 c3 (g + 8, 2t + {0,1})      [g = lane >> 2, t = lane & 3]
+__device__ __forceinline__ void ro_mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ro_to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
 template <bool DBG>      // DBG: step-0 dumps for the validation hook (pb_rollout_debug_buffers); compiled out of the product path
 __global__ void __launch_bounds__(RO_THREADS, 1)
 k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_constant__ CUtensorMap map_carry,
@@ -382,13 +395,27 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
         fence_proxy_async_smem();
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tile_full[0])) : "memory");
 
+        // head products on mma.sync fragments (like k_mlp_update_xt and k_policy_mlp_sample): out[32 rows][8] = relu(h) . W_heads^T
+        // with the warp's relu(h) staged K-major ([hidden unit][row], 16-byte pieces XORed with unit & 7) in the observation
+        // tile that is NOT in flight, W_heads fragments resident in registers (k = t + 4j <-> hidden unit 8kb + 2t + j), and the
+        // m index permuted (m = g + 8h of block mb <-> row 4g + 2mb + h) so that an A fragment is one LDS.128.  A thread-per-row
+        // FFMA formulation (640 FFMA + constant loads per step at one warp per scheduler) was 25 % of the step.
+        const int g = lane >> 2, tq = lane & 3;
+        uint32_t hb[16][2];
+#pragma unroll
+        for (int kb = 0; kb < 16; ++kb) {
+            hb[kb][0] = ro_to_tf32(c_ro_wh[g * 128 + 8 * kb + 2 * tq]);
+            hb[kb][1] = ro_to_tf32(c_ro_wh[g * 128 + 8 * kb + 2 * tq + 1]);
+        }
+        const float bh_row[8] = {c_ro_bh[0], c_ro_bh[1], c_ro_bh[2], c_ro_bh[3], c_ro_bh[4], c_ro_bh[5], c_ro_bh[6], c_ro_bh[7]};
+
         for (int t = 0; t < H; ++t) {
             // ---- policy on obs(t): hidden row from TMEM -> heads -> sample
             mbar_wait(h_full, (uint32_t)(t & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float out[8];
-#pragma unroll
-            for (int a = 0; a < 8; ++a) out[a] = c_ro_bh[a];
+            // (the MMA thread waited for the tensor store of obs(t-1) before it committed h_full(t): the other tile is free)
+            uint8_t* blk = smem + RO_SMEM_X + ((t + 1) & 1) * RO_TILE_BYTES + warp * RO_KBLK_BYTES;   // [128 hidden units][32 rows]
+            uint8_t* st_row = blk + ((lane & 3) << 2);
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -398,11 +425,38 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
                 for (int k = 0; k < 32; ++k) {
                     const float rh = fmaxf(v[k] + c_ro_benc[32 * c + k], 0.f);
                     if (DBG && p.dbg_hidden && t == 0) p.dbg_hidden[(int64_t)e * 128 + 32 * c + k] = rh;
-#pragma unroll
-                    for (int a = 0; a < RO_HEADS; ++a) out[a] = fmaf(rh, c_ro_wh[a * 128 + 32 * c + k], out[a]);   // rows >= 5: zero padding
+                    *reinterpret_cast<float*>(st_row + (32 * c + k) * 128 + ((((lane >> 2) ^ (k & 7))) << 4)) = rh;
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            float out[8];
+            {
+                float hp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                const uint8_t* a_lo = blk + (2 * tq) * 128 + ((g ^ (2 * tq)) << 4);          // hidden unit 8kb + 2t, rows 4g..4g+3
+                const uint8_t* a_hi = blk + (2 * tq + 1) * 128 + ((g ^ (2 * tq + 1)) << 4);  // hidden unit 8kb + 2t + 1
+#pragma unroll
+                for (int kb = 0; kb < 16; ++kb) {
+                    const float4 lo = *reinterpret_cast<const float4*>(a_lo + kb * 1024);
+                    const float4 hi = *reinterpret_cast<const float4*>(a_hi + kb * 1024);
+                    ro_mma_tf32(hp[0], __float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(hi.x), __float_as_uint(hi.y), hb[kb][0], hb[kb][1]);
+                    ro_mma_tf32(hp[1], __float_as_uint(lo.z), __float_as_uint(lo.w), __float_as_uint(hi.z), __float_as_uint(hi.w), hb[kb][0], hb[kb][1]);
+                }
+                __syncwarp();        // all fragment loads done: the head of the block becomes the [32 rows][10] redistribution scratch
+                float* scr = reinterpret_cast<float*>(blk);
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    *reinterpret_cast<float2*>(scr + (4 * g + 2 * mb) * 10 + 2 * tq) = make_float2(hp[mb][0], hp[mb][1]);
+                    *reinterpret_cast<float2*>(scr + (4 * g + 2 * mb + 1) * 10 + 2 * tq) = make_float2(hp[mb][2], hp[mb][3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2) {
+                    const float2 o2 = *reinterpret_cast<const float2*>(scr + lane * 10 + 2 * a2);
+                    out[2 * a2] = o2.x + bh_row[2 * a2];
+                    out[2 * a2 + 1] = o2.y + bh_row[2 * a2 + 1];
+                }
+            }
             if (DBG && p.dbg_out && t == 0)
 #pragma unroll
                 for (int a = 0; a < 8; ++a) p.dbg_out[(int64_t)e * 8 + a] = out[a];
@@ -489,6 +543,7 @@ k_breakout_rollout(const __grid_constant__ CUtensorMap map_obs, const __grid_con
                 p.out_terminals[e] = terminal ? 1 : 0;
             }
             const int s1 = (t + 1) & 1;
+            asm volatile("bar.sync 1, 128;" ::: "memory");     // every env warp is done with its relu(h) block in that tile
             ro_write_obs(smem + RO_SMEM_X + s1 * RO_TILE_BYTES, r, px, bx, by, vx, vy, lives, in_play, bricks);
             fence_proxy_async_smem();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tile_full[s1])) : "memory");

@@ -89,7 +89,10 @@ def test_fused_rollout_replays_through_oracle(n, h, kwargs):
         w_cat, b_cat = (t.detach().double() for t in model.head_matrix())
         x = exp.obs.double()
         hid = torch.relu(x @ w_t.t() + b_enc)
-        out = hid @ w_cat.t() + b_cat
+        # the head products run on mma.sync: relu(h) truncated to TF32 by the tensor core, W_heads rounded to TF32 (cvt.rna)
+        hid_t = (hid.float().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        w_cat_r = ((w_cat.float().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).double()
+        out = hid_t @ w_cat_r.t() + b_cat
         logits, value = out[:, :n_act], out[:, n_act]
         norm = logits - logits.logsumexp(-1, keepdim=True)
         lp = norm.gather(-1, exp.actions.view(-1, 1)).squeeze(-1)
@@ -101,7 +104,7 @@ def test_fused_rollout_replays_through_oracle(n, h, kwargs):
             eo = (dbg_o[:, :5].double() - out[:n, :5]).abs()
             print(f'[diag] head outputs step 0: max err per head {[f"{float(eo[:, a].max()):.2e}" for a in range(5)]}', flush=True)
             print(f'[diag] stored values vs kernel out[4] at step 0: {float((exp.values[:n].double() - dbg_o[:, 4].double()).abs().max()):.3e}', flush=True)
-            o_from_h = dbg_h.double() @ w_cat.t() + b_cat
+            o_from_h = (dbg_h.view(torch.int32) & ~0x1FFF).view(torch.float32).double() @ w_cat_r.t() + b_cat
             print(f'[diag] heads recomputed from the kernel hidden vs kernel out: {float((dbg_o[:, :5].double() - o_from_h[:, :5]).abs().max()):.3e}', flush=True)
         dv = float((exp.values.double() - value).abs().max())
         if dv >= 2e-4:       # diagnostics: which reference is the kernel closest to?
