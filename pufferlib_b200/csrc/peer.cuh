@@ -93,30 +93,41 @@ __device__ __forceinline__ void pb_peer_allreduce_slice(const pb_peer_comm& c, f
     const int64_t lo = (int64_t)b * chunk, hi = lo + chunk < n ? lo + chunk : n;
     const int64_t slot_off = PB_PEER_HEADER_BYTES / 4 + (int64_t)(e & 1) * c.capacity;
     float* mine = reinterpret_cast<float*>(c.base[c.rank]) + slot_off;
-    for (int64_t i = lo + tid; i < hi; i += nt) mine[i] = flat[i];
-    __threadfence_system();
+    // 128-bit accesses where the layout allows (slices start at multiples of 4 floats): one peer load per thread and rank,
+    // all in flight at once -- the exchange is a handful of NVLink round trips, not bandwidth
+    const bool vec = (c.capacity & 3) == 0 && (reinterpret_cast<uintptr_t>(flat) & 15) == 0;
+    const int64_t hi4 = vec ? lo + ((hi - lo) & ~(int64_t)3) : lo;          // [lo, hi4) in float4 steps, [hi4, hi) scalar
+    for (int64_t i = lo + 4 * tid; i < hi4; i += 4 * nt)
+        *reinterpret_cast<float4*>(mine + i) = *reinterpret_cast<const float4*>(flat + i);
+    for (int64_t i = hi4 + tid; i < hi; i += nt) mine[i] = flat[i];
     __syncthreads();
     if (tid < c.world) {
+        __threadfence_system();      // (cumulative: the CTA barrier ordered every thread's slot writes before this thread)
         uint64_t* flag = reinterpret_cast<uint64_t*>(reinterpret_cast<char*>(c.base[tid]) + 128 * c.rank + 8 * b);
         pb_st_release_sys_u64(flag, e);
         const uint64_t* theirs = reinterpret_cast<const uint64_t*>(reinterpret_cast<const char*>(c.base[c.rank]) + 128 * tid + 8 * b);
         const long long t0 = clock64();
         while (pb_ld_acquire_sys_u64(theirs) < e) {
             if (clock64() - t0 > 20000000000ll) __trap();
-            __nanosleep(32);
         }
     }
     __syncthreads();
     double sq = 0.0;
-    for (int64_t i = lo + tid; i < hi; i += nt) {
-        float v[PB_PEER_MAX_RANKS];
+    for (int64_t i = lo + 4 * tid; i < hi4; i += 4 * nt) {
+        float4 v[PB_PEER_MAX_RANKS];
 #pragma unroll
         for (int r = 0; r < PB_PEER_MAX_RANKS; ++r)
-            if (r < c.world) v[r] = pb_ld_relaxed_sys_f32(reinterpret_cast<const float*>(c.base[r]) + slot_off + i);
-        float s = 0.f;
+            if (r < c.world) v[r] = pb_ld_relaxed_sys_f32x4(reinterpret_cast<const float*>(c.base[r]) + slot_off + i);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < PB_PEER_MAX_RANKS; ++r)      // rank order: the same bits on every rank
-            if (r < c.world) s += v[r];
+            if (r < c.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+        *reinterpret_cast<float4*>(flat + i) = s;
+        sq += ((double)s.x * (double)s.x + (double)s.y * (double)s.y) + ((double)s.z * (double)s.z + (double)s.w * (double)s.w);
+    }
+    for (int64_t i = hi4 + tid; i < hi; i += nt) {
+        float s = 0.f;
+        for (int r = 0; r < c.world; ++r) s += pb_ld_relaxed_sys_f32(reinterpret_cast<const float*>(c.base[r]) + slot_off + i);
         flat[i] = s;
         sq += (double)s * (double)s;
     }
