@@ -367,6 +367,12 @@ int pb_clip_adam_parts(const pb_adam_tensor* tensors, int32_t n_tensors, float m
                        const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
                        const double* sumsq_parts, int32_t n_parts, unsigned long long* peer_epoch, const pb_head_pack* pack,
                        void* stream);
+/* pb_peer_allreduce_parts + pb_clip_adam_parts as ONE kernel (pb_peer_slices() CTAs with a grid barrier between the exchange
+ * and the update): the multi-GPU optimizer step of the captured update graph.  sumsq_scratch: pb_peer_slices() doubles. */
+int pb_clip_adam_peer_parts(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
+                            const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
+                            const pb_peer_comm* comm, float* grad_flat, int64_t grad_flat_numel, double* sumsq_scratch,
+                            const pb_head_pack* pack, void* stream);
 int pb_clip_adam_peer(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale, float lr,
                       const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
                       const pb_peer_comm* comm, float* grad_flat, int64_t grad_flat_numel, void* stream);

@@ -420,21 +420,21 @@ class _DefaultMLPUpdate:
         if self.used_fused and in_kernel and (self.world == 1 or self.peer is not None) and bool(getattr(config, 'adam_parts', True)):
             # the fused update's reduce step left the gradient's sum of squares as partial sums: multi-CTA clip + Adam without a
             # norm pass; several ranks: sliced peer all-reduce first, which leaves its own partial sums of squares
-            parts = C.c_void_p(self.fused_ws.data_ptr() + lib.pb_mlp_update_sumsq_offset())
-            n_parts, epoch = lib.pb_mlp_update_sumsq_parts(), None
-            if self.peer is not None:
-                if self.peer_parts is None:
-                    self.peer_parts = torch.zeros(lib.pb_peer_slices(), dtype=torch.float64, device=self.gflat.device)
-                _native.check(lib.pb_peer_allreduce_parts(C.byref(self.peer.struct), _native.ptr(self.gflat), self.gflat.numel(),
-                                                          _native.ptr(self.peer_parts), _native.stream_ptr()))
-                parts, n_parts, epoch = _native.ptr(self.peer_parts), lib.pb_peer_slices(), _native.ptr(self.peer.epoch)
             m = self.model
             if self.head_pack is None:      # the head matrix is rebuilt by the last CTA of the optimizer kernel
                 self.head_pack = _native.HeadPack(m.decoder.weight.data_ptr(), m.decoder.bias.data_ptr(), m.value_head.weight.data_ptr(),
                                                   m.value_head.bias.data_ptr(), self.w_cat.data_ptr(), self.b_cat.data_ptr(),
                                                   self.n_act, self.hid)
-            _native.check(lib.pb_clip_adam_parts(self.tensors, len(self.tensors), *hyper, parts, n_parts, epoch,
-                                                 C.byref(self.head_pack), _native.stream_ptr()))
+            if self.peer is not None:       # exchange + clip + Adam: one kernel
+                if self.peer_parts is None:
+                    self.peer_parts = torch.zeros(lib.pb_peer_slices(), dtype=torch.float64, device=self.gflat.device)
+                _native.check(lib.pb_clip_adam_peer_parts(
+                    self.tensors, len(self.tensors), *hyper, C.byref(self.peer.struct), _native.ptr(self.gflat), self.gflat.numel(),
+                    _native.ptr(self.peer_parts), C.byref(self.head_pack), _native.stream_ptr()))
+            else:
+                parts = C.c_void_p(self.fused_ws.data_ptr() + lib.pb_mlp_update_sumsq_offset())
+                _native.check(lib.pb_clip_adam_parts(self.tensors, len(self.tensors), *hyper, parts, lib.pb_mlp_update_sumsq_parts(),
+                                                     None, C.byref(self.head_pack), _native.stream_ptr()))
             return
         else:
             _native.check(lib.pb_clip_adam_peer(

@@ -100,19 +100,47 @@ __global__ void __launch_bounds__(CA_THREADS) k_clip_adam(AdamArgs a) {
 // Multi-CTA form for callers that already hold the gradient's sum of squares as partial sums (k_update_reduce of the fused
 // update, or the sliced peer all-reduce): no norm pass, every CTA sums the partials in the same fixed order, then updates
 // its share of the elements.  The step counters are advanced by the LAST CTA to finish (all others have read them).
-constexpr int CAP_THREADS = 256, CAP_BLOCKS = 32;
+constexpr int CAP_BLOCKS = 32;
 __device__ unsigned int g_cap_ticket = 0;
 
+// PEER: the sliced NVLink all-reduce of the flat gradient (peer.cuh) runs first in the same kernel -- one CTA per slice, a grid
+// barrier among the PB_PEER_SLICES co-resident CTAs, then clip + Adam: one launch per optimizer step for any world size.
+__device__ unsigned int g_gb_count = 0;
+__device__ volatile unsigned int g_gb_gen = 0;
+
+template <int CAP_THREADS, bool PEER>
 __global__ void __launch_bounds__(CAP_THREADS) k_clip_adam_parts(AdamArgs a, const double* __restrict__ parts, int n_parts,
-                                                                unsigned long long* peer_epoch, pb_head_pack pack) {
+                                                                unsigned long long* peer_epoch, pb_head_pack pack,
+                                                                double* peer_parts) {
     __shared__ int s_last;
     __shared__ double s_red[CAP_THREADS / 32];
+    if (PEER) {
+        pb_peer_allreduce_slice(a.peer, a.flat, a.flat_n, peer_parts);       // flat slice summed over the ranks + its sum of squares
+        __syncthreads();
+        if (threadIdx.x == 0) {          // grid barrier: every slice and every partial sum is in global memory
+            __threadfence();
+            const unsigned int gen = g_gb_gen;
+            if (atomicAdd(&g_gb_count, 1u) == gridDim.x - 1) {
+                g_gb_count = 0;
+                __threadfence();
+                g_gb_gen = gen + 1;
+            } else {
+                const long long t0 = clock64();
+                while (g_gb_gen == gen)
+                    if (clock64() - t0 > 20000000000ll) __trap();
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        parts = peer_parts;
+        n_parts = (int)gridDim.x;
+    }
     __shared__ float s_coef;
     __shared__ float s_step_size[CA_MAX_TENSORS], s_bc2_sqrt[CA_MAX_TENSORS], s_new_step[CA_MAX_TENSORS];
     __shared__ int64_t s_first[CA_MAX_TENSORS + 1];
     const int tid = threadIdx.x;
     double d = 0.0;
-    for (int i = tid; i < n_parts; i += CAP_THREADS) d += parts[i];          // fixed assignment and order: same bits in every CTA
+    for (int i = tid; i < n_parts; i += CAP_THREADS) d += PEER ? ((volatile const double*)parts)[i] : parts[i];   // fixed assignment and order: same bits in every CTA
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
     if ((tid & 31) == 0) s_red[tid >> 5] = d;
@@ -148,7 +176,9 @@ __global__ void __launch_bounds__(CAP_THREADS) k_clip_adam_parts(AdamArgs a, con
         int k = 0;
         while (j >= s_first[k + 1]) ++k;
         const int64_t i = j - s_first[k];
-        const float x = a.t[k].grad[i] * coef;
+        // PEER: the summed gradient was written by other CTAs of this launch: read it from L2 (an L1 line fetched while copying
+        // this CTA's own slice may hold the neighbouring slice's pre-exchange values)
+        const float x = (PEER ? __ldcg(a.t[k].grad + i) : a.t[k].grad[i]) * coef;
         float* m = a.t[k].exp_avg;
         float* v = a.t[k].exp_avg_sq;
         const float mi = m[i] + w1 * (x - m[i]);                  // lerp(exp_avg, grad, 1 - beta1)
@@ -287,7 +317,55 @@ extern "C" int pb_clip_adam_parts(const pb_adam_tensor* tensors, int32_t n_tenso
                    PB_ERR_INVALID, "pb_clip_adam_parts: bad head-pack arguments");
         hp = *pack;
     }
-    k_clip_adam_parts<<<CAP_BLOCKS, CAP_THREADS, 0, (cudaStream_t)stream>>>(a, sumsq_parts, n_parts, peer_epoch, hp);
+    k_clip_adam_parts<256, false><<<CAP_BLOCKS, 256, 0, (cudaStream_t)stream>>>(a, sumsq_parts, n_parts, peer_epoch, hp, nullptr);
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+}
+
+// The same with the gradient all-reduce over NVLink peer memory in front, in ONE kernel (pb_peer_slices() CTAs): replaces the
+// pair pb_peer_allreduce_parts + pb_clip_adam_parts.  sumsq_scratch: pb_peer_slices() doubles of device memory.
+extern "C" int pb_clip_adam_peer_parts(const pb_adam_tensor* tensors, int32_t n_tensors, float max_grad_norm, float grad_scale,
+                                       float lr, const float* lr_dev, float beta1, float beta2, float eps, float* total_norm_out,
+                                       const pb_peer_comm* comm, float* grad_flat, int64_t grad_flat_numel, double* sumsq_scratch,
+                                       const pb_head_pack* pack, void* stream) {
+    PB_REQUIRE(tensors && n_tensors >= 1 && n_tensors <= CA_MAX_TENSORS && comm && grad_flat && sumsq_scratch, PB_ERR_INVALID,
+               "pb_clip_adam_peer_parts: bad arguments");
+    PB_REQUIRE(comm->world >= 2 && comm->world <= PB_PEER_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world && comm->epoch &&
+                   grad_flat_numel >= 1 && grad_flat_numel <= comm->capacity,
+               PB_ERR_INVALID, "pb_clip_adam_peer_parts: bad communicator or flat gradient buffer");
+    for (int r = 0; r < comm->world; ++r) PB_REQUIRE(comm->base[r], PB_ERR_INVALID, "pb_clip_adam_peer_parts: peer %d not mapped", r);
+    AdamArgs a{};
+    for (int k = 0; k < n_tensors; ++k) {
+        const pb_adam_tensor& t = tensors[k];
+        PB_REQUIRE(t.param && t.exp_avg && t.exp_avg_sq && t.step && t.grad && t.numel >= 1, PB_ERR_INVALID,
+                   "pb_clip_adam_peer_parts: tensor %d has a null pointer or no elements", k);
+        PB_REQUIRE(t.grad >= grad_flat && t.grad + t.numel <= grad_flat + grad_flat_numel, PB_ERR_INVALID,
+                   "pb_clip_adam_peer_parts: gradient %d lies outside the flat buffer", k);
+        a.t[k] = t;
+    }
+    PB_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f && grad_scale > 0.f,
+               PB_ERR_INVALID, "pb_clip_adam_peer_parts: bad hyper-parameters");
+    a.n = n_tensors;
+    a.max_norm = max_grad_norm;
+    a.grad_scale = grad_scale;
+    a.lr = lr;
+    a.lr_dev = lr_dev;
+    a.beta1 = beta1;
+    a.beta2 = beta2;
+    a.eps = eps;
+    a.total_norm_out = total_norm_out;
+    a.peer = *comm;
+    a.flat = grad_flat;
+    a.flat_n = grad_flat_numel;
+    pb_head_pack hp{};
+    if (pack) {
+        PB_REQUIRE(pack->w_dec && pack->b_dec && pack->w_val && pack->b_val && pack->w_cat && pack->b_cat && pack->n_act >= 1 &&
+                       pack->n_act <= 7 && pack->hid >= 1,
+                   PB_ERR_INVALID, "pb_clip_adam_peer_parts: bad head-pack arguments");
+        hp = *pack;
+    }
+    k_clip_adam_parts<512, true><<<PB_PEER_SLICES, 512, 0, (cudaStream_t)stream>>>(
+        a, nullptr, 0, reinterpret_cast<unsigned long long*>(comm->epoch), hp, sumsq_scratch);
     PB_LAUNCH_CHECK();
     return PB_OK;
 }
