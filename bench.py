@@ -503,7 +503,7 @@ def run_b200(args):
             'config': {'workload': f'{args.env} num_envs={n}/GPU horizon={h} MLP hidden={args.hidden} '
                                    f'(BASELINE.json configs[1]; x{world} ranks = configs[4])',
                        'global_batch': world * n * h, 'minibatch_size': n * h // args.minibatches, 'update_epochs': args.epochs,
-                       'bptt_horizon': 16, 'parallelism': f'dp{world} (env shards + 1 NCCL grad all-reduce/step)',
+                       'bptt_horizon': 16, 'parallelism': f'dp{world} (env shards; one 68.6 KB gradient exchange per optimizer step over NVLink peer memory, inside the update graph)',
                        'l2': 'inputs larger than L2 (1 GiB rollout rotates; no flush needed)',
                        'cuda_graph_rollout': not args.no_graph,
                        'cuda_graph_train': 'whole' if data.train_graph_state == 2 else ('segments' if data.train_segments else False), 'zero_copy_minibatches': getattr(data.experience, '_slabs', None) is not None, 'note': data.msg},
