@@ -350,7 +350,8 @@ int pb_peer_allreduce(const pb_peer_comm* comm, float* flat, int64_t n, void* st
 /* Multi-CTA forms (the single-CTA calls above stay for callers without partial sums of squares): pb_peer_allreduce_parts
  * sums flat[0..n) over the ranks with pb_peer_slices() CTAs and writes that many partial sums of squares of the result;
  * pb_clip_adam_parts is pb_clip_adam with the norm taken from n_parts partial sums of squares of the summed, unscaled
- * gradient; it advances *peer_epoch (nullable: the communicator's counter) for the all-reduce that preceded it. */
+ * gradient; it advances *peer_epoch (nullable: the communicator's counter) for the all-reduce that preceded it.  One optimizer
+ * step may be in flight per device at a time (device-wide ticket counters). */
 int pb_peer_allreduce_parts(const pb_peer_comm* comm, float* flat, int64_t n, double* sumsq_parts, void* stream);
 int32_t pb_peer_slices(void);
 typedef struct pb_head_pack {   /* optional tail of pb_clip_adam_parts: pb_pack_heads (without the encoder copy) on the updated parameters */

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(CA_THREADS) k_clip_adam(AdamArgs a) {
 // update, or the sliced peer all-reduce): no norm pass, every CTA sums the partials in the same fixed order, then updates
 // its share of the elements.  The step counters are advanced by the LAST CTA to finish (all others have read them).
 constexpr int CAP_BLOCKS = 32;
+// (one optimizer step in flight per device: the counters below are module-wide, like the trainer that owns the stream)
 __device__ unsigned int g_cap_ticket = 0;
 
 // PEER: the sliced NVLink all-reduce of the flat gradient (peer.cuh) runs first in the same kernel -- one CTA per slice, a grid
