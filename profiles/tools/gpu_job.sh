@@ -1,7 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
 run() { name=$1; t=$2; shift 2; ( timeout $t "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?" >> gpurun_out/$name.log ); echo "== $name: $(tail -1 gpurun_out/$name.log)"; }
-run t_all 900 python -m pytest tests -m gpu -x -q
-tail -4 gpurun_out/t_all.log
-run smoke 200 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')"
-tail -2 gpurun_out/smoke.log
+run smoke 200 python -c "import __graft_entry__ as g; g.smoke()"
+tail -4 gpurun_out/smoke.log
